@@ -1,0 +1,179 @@
+// Host-side launcher for the tcgen05 implicit-GEMM convolution: builds the TMA tensor maps for the
+// activation tensor and the packed weights, picks the pixel box / pipeline depth, launches.
+#include "conv_tc.cuh"
+#include "launch.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace biu {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+static int pow2_ceil(int v) { return 1 << ilog2(v); }
+
+// Choose a pixel box of exactly 128 pixels: grow along w, then h, then d, then batch.
+void choose_box(int W, int H, int D, int B, int* lbw, int* lbh, int* lbd, int* lbb) {
+  int rem = 7;
+  int lw = ilog2(pow2_ceil(W)); if (lw > rem) lw = rem; rem -= lw;
+  // keep the box at most 32 wide when there are rows to stack: better halo locality in L2
+  if (lw > 5 && H > 1) { rem += lw - 5; lw = 5; }
+  int lh = ilog2(pow2_ceil(H)); if (lh > rem) lh = rem; rem -= lh;
+  int ld = ilog2(pow2_ceil(D)); if (ld > rem) ld = rem; rem -= ld;
+  int lb = rem;  // whatever is left goes to the batch dim (OOB images are zero-filled and masked)
+  *lbw = lw; *lbh = lh; *lbd = ld; *lbb = lb;
+}
+
+static int encode_act_map(CUtensorMap* tm, const void* base, int esz, int C, int W, int H, int D, int B, int ctot,
+                          int ck, int bw, int bh, int bd, int bb) {
+  EncodeTiledFn enc = get_encode_fn();
+  BIU_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)ctot * esz, (cuuint64_t)W * ctot * esz, (cuuint64_t)H * W * ctot * esz,
+                           (cuuint64_t)D * H * W * ctot * esz};
+  cuuint32_t box[5] = {(cuuint32_t)ck, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bb};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const int rb = ck * esz;
+  CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(tm, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BIU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with %d (C=%d W=%d H=%d D=%d B=%d ctot=%d ck=%d)",
+              (int)r, C, W, H, D, B, ctot, ck);
+  return 0;
+}
+
+static int encode_wgt_map(CUtensorMap* tm, const void* base, int esz, int cin, int ntotal, int taps, int ck,
+                          int n_blk) {
+  EncodeTiledFn enc = get_encode_fn();
+  BIU_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)ntotal, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)cin * esz, (cuuint64_t)ntotal * cin * esz};
+  cuuint32_t box[3] = {(cuuint32_t)ck, (cuuint32_t)n_blk, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const int rb = ck * esz;
+  CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                    : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(tm, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BIU_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with %d (cin=%d n=%d taps=%d ck=%d nblk=%d)",
+              (int)r, cin, ntotal, taps, ck, n_blk);
+  return 0;
+}
+
+int pick_ck(int cin, int esz) {
+  const int cands[3] = {128 / esz, 64 / esz, 32 / esz};
+  for (int i = 0; i < 3; ++i)
+    if (cin % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+bool conv_tc_supported(const ConvTcArgs& a) {
+  if (a.esz != 2 && a.esz != 4) return false;
+  if (pick_ck(a.cin, a.esz) == 0) return false;
+  if (a.n_total % 16 != 0) return false;
+  if (a.in_ctot % (16 / a.esz) != 0 || a.in_coff % (16 / a.esz) != 0) return false;
+  if (a.mode != EPI_HEAD && (a.out_ctot % (16 / a.esz) != 0 || a.out_coff % (16 / a.esz) != 0)) return false;
+  if (a.mode == EPI_UP && a.up_cout % 16 != 0) return false;
+  if (a.mode == EPI_HEAD && (a.n_total > 256 || a.head_n > kMaxHead)) return false;
+  return true;
+}
+
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
+  BIU_REQUIRE(conv_tc_supported(a), "conv_tc: unsupported configuration (cin=%d n=%d esz=%d mode=%d)", a.cin,
+              a.n_total, a.esz, a.mode);
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
+  choose_box(a.W, a.H, a.D, a.B, &p.lbw, &p.lbh, &p.lbd, &p.lbb);
+  p.tiles_w = ceil_div(a.W, 1 << p.lbw);
+  p.tiles_h = ceil_div(a.H, 1 << p.lbh);
+  p.tiles_d = ceil_div(a.D, 1 << p.lbd);
+  p.tiles_b = ceil_div(a.B, 1 << p.lbb);
+  p.kw = a.kw; p.kh = a.kh; p.kd = a.kd;
+  p.ck = pick_ck(a.cin, a.esz);
+  p.cin_chunks = a.cin / p.ck;
+  p.row_bytes = p.ck * a.esz;
+  // N per CTA: whole N when it fits one accumulator, otherwise the largest divisor <= 256
+  int n_blk = a.n_total;
+  if (n_blk > 256) {
+    n_blk = 256;
+    while (a.n_total % n_blk != 0) n_blk -= 16;
+  }
+  if (a.mode == EPI_UP && n_blk > a.up_cout && n_blk % a.up_cout != 0) n_blk = a.up_cout;
+  p.n_blk = n_blk;
+  p.mode = a.mode;
+  p.slope = a.slope;
+  p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out; p.out_ctot = a.out_ctot; p.out_coff = a.out_coff;
+  p.up_cout = a.up_cout; p.up_dims = a.up_dims;
+  p.head_n = a.head_n; p.head_w = a.head_w; p.head_b = a.head_b;
+  for (int i = 0; i < kMaxHead; ++i) p.head_act[i] = a.head_act[i];
+  p.out_val = a.out_val; p.out_u8 = a.out_u8;
+
+  const int a_bytes = 128 * p.row_bytes;
+  const int b_bytes = (n_blk * p.row_bytes + 1023) & ~1023;
+  const int stage_bytes = a_bytes + b_bytes;
+  const int num_kb = p.cin_chunks * a.kw * a.kh * a.kd;
+  int stages = (a.smem_budget > 0 ? a.smem_budget : 96 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > num_kb) stages = num_kb;
+  if (stages < 2) stages = num_kb < 2 ? 1 : 2;
+  p.stages = stages;
+  const int smem = stages * stage_bytes + 1024;
+
+  CUtensorMap tmA, tmB;
+  const char* in_base = reinterpret_cast<const char*>(a.in) + (size_t)a.in_coff * a.esz;
+  if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, p.ck, 1 << p.lbw,
+                              1 << p.lbh, 1 << p.lbd, 1 << p.lbb))
+    return rc;
+  if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, a.kw * a.kh * a.kd, p.ck, n_blk)) return rc;
+
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_d * p.tiles_b, a.n_total / n_blk);
+  if (a.esz == 2) {
+    static int max_set = 0;
+    if (smem > max_set) {
+      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      max_set = smem;
+    }
+    conv_tc_kernel<2><<<grid, 192, smem, stream>>>(tmA, tmB, p);
+  } else {
+    static int max_set = 0;
+    if (smem > max_set) {
+      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      max_set = smem;
+    }
+    conv_tc_kernel<4><<<grid, 192, smem, stream>>>(tmA, tmB, p);
+  }
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int read_device_fault(unsigned int* out) {
+  BIU_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_device_fault, sizeof(unsigned int)));
+  return 0;
+}
+
+}  // namespace biu

@@ -1,0 +1,395 @@
+// CUDA-core kernels of the network: first layer (1..4 input channels), 2x pooling / nearest resampling,
+// standalone 1x1 head, and a shared-memory-tiled fp32 direct convolution / transposed convolution used for the
+// exact-fp32 mode and for channel counts the tensor-core kernel cannot take. All NHWC / NDHWC.
+#include "common.cuh"
+#include "launch.h"
+
+namespace biu {
+
+template <typename T> __device__ __forceinline__ float ld_act(const T* p);
+template <> __device__ __forceinline__ float ld_act<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+template <typename T> __device__ __forceinline__ void st_act(T* p, float v, int round_tf32);
+template <> __device__ __forceinline__ void st_act<float>(float* p, float v, int round_tf32) {
+  *p = round_tf32 ? to_tf32(v) : v;
+}
+template <> __device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16* p, float v, int) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// First block: Conv(k=3,pad=1) on a planar few-channel input + folded BN + LeakyReLU (unet/unet.py:20,54-60;
+// unet3d/unet3d.py:24). u8 tiles are converted as float32(u8)/255 (unet/predict.py:192). One thread per
+// (pixel, 8 output channels): 16-byte bf16 stores; weights staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <typename TIN, typename TOUT>
+__global__ void __launch_bounds__(256) first_conv_kernel(FirstConvArgs a) {
+  extern __shared__ float sw[];  // [taps*cin][cout_pad] then scale[cout_pad], shift[cout_pad]
+  const int taps = 9 * a.kd;
+  const int kk = taps * a.cin;
+  float* s_scale = sw + kk * a.cout_pad;
+  float* s_shift = s_scale + a.cout_pad;
+  for (int i = threadIdx.x; i < kk * a.cout_pad; i += blockDim.x) {
+    const int co = i % a.cout_pad, k = i / a.cout_pad;
+    sw[i] = co < a.cout ? a.wgt[k * a.cout + co] : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.cout_pad; i += blockDim.x) {
+    s_scale[i] = i < a.cout ? a.scale[i] : 0.f;
+    s_shift[i] = i < a.cout ? a.shift[i] : 0.f;
+  }
+  __syncthreads();
+  const int groups = a.cout_pad / 8;
+  const long long npix = (long long)a.B * a.D * a.H * a.W;
+  const long long plane = (long long)a.D * a.H * a.W;
+  const TIN* in = reinterpret_cast<const TIN*>(a.in);
+  TOUT* out = reinterpret_cast<TOUT*>(a.out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < npix * groups;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const long long pix = idx / groups;
+    long long r = pix;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int z = (int)(r % a.D); r /= a.D;
+    const int b = (int)r;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int tap = 0;
+    for (int dz = 0; dz < a.kd; ++dz) {
+      const int zz = z + dz - (a.kd >> 1);
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y + dy - 1;
+        for (int dx = 0; dx < 3; ++dx, ++tap) {
+          const int xx = x + dx - 1;
+          if (zz < 0 || zz >= a.D || yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) continue;
+          for (int ci = 0; ci < a.cin; ++ci) {
+            const long long off = ((long long)b * a.cin + ci) * plane + ((long long)zz * a.H + yy) * a.W + xx;
+            float v;
+            if (sizeof(TIN) == 1) v = __fdiv_rn((float)in[off], 255.0f); else v = (float)in[off];
+            const float* w = sw + (tap * a.cin + ci) * a.cout_pad + g * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, w[j], acc[j]);
+          }
+        }
+      }
+    }
+    TOUT* o = out + pix * a.out_ctot + a.out_coff + g * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(acc[j], s_scale[g * 8 + j], s_shift[g * 8 + j]);
+      t = t > 0.f ? t : t * a.slope;
+      st_act<TOUT>(o + j, t, a.round_tf32);
+    }
+  }
+}
+
+int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
+  BIU_REQUIRE(a.cout_pad % 8 == 0 && a.cout_pad >= a.cout, "first_conv: cout_pad must be a multiple of 8");
+  BIU_REQUIRE(a.cin >= 1 && a.cin <= 16, "first_conv: 1..16 input channels supported (got %d)", a.cin);
+  const int taps = 9 * a.kd;
+  const size_t smem = ((size_t)taps * a.cin * a.cout_pad + 2 * a.cout_pad) * sizeof(float);
+  BIU_REQUIRE(smem <= 200 * 1024, "first_conv: weights do not fit shared memory");
+  const long long work = (long long)a.B * a.D * a.H * a.W * (a.cout_pad / 8);
+  long long blocks = ceil_div_ll(work, 256);
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  if (blocks < 1) blocks = 1;
+#define BIU_FC(TIN, TOUT)                                                                                      \
+  do {                                                                                                         \
+    if (smem > 48 * 1024)                                                                                      \
+      BIU_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<TIN, TOUT>,                                        \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+    first_conv_kernel<TIN, TOUT><<<(int)blocks, 256, smem, stream>>>(a);                                       \
+  } while (0)
+  if (a.in_kind == 0 && a.esz == 2) BIU_FC(uint8_t, __nv_bfloat16);
+  else if (a.in_kind == 0 && a.esz == 4) BIU_FC(uint8_t, float);
+  else if (a.in_kind == 1 && a.esz == 2) BIU_FC(float, __nv_bfloat16);
+  else if (a.in_kind == 1 && a.esz == 4) BIU_FC(float, float);
+  else BIU_REQUIRE(false, "first_conv: bad in_kind/esz");
+#undef BIU_FC
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool(k=2,s=2) (unet/unet.py:22, unet3d/unet3d.py:26) or nearest x0.5 (multi_output_unet3d.py:112):
+// 16-byte vectors along the channel dim.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) pool2_kernel(PoolArgs a) {
+  const int oW = a.W / 2, oH = a.H / 2, oD = a.dims == 3 ? a.D / 2 : a.D;
+  const int cv = a.c / VEC;
+  const long long total = (long long)a.B * oD * oH * oW * cv;
+  const T* in = reinterpret_cast<const T*>(a.in);
+  T* out = reinterpret_cast<T*>(a.out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int c = (int)(r % cv) * VEC; r /= cv;
+    const int x = (int)(r % oW); r /= oW;
+    const int y = (int)(r % oH); r /= oH;
+    const int z = (int)(r % oD); r /= oD;
+    const int b = (int)r;
+    float m[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+    const int nz = (a.dims == 3 && a.mode == 0) ? 2 : 1;
+    const int nyx = a.mode == 0 ? 2 : 1;
+    for (int dz = 0; dz < nz; ++dz)
+      for (int dy = 0; dy < nyx; ++dy)
+        for (int dx = 0; dx < nyx; ++dx) {
+          const int iz = a.dims == 3 ? 2 * z + dz : z;
+          const long long p = (((long long)b * a.D + iz) * a.H + (2 * y + dy)) * a.W + (2 * x + dx);
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + p * a.in_ctot + a.in_coff + c));
+          const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) m[k] = fmaxf(m[k], (float)e[k]);
+        }
+    uint4 q;
+    T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) e[k] = (T)m[k];
+    const long long op = (((long long)b * oD + z) * oH + y) * oW + x;
+    *reinterpret_cast<uint4*>(out + op * a.out_ctot + a.out_coff + c) = q;
+  }
+}
+
+int launch_pool2(const PoolArgs& a, cudaStream_t stream) {
+  const int vec = 16 / a.esz;
+  BIU_REQUIRE(a.c % vec == 0 && a.in_ctot % vec == 0 && a.in_coff % vec == 0 && a.out_ctot % vec == 0 &&
+                  a.out_coff % vec == 0,
+              "pool2: channel counts must be multiples of %d", vec);
+  const long long total = (long long)a.B * (a.dims == 3 ? a.D / 2 : a.D) * (a.H / 2) * (a.W / 2) * (a.c / vec);
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  if (a.esz == 2) pool2_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);
+  else pool2_kernel<float, 4><<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// nearest x2 upsampling: out[2z+a, 2y+b, 2x+c] = in[z, y, x] (multi_output_unet3d.py:138,147,156)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) up_nearest_kernel(UpNearestArgs a) {
+  const int oW = a.W * 2, oH = a.H * 2, oD = a.dims == 3 ? a.D * 2 : a.D;
+  const int cv = a.c / VEC;
+  const long long total = (long long)a.B * oD * oH * oW * cv;
+  const T* in = reinterpret_cast<const T*>(a.in);
+  T* out = reinterpret_cast<T*>(a.out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int c = (int)(r % cv) * VEC; r /= cv;
+    const int x = (int)(r % oW); r /= oW;
+    const int y = (int)(r % oH); r /= oH;
+    const int z = (int)(r % oD); r /= oD;
+    const int b = (int)r;
+    const int iz = a.dims == 3 ? z / 2 : z;
+    const long long p = (((long long)b * a.D + iz) * a.H + y / 2) * a.W + x / 2;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + p * a.in_ctot + a.in_coff + c));
+    const long long op = (((long long)b * oD + z) * oH + y) * oW + x;
+    *reinterpret_cast<uint4*>(out + op * a.out_ctot + a.out_coff + c) = q;
+  }
+}
+int launch_up_nearest(const UpNearestArgs& a, cudaStream_t stream) {
+  const int vec = 16 / a.esz;
+  BIU_REQUIRE(a.c % vec == 0 && a.in_ctot % vec == 0 && a.in_coff % vec == 0 && a.out_ctot % vec == 0 &&
+                  a.out_coff % vec == 0,
+              "up_nearest: channel counts must be multiples of %d", vec);
+  const long long total = (long long)a.B * (a.dims == 3 ? a.D * 2 : a.D) * a.H * 2 * a.W * 2 * (a.c / vec);
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  if (a.esz == 2) up_nearest_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);
+  else up_nearest_kernel<float, 4><<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standalone 1x1 head + activation (unet/unet.py:50-52,104; multi_output_unet3d.py:164-168)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
+  const long long total = a.npix_per_img * a.B;
+  const T* in = reinterpret_cast<const T*>(a.in);
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(pix / a.npix_per_img);
+    const long long sp = pix - (long long)b * a.npix_per_img;
+    const T* src = in + pix * a.in_ctot + a.in_coff;
+    for (int h = 0; h < a.head_n; ++h) {
+      float s = 0.f;
+      for (int c = 0; c < a.cin; ++c) s = fmaf(ld_act<T>(src + c), __ldg(a.w + h * a.cin + c), s);
+      s += __ldg(a.b + h);
+      float v;
+      switch (a.act[h]) {
+        case 1: v = 1.0f / (1.0f + expf(-s)); break;
+        case 2: v = tanhf(s); break;
+        case 3: v = fmaxf(s, 0.f); break;
+        default: v = s;
+      }
+      const long long o = ((long long)b * a.head_n + h) * a.npix_per_img + sp;
+      if (a.out_val) a.out_val[o] = v;
+      if (a.out_u8) a.out_u8[o] = (uint8_t)(v * 255.0f);
+    }
+  }
+}
+int launch_head(const HeadArgs& a, cudaStream_t stream) {
+  const long long total = a.npix_per_img * a.B;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  if (a.esz == 2) head_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>(a);
+  else head_kernel<float><<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct convolution, fp32 accumulate on CUDA cores. Block = 64 pixels x 64 output channels, 256 threads,
+// each thread 4 pixels x 4 channels; K loop over (tap, 16-channel slices) staged through shared memory.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) direct_conv_kernel(DirectConvArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const long long npix = (long long)a.B * a.D * a.H * a.W;
+  const long long pix0 = (long long)blockIdx.x * 64;
+  const int co0 = blockIdx.y * 64;
+  const int tp = threadIdx.x & 15;        // pixel group (4 pixels: tp*4..)
+  const int tc = threadIdx.x >> 4;        // channel group (4 channels: tc*4..)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const T* in = reinterpret_cast<const T*>(a.in);
+
+  // staging roles: thread loads A element (pixel lp, channel lc..)
+  const int lp = threadIdx.x & 63;        // pixel within tile
+  const int lq = threadIdx.x >> 6;        // 0..3 -> channels lq*4..lq*4+3
+  const long long my_pix = pix0 + lp;
+  int mx = 0, my = 0, mz = 0, mb = 0;
+  if (my_pix < npix) {
+    long long r = my_pix;
+    mx = (int)(r % a.W); r /= a.W;
+    my = (int)(r % a.H); r /= a.H;
+    mz = (int)(r % a.D); r /= a.D;
+    mb = (int)r;
+  }
+  int tap = 0;
+  for (int dz = 0; dz < a.kd; ++dz)
+    for (int dy = 0; dy < a.kh; ++dy)
+      for (int dx = 0; dx < a.kw; ++dx, ++tap) {
+        const int zz = mz + dz - (a.kd >> 1), yy = my + dy - (a.kh >> 1), xx = mx + dx - (a.kw >> 1);
+        const bool inb = my_pix < npix && zz >= 0 && zz < a.D && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+        const long long spix = (((long long)mb * a.D + zz) * a.H + yy) * a.W + xx;
+        for (int c0 = 0; c0 < a.cin; c0 += 16) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = c0 + lq * 4 + k;
+            As[lq * 4 + k][lp] = (inb && c < a.cin) ? ld_act<T>(in + spix * a.in_ctot + a.in_coff + c) : 0.f;
+          }
+          // weights: 16 x 64 slice; thread -> (row = tid/16, cols (tid%16)*4..+3)
+          {
+            const int wr = threadIdx.x >> 4, wc = (threadIdx.x & 15) * 4;
+            const int c = c0 + wr;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int co = co0 + wc + k;
+              Ws[wr][wc + k] = (c < a.cin && co < a.cout) ? __ldg(a.wgt + ((long long)tap * a.cin + c) * a.cout + co) : 0.f;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float av[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[k][tp * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = Ws[k][tc * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+          }
+          __syncthreads();
+        }
+      }
+  T* out = reinterpret_cast<T*>(a.out);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long pix = pix0 + tp * 4 + i;
+    if (pix >= npix) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tc * 4 + j;
+      if (co >= a.cout) continue;
+      float t = acc[i][j];
+      t = fmaf(t, a.scale ? __ldg(a.scale + co) : 1.f, __ldg(a.shift + co));
+      t = t > 0.f ? t : t * a.slope;
+      st_act<T>(out + pix * a.out_ctot + a.out_coff + co, t, a.round_tf32);
+    }
+  }
+}
+
+int launch_direct_conv(const DirectConvArgs& a, cudaStream_t stream) {
+  const long long npix = (long long)a.B * a.D * a.H * a.W;
+  dim3 grid((unsigned)ceil_div_ll(npix, 64), (unsigned)ceil_div(a.cout, 64));
+  if (a.esz == 2) direct_conv_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
+  else direct_conv_kernel<float><<<grid, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ConvTranspose(k=2,s=2): out[2p+q] = bias + sum_ci in[p,ci] * W[q][ci][co] (unet/unet.py:38, unet3d/unet3d.py:40-42)
+template <typename T>
+__global__ void __launch_bounds__(256) direct_up_kernel(DirectUpArgs a) {
+  const int nq = a.dims == 3 ? 8 : 4;
+  const long long npix = (long long)a.B * a.D * a.H * a.W;
+  const long long total = npix * nq * a.cout;
+  const T* in = reinterpret_cast<const T*>(a.in);
+  T* out = reinterpret_cast<T*>(a.out);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int co = (int)(r % a.cout); r /= a.cout;
+    const int q = (int)(r % nq); r /= nq;
+    const long long pix = r;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int z = (int)(r % a.D); r /= a.D;
+    const int b = (int)r;
+    float s = 0.f;
+    const T* src = in + pix * a.in_ctot + a.in_coff;
+    const float* w = a.wgt + (long long)q * a.cin * a.cout + co;
+    for (int c = 0; c < a.cin; ++c) s = fmaf(ld_act<T>(src + c), __ldg(w + (long long)c * a.cout), s);
+    s += __ldg(a.bias + co);
+    const int ax = q & 1, ay = (q >> 1) & 1, az = (q >> 2) & 1;
+    const int oW = 2 * a.W, oH = 2 * a.H, oD = a.dims == 3 ? 2 * a.D : a.D;
+    const int oz = a.dims == 3 ? 2 * z + az : z;
+    const long long op = (((long long)b * oD + oz) * oH + (2 * y + ay)) * oW + (2 * x + ax);
+    st_act<T>(out + op * a.out_ctot + a.out_coff + co, s, a.round_tf32);
+  }
+}
+int launch_direct_up(const DirectUpArgs& a, cudaStream_t stream) {
+  const long long total = (long long)a.B * a.D * a.H * a.W * (a.dims == 3 ? 8 : 4) * a.cout;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  if (a.esz == 2) direct_up_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>(a);
+  else direct_up_kernel<float><<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace biu

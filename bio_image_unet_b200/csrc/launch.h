@@ -1,0 +1,174 @@
+// Internal launcher interface shared by the C-ABI (capi.cu) and the network planner (net.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace biu {
+
+// ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) -------------------------------------------------------------
+struct ConvTcArgs {
+  int esz;                      // 2 = bf16 operands, 4 = tf32 operands (fp32 storage)
+  const void* in;               // NHWC / NDHWC activations
+  int in_ctot, in_coff;         // channel stride / offset of the source buffer
+  int cin;                      // logical input channels (multiple of 16 bf16 / 8 fp32)
+  int W, H, D, B;
+  int kw, kh, kd;               // 3 or 1
+  const void* wgt;              // packed [tap][n_total][cin]
+  int n_total;                  // Cout, or 2^dims * Cout for the transposed convolution
+  int mode;                     // EpiMode
+  float slope;
+  const float* scale;
+  const float* shift;
+  void* out;
+  int out_ctot, out_coff;
+  int up_cout, up_dims;
+  int head_n;
+  const float* head_w;
+  const float* head_b;
+  int head_act[8];
+  float* out_val;
+  uint8_t* out_u8;
+  int smem_budget;              // 0 = default
+};
+bool conv_tc_supported(const ConvTcArgs& a);
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
+int read_device_fault(unsigned int* out);
+int pick_ck(int cin, int esz);
+
+// ---- CUDA-core kernels (direct.cu): exact-fp32 path and shapes the tensor path cannot take ------------------------
+struct DirectConvArgs {
+  int esz;                      // activation storage: 2 = bf16, 4 = fp32
+  const void* in;
+  int in_ctot, in_coff, cin;
+  int W, H, D, B;
+  int kw, kh, kd;
+  const float* wgt;             // fp32 [tap][cin][cout]
+  int cout;
+  float slope;                  // LeakyReLU slope; 1.0 => identity
+  const float* scale;           // [cout] (nullptr => 1)
+  const float* shift;           // [cout]
+  void* out;
+  int out_ctot, out_coff;
+  int round_tf32;               // round stored fp32 activations to tf32 (so the tensor path can consume them)
+};
+int launch_direct_conv(const DirectConvArgs& a, cudaStream_t stream);
+
+struct DirectUpArgs {           // ConvTranspose(k=2,s=2): fp32 weights [q][cin][cout], q = (az,ay,ax) bits
+  int esz;
+  const void* in;
+  int in_ctot, in_coff, cin;
+  int W, H, D, B;
+  int dims;
+  const float* wgt;
+  const float* bias;
+  int cout;
+  void* out;
+  int out_ctot, out_coff;
+  int round_tf32;
+};
+int launch_direct_up(const DirectUpArgs& a, cudaStream_t stream);
+
+struct FirstConvArgs {          // planar u8 / f32 input with few channels -> NHWC features
+  int in_kind;                  // 0 = u8 (value/255), 1 = f32
+  const void* in;               // [B][cin][D][H][W]
+  int cin;
+  int W, H, D, B;
+  int kd;                       // 1 (2D) or 3
+  const float* wgt;             // fp32 [tap][cin][cout]
+  int cout;                     // real output channels
+  float slope;
+  const float* scale;
+  const float* shift;
+  int esz;
+  void* out;                    // NHWC, channels [coff, coff+cout_pad) written (pad = zeros)
+  int out_ctot, out_coff, cout_pad;
+  int round_tf32;
+};
+int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream);
+
+struct PoolArgs {
+  int esz;
+  const void* in;
+  int in_ctot, in_coff, c;
+  int W, H, D, B;               // input extents
+  int dims;                     // 2: pool (h,w); 3: pool (d,h,w)
+  int mode;                     // 0 = max, 1 = nearest (take the even-index sample)
+  void* out;                    // [B][D'][H/2][W/2][out_ctot]
+  int out_ctot, out_coff;
+};
+int launch_pool2(const PoolArgs& a, cudaStream_t stream);
+
+struct UpNearestArgs {          // nearest-neighbour x2 upsampling (multi_output_unet3d, use_interpolation=True)
+  int esz;
+  const void* in;
+  int in_ctot, in_coff, c;
+  int W, H, D, B;               // input extents
+  int dims;
+  void* out;
+  int out_ctot, out_coff;
+};
+int launch_up_nearest(const UpNearestArgs& a, cudaStream_t stream);
+
+struct HeadArgs {               // 1x1 head + activation on NHWC features -> planar
+  int esz;
+  const void* in;
+  int in_ctot, in_coff, cin;
+  long long npix_per_img;       // D*H*W
+  int B;
+  int head_n;
+  const float* w;               // [head_n][cin]
+  const float* b;
+  int act[8];
+  float* out_val;
+  uint8_t* out_u8;
+};
+int launch_head(const HeadArgs& a, cudaStream_t stream);
+
+// ---- HBM-bound pipeline kernels (pipeline.cu) -------------------------------------------------------------------
+int launch_histogram(const void* img, int dtype_bytes, long long n_per_frame, int frames, unsigned int* hist,
+                     cudaStream_t stream);
+int launch_hist_sum(const unsigned int* hist, int frames, unsigned int* out, cudaStream_t stream);
+int launch_norm_lut(const unsigned int* hist_bounds, const unsigned int* hist_range, long long bounds_stride,
+                    long long range_stride, int frames, double q_lo, double q_hi, int invert, uint8_t* lut,
+                    double* params, cudaStream_t stream);
+int launch_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
+                     long long lut_stride, uint8_t* out, cudaStream_t stream);
+struct GatherArgs {
+  const uint8_t* src;           // [F][Z][H][W]
+  int F, Z, H, W;
+  int pad_mode;                 // 0 = reflect, 1 = constant zero
+  const int* zs; const int* ys; const int* xs;   // device arrays of tile starts
+  int nz, ny, nx;
+  int pd, ph, pw;               // tile extents
+  uint8_t* dst;                 // [F*nz*ny*nx][pd][ph][pw]
+};
+int launch_gather_tiles(const GatherArgs& a, cudaStream_t stream);
+struct StitchMeanArgs {         // unet/predict.py:204-229 == integer sum // count
+  const uint8_t* tiles;         // [F][ny*nx][C][ph][pw]
+  int F, C, H, W;               // output extents (already cropped to the image)
+  const int* ys; const int* xs;
+  int ny, nx, ph, pw;
+  uint8_t* out;                 // [F][C][H][W]
+};
+int launch_stitch_mean(const StitchMeanArgs& a, cudaStream_t stream);
+struct StitchMod3Args {         // unet3d/predict.py:173-195
+  const uint8_t* tiles;         // [nz*ny*nx][pd][ph][pw]
+  int Z, H, W;
+  const int* zs; const int* ys; const int* xs;
+  int nz, ny, nx, pd, ph, pw;
+  uint8_t* out;                 // [Z][H][W]
+};
+int launch_stitch_mod3(const StitchMod3Args& a, cudaStream_t stream);
+struct StitchRampArgs {         // multi_output_unet3d/predict.py:203-307
+  const float* tiles;           // [V][nz*ny*nx][C][pd][ph][pw]
+  int V, C, Z, H, W;
+  const int* zs; const int* ys; const int* xs;
+  int nz, ny, nx, pd, ph, pw;
+  int margin;
+  float* out;                   // [V][C][Z][H][W]
+};
+int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream);
+
+
+
+}  // namespace biu

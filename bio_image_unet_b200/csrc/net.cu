@@ -1,0 +1,594 @@
+// Layer programs of the reference's model families and their execution on a batch of tiles.
+//   Unet          unet/unet.py:16-104            (2D, depth 4)
+//   Siam_UNet     siam_unet/siam_unet.py:18-148  (twin encoder, shared weights)
+//   UNet3D        unet3d/unet3d.py:18-99         (3D, depth 3)
+//   MultiOutputUnet3D  multi_output_unet3d/multi_output_unet3d.py:13-170
+// Activations are NHWC / NDHWC with channel counts padded to 16; torch.cat((up, skip), 1) is replaced by
+// writing both producers into one buffer at channel offsets.
+#include "net.h"
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace biu {
+
+static int pad16(int c) { return (c + 15) / 16 * 16; }
+
+static float host_round_tf32(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return v;
+  u += 0x1000u;            // round to nearest, ties away (cvt.rna)
+  u &= 0xFFFFE000u;
+  memcpy(&v, &u, 4);
+  return v;
+}
+static uint16_t host_bf16(float v) {
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);   // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+struct Builder {
+  Net* n;
+  int buf(const std::string& name, int level, int ctot, int batch_mul = 1) {
+    Buf b;
+    b.level = level; b.ctot = ctot; b.batch_mul = batch_mul; b.name = name;
+    n->bufs.push_back(b);
+    return (int)n->bufs.size() - 1;
+  }
+  int conv_layer(const std::string& name, std::vector<Segment> segs, int cin_phys, int cout, int k) {
+    ConvLayer L;
+    L.name = name;
+    L.segs = segs;
+    L.cin_log = 0;
+    for (auto& s : segs) L.cin_log += s.count;
+    L.cin_phys = cin_phys;
+    L.cout = cout;
+    L.cout_pad = pad16(cout);
+    L.kw = L.kh = k;
+    L.kd = n->dims == 3 ? k : 1;
+    n->layers.push_back(L);
+    return (int)n->layers.size() - 1;
+  }
+  int up_layer(const std::string& name, int cin, int cout) {
+    ConvLayer L;
+    L.name = name;
+    L.segs = {{0, cin, 0}};
+    L.cin_log = cin; L.cin_phys = pad16(cin);
+    L.cout = cout; L.cout_pad = pad16(cout);
+    L.is_up = true;
+    L.nq = n->dims == 3 ? 8 : 4;
+    n->layers.push_back(L);
+    return (int)n->layers.size() - 1;
+  }
+  void op(OpKind kind, int layer, int src, int src_coff, int dst, int dst_coff, int c, int level, int batch_mul = 1,
+          int src_img0 = 0, int dst_img0 = 0, int pool_mode = 0) {
+    Op o;
+    o.kind = kind; o.layer = layer; o.src = src; o.src_coff = src_coff; o.dst = dst; o.dst_coff = dst_coff;
+    o.c = c; o.level = level; o.batch_mul = batch_mul; o.src_img0 = src_img0; o.dst_img0 = dst_img0;
+    o.pool_mode = pool_mode;
+    n->ops.push_back(o);
+  }
+  // plain block: src buffer (dense, logical channels = cin) -> dst
+  void block(const std::string& name, int src, int cin, int dst, int dst_coff, int cout, int level, int bm = 1) {
+    int L = conv_layer(name, {{0, cin, 0}}, pad16(cin), cout, 3);
+    op(OP_CONV, L, src, 0, dst, dst_coff, pad16(cin), level, bm);
+  }
+  // block reading a concat buffer [up | skip]
+  void block_cat(const std::string& name, int src, int c_up, int c_skip, int dst, int cout, int level) {
+    int L = conv_layer(name, {{0, c_up, 0}, {c_up, c_skip, pad16(c_up)}}, pad16(c_up) + pad16(c_skip), cout, 3);
+    op(OP_CONV, L, src, 0, dst, 0, pad16(c_up) + pad16(c_skip), level);
+  }
+};
+
+int net_build(Net* n) {
+  n->layers.clear(); n->bufs.clear(); n->ops.clear();
+  Builder b{n};
+  const int nf = n->nf;
+  n->esz = n->precision == PREC_BF16 ? 2 : 4;
+  n->head_total = 0;
+  for (int c : n->head_channels) n->head_total += c;
+  BIU_REQUIRE(n->head_total >= 1 && n->head_total <= kMaxHead, "between 1 and %d output channels supported (got %d)",
+              kMaxHead, n->head_total);
+  BIU_REQUIRE(nf >= 2 && nf % 2 == 0, "n_filter must be even (got %d)", nf);
+
+  if (n->kind == NET_UNET2D || n->kind == NET_SIAM2D) {
+    n->dims = 2;
+    n->levels = 4;
+    const bool siam = n->kind == NET_SIAM2D;
+    BIU_REQUIRE(!(siam && n->siam_mode == SIAM_CORR), "Siam_UNet mode='corr' is not implemented by this engine");
+    // 'control' ignores the previous frame (siam_unet.py:122-123): its encoder pass is dead work and is skipped
+    const int bm = (siam && n->siam_mode != SIAM_CONTROL) ? 2 : 1;
+    int ch[5] = {nf, 2 * nf, 4 * nf, 8 * nf, 16 * nf};
+    int e_a[4], cat[4], m[4], d_a[4], d_b[4];
+    for (int l = 0; l < 4; ++l) {
+      e_a[l] = b.buf("e" + std::to_string(2 * l + 1), l, pad16(ch[l]), bm);
+      cat[l] = b.buf("cat" + std::to_string(4 - l), l, 2 * pad16(ch[l]), bm);
+      m[l] = b.buf("m" + std::to_string(l + 1), l + 1, pad16(ch[l]), bm);
+    }
+    int join = -1, joincat = -1;
+    if (siam && n->siam_mode == SIAM_CONCAT) joincat = b.buf("joincat", 4, 2 * pad16(ch[3]));
+    if (siam && n->siam_mode != SIAM_CONTROL) join = b.buf("join", 4, pad16(ch[3]));
+    int mid1 = b.buf("mid1", 4, pad16(ch[4]));
+    int mid2 = b.buf("mid2", 4, pad16(ch[4]));
+    for (int l = 3; l >= 0; --l) {
+      d_a[l] = b.buf("d" + std::to_string(2 * (3 - l) + 1), l, pad16(ch[l]));
+      d_b[l] = l > 0 ? b.buf("d" + std::to_string(2 * (3 - l) + 2), l, pad16(ch[l])) : -1;
+    }
+    // encoder
+    for (int l = 0; l < 4; ++l) {
+      const std::string n1 = "encode" + std::to_string(2 * l + 1), n2 = "encode" + std::to_string(2 * l + 2);
+      if (l == 0) {
+        int L = b.conv_layer(n1, {{0, n->in_ch, 0}}, n->in_ch, ch[0], 3);
+        b.op(OP_FIRST, L, -1, 0, e_a[0], 0, n->in_ch, 0, 1, 0, 0);
+        if (bm == 2) b.op(OP_FIRST, L, -2, 0, e_a[0], 0, n->in_ch, 0, 1, 0, 1);
+      } else {
+        int L = b.conv_layer(n1, {{0, ch[l - 1], 0}}, pad16(ch[l - 1]), ch[l], 3);
+        b.op(OP_CONV, L, m[l - 1], 0, e_a[l], 0, pad16(ch[l - 1]), l, bm);
+      }
+      {
+        int L = b.conv_layer(n2, {{0, ch[l], 0}}, pad16(ch[l]), ch[l], 3);
+        b.op(OP_CONV, L, e_a[l], 0, cat[l], pad16(ch[l]), pad16(ch[l]), l, bm);
+      }
+      if (l < 3 || !siam || n->siam_mode == SIAM_MAX || n->siam_mode == SIAM_CONTROL) {
+        b.op(OP_POOL, -1, cat[l], pad16(ch[l]), m[l], 0, pad16(ch[l]), l, bm);
+      } else {  // concat join: pooled current -> channels [0, 8nf), pooled previous -> [8nf, 16nf)
+        b.op(OP_POOL, -1, cat[l], pad16(ch[l]), joincat, 0, pad16(ch[l]), l, 1, 0, 0);
+        b.op(OP_POOL, -1, cat[l], pad16(ch[l]), joincat, pad16(ch[l]), pad16(ch[l]), l, 1, 1, 0);
+      }
+    }
+    int mid_src = m[3];
+    if (siam && n->siam_mode == SIAM_CONCAT) {
+      int L = b.conv_layer("conv_concat", {{0, ch[3], 0}, {ch[3], ch[3], pad16(ch[3])}}, 2 * pad16(ch[3]), ch[3], 3);
+      b.op(OP_CONV, L, joincat, 0, join, 0, 2 * pad16(ch[3]), 4);
+      mid_src = join;
+    } else if (siam && n->siam_mode == SIAM_MAX) {
+      Op o; o.kind = OP_MAXJOIN; o.src = m[3]; o.dst = join; o.c = pad16(ch[3]); o.level = 4; o.src2 = 1;
+      n->ops.push_back(o);
+      mid_src = join;
+    }
+    b.block("middle_conv1", mid_src, ch[3], mid1, 0, ch[4], 4);
+    b.block("middle_conv2", mid1, ch[4], mid2, 0, ch[4], 4);
+    // decoder
+    int prev = mid2, prev_c = ch[4];
+    for (int l = 3; l >= 0; --l) {
+      const int k = 3 - l;  // 0..3
+      int U = b.up_layer("up" + std::to_string(k + 1), prev_c, ch[l]);
+      b.op(OP_UP, U, prev, 0, cat[l], 0, pad16(prev_c), l + 1);
+      b.block_cat("decode" + std::to_string(2 * k + 1), cat[l], ch[l], ch[l], d_a[l], ch[l], l);
+      if (l > 0) {
+        b.block("decode" + std::to_string(2 * k + 2), d_a[l], ch[l], d_b[l], 0, ch[l], l);
+        prev = d_b[l]; prev_c = ch[l];
+      } else {
+        int L = b.conv_layer("decode8", {{0, ch[0], 0}}, pad16(ch[0]), ch[0], 3);
+        b.op(OP_CONV_HEAD, L, d_a[0], 0, -1, 0, pad16(ch[0]), 0);
+      }
+    }
+  } else if (n->kind == NET_UNET3D || n->kind == NET_MO3D) {
+    n->dims = 3;
+    n->levels = 3;
+    const bool interp = n->use_interp != 0;
+    BIU_REQUIRE(!(n->kind == NET_UNET3D && interp),
+                "UNet3D(use_interpolation=True) (trilinear upsampling) is not implemented by this engine");
+    const int h = nf / 2;
+    // level l: first conv a[l] -> b[l] channels, second -> c[l]
+    int c_in[4] = {n->in_ch, nf, 2 * nf, 4 * nf};
+    int c_a[4] = {h, nf, 2 * nf, 4 * nf};
+    int c_b[4] = {nf, 2 * nf, 4 * nf, 8 * nf};
+    int up_c[3] = {2 * nf, 4 * nf, 8 * nf};          // channels of the upsampled tensor arriving at level l
+    int e_a[3], cat[3], m[3];
+    for (int l = 0; l < 3; ++l) {
+      e_a[l] = b.buf("e" + std::to_string(2 * l + 1), l, pad16(c_a[l]));
+      cat[l] = b.buf("cat" + std::to_string(3 - l), l, pad16(up_c[l]) + pad16(c_b[l]));
+      m[l] = b.buf("m" + std::to_string(l + 1), l + 1, pad16(c_b[l]));
+    }
+    int mid1 = b.buf("mid1", 3, pad16(c_a[3]));
+    int mid2 = b.buf("mid2", 3, pad16(c_b[3]));
+    int dec_out[3] = {h, 2 * nf, 4 * nf};             // decode6 / decode4 / decode2 outputs
+    int dec_mid[3] = {nf, 2 * nf, 4 * nf};            // decode5 / decode3 / decode1 outputs
+    int d_a[3], d_b[3], upt[3];
+    for (int l = 2; l >= 0; --l) {
+      d_a[l] = b.buf("d" + std::to_string(2 * (2 - l) + 1), l, pad16(dec_mid[l]));
+      d_b[l] = l > 0 ? b.buf("d" + std::to_string(2 * (2 - l) + 2), l, pad16(dec_out[l])) : -1;
+      upt[l] = interp ? b.buf("upn" + std::to_string(3 - l), l, pad16(up_c[l])) : -1;
+    }
+    for (int l = 0; l < 3; ++l) {
+      const std::string n1 = "encode" + std::to_string(2 * l + 1), n2 = "encode" + std::to_string(2 * l + 2);
+      if (l == 0) {
+        int L = b.conv_layer(n1, {{0, n->in_ch, 0}}, n->in_ch, c_a[0], 3);
+        b.op(OP_FIRST, L, -1, 0, e_a[0], 0, n->in_ch, 0);
+      } else {
+        b.block(n1, m[l - 1], c_in[l], e_a[l], 0, c_a[l], l);
+      }
+      b.block(n2, e_a[l], c_a[l], cat[l], pad16(up_c[l]), c_b[l], l);
+      b.op(OP_POOL, -1, cat[l], pad16(up_c[l]), m[l], 0, pad16(c_b[l]), l, 1, 0, 0, interp ? 1 : 0);
+    }
+    b.block("middle_conv1", m[2], c_in[3], mid1, 0, c_a[3], 3);
+    b.block("middle_conv2", mid1, c_a[3], mid2, 0, c_b[3], 3);
+    int prev = mid2, prev_c = c_b[3];
+    for (int l = 2; l >= 0; --l) {
+      const int k = 2 - l;
+      if (!interp) {
+        int U = b.up_layer("up" + std::to_string(k + 1), prev_c, prev_c);
+        b.op(OP_UP, U, prev, 0, cat[l], 0, pad16(prev_c), l + 1);
+      } else {
+        b.op(OP_UPNEAREST, -1, prev, 0, upt[l], 0, pad16(prev_c), l + 1);
+        b.block("up" + std::to_string(k + 1) + "_conv", upt[l], prev_c, cat[l], 0, prev_c, l);
+      }
+      b.block_cat("decode" + std::to_string(2 * k + 1), cat[l], up_c[l], c_b[l], d_a[l], dec_mid[l], l);
+      if (l > 0) {
+        b.block("decode" + std::to_string(2 * k + 2), d_a[l], dec_mid[l], d_b[l], 0, dec_out[l], l);
+        prev = d_b[l]; prev_c = dec_out[l];
+      } else {
+        int L = b.conv_layer("decode6", {{0, dec_mid[0], 0}}, pad16(dec_mid[0]), dec_out[0], 3);
+        b.op(OP_CONV_HEAD, L, d_a[0], 0, -1, 0, pad16(dec_mid[0]), 0);
+      }
+    }
+  } else {
+    BIU_REQUIRE(false, "unknown network kind %d", n->kind);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static const HostTensor* find_param(Net* n, const std::string& name) {
+  auto it = n->params.find(name);
+  return it == n->params.end() ? nullptr : &it->second;
+}
+
+template <typename T>
+static int upload(Net* n, const std::vector<T>& h, T** dptr) {
+  void* d = nullptr;
+  BIU_CHECK_CUDA(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+  BIU_CHECK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  n->dev_allocs.push_back(d);
+  *dptr = reinterpret_cast<T*>(d);
+  return 0;
+}
+
+int net_finalize(Net* n) {
+  for (auto& L : n->layers) {
+    const int taps = L.kd * L.kh * L.kw;
+    if (!L.is_up) {
+      const HostTensor* w = find_param(n, L.name + ".0.weight");
+      const HostTensor* bias = find_param(n, L.name + ".0.bias");
+      const HostTensor* g = find_param(n, L.name + ".1.weight");
+      const HostTensor* be = find_param(n, L.name + ".1.bias");
+      const HostTensor* mu = find_param(n, L.name + ".1.running_mean");
+      const HostTensor* var = find_param(n, L.name + ".1.running_var");
+      BIU_REQUIRE(w && bias && g && be && mu && var, "state_dict is missing parameters of block '%s'", L.name.c_str());
+      BIU_REQUIRE((long long)w->data.size() == (long long)L.cout * L.cin_log * taps,
+                  "'%s.0.weight' has %lld elements, expected %lld", L.name.c_str(), (long long)w->data.size(),
+                  (long long)L.cout * L.cin_log * taps);
+      std::vector<float> scale(L.cout_pad, 0.f), shift(L.cout_pad, 0.f);
+      for (int co = 0; co < L.cout; ++co) {
+        const double s = (double)g->data[co] / std::sqrt((double)var->data[co] + 1e-5);
+        scale[co] = (float)s;
+        shift[co] = (float)((double)be->data[co] + ((double)bias->data[co] - (double)mu->data[co]) * s);
+      }
+      // physical channel of every logical input channel
+      std::vector<int> phys(L.cin_log);
+      for (auto& sg : L.segs)
+        for (int i = 0; i < sg.count; ++i) phys[sg.lstart + i] = sg.pstart + i;
+      std::vector<float> wd((size_t)taps * L.cin_phys * L.cout_pad, 0.f);
+      for (int co = 0; co < L.cout; ++co)
+        for (int ci = 0; ci < L.cin_log; ++ci)
+          for (int t = 0; t < taps; ++t)
+            wd[((size_t)t * L.cin_phys + phys[ci]) * L.cout_pad + co] = w->data[((size_t)co * L.cin_log + ci) * taps + t];
+      if (upload(n, wd, &L.w_direct)) return -1;
+      if (upload(n, scale, &L.scale)) return -1;
+      if (upload(n, shift, &L.shift)) return -1;
+      if (n->precision != PREC_FP32 && L.cin_phys % 16 == 0) {
+        const size_t cnt = (size_t)taps * L.cout_pad * L.cin_phys;
+        if (n->esz == 2) {
+          std::vector<uint16_t> wp(cnt, 0);
+          for (int t = 0; t < taps; ++t)
+            for (int co = 0; co < L.cout; ++co)
+              for (int ci = 0; ci < L.cin_log; ++ci)
+                wp[((size_t)t * L.cout_pad + co) * L.cin_phys + phys[ci]] =
+                    host_bf16(w->data[((size_t)co * L.cin_log + ci) * taps + t]);
+          uint16_t* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_tc = d;
+        } else {
+          std::vector<float> wp(cnt, 0.f);
+          for (int t = 0; t < taps; ++t)
+            for (int co = 0; co < L.cout; ++co)
+              for (int ci = 0; ci < L.cin_log; ++ci)
+                wp[((size_t)t * L.cout_pad + co) * L.cin_phys + phys[ci]] =
+                    host_round_tf32(w->data[((size_t)co * L.cin_log + ci) * taps + t]);
+          float* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_tc = d;
+        }
+      }
+    } else {
+      const HostTensor* w = find_param(n, L.name + ".weight");
+      const HostTensor* bias = find_param(n, L.name + ".bias");
+      BIU_REQUIRE(w && bias, "state_dict is missing parameters of '%s'", L.name.c_str());
+      BIU_REQUIRE((long long)w->data.size() == (long long)L.cin_log * L.cout * L.nq,
+                  "'%s.weight' has %lld elements, expected %lld", L.name.c_str(), (long long)w->data.size(),
+                  (long long)L.cin_log * L.cout * L.nq);
+      // torch layout [Cin][Cout][(2)][2][2]; q = (az*2 + ay)*2 + ax is the flattened kernel index
+      std::vector<float> wd((size_t)L.nq * L.cin_phys * L.cout_pad, 0.f);
+      std::vector<float> shift((size_t)L.nq * L.cout_pad, 0.f), scale((size_t)L.nq * L.cout_pad, 1.f);
+      for (int q = 0; q < L.nq; ++q)
+        for (int co = 0; co < L.cout; ++co) {
+          shift[(size_t)q * L.cout_pad + co] = bias->data[co];
+          for (int ci = 0; ci < L.cin_log; ++ci)
+            wd[((size_t)q * L.cin_phys + ci) * L.cout_pad + co] = w->data[((size_t)ci * L.cout + co) * L.nq + q];
+        }
+      if (upload(n, wd, &L.w_direct)) return -1;
+      if (upload(n, scale, &L.scale)) return -1;
+      if (upload(n, shift, &L.shift)) return -1;
+      if (n->precision != PREC_FP32) {
+        const size_t cnt = (size_t)L.nq * L.cout_pad * L.cin_phys;
+        if (n->esz == 2) {
+          std::vector<uint16_t> wp(cnt, 0);
+          for (int q = 0; q < L.nq; ++q)
+            for (int co = 0; co < L.cout; ++co)
+              for (int ci = 0; ci < L.cin_log; ++ci)
+                wp[((size_t)q * L.cout_pad + co) * L.cin_phys + ci] =
+                    host_bf16(w->data[((size_t)ci * L.cout + co) * L.nq + q]);
+          uint16_t* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_tc = d;
+        } else {
+          std::vector<float> wp(cnt, 0.f);
+          for (int q = 0; q < L.nq; ++q)
+            for (int co = 0; co < L.cout; ++co)
+              for (int ci = 0; ci < L.cin_log; ++ci)
+                wp[((size_t)q * L.cout_pad + co) * L.cin_phys + ci] =
+                    host_round_tf32(w->data[((size_t)ci * L.cout + co) * L.nq + q]);
+          float* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_tc = d;
+        }
+      }
+    }
+  }
+  // head(s): 2D 'final.0', 3D 'final', multi-output 'output_layers.<name>'
+  {
+    const ConvLayer& last = n->layers[n->ops.back().layer];
+    std::vector<float> hw((size_t)n->head_total * last.cout_pad, 0.f), hb(n->head_total, 0.f);
+    int row = 0;
+    for (size_t hi = 0; hi < n->head_channels.size(); ++hi) {
+      std::string base;
+      if (n->kind == NET_MO3D) base = "output_layers." + n->head_names[hi];
+      else if (n->kind == NET_UNET3D) base = "final";
+      else base = "final.0";
+      const HostTensor* w = find_param(n, base + ".weight");
+      const HostTensor* bias = find_param(n, base + ".bias");
+      BIU_REQUIRE(w && bias, "state_dict is missing the head '%s'", base.c_str());
+      BIU_REQUIRE((long long)w->data.size() == (long long)n->head_channels[hi] * last.cout,
+                  "'%s.weight' has %lld elements, expected %lld", base.c_str(), (long long)w->data.size(),
+                  (long long)n->head_channels[hi] * last.cout);
+      for (int c = 0; c < n->head_channels[hi]; ++c, ++row) {
+        for (int ci = 0; ci < last.cout; ++ci) hw[(size_t)row * last.cout_pad + ci] = w->data[(size_t)c * last.cout + ci];
+        hb[row] = bias->data[c];
+      }
+    }
+    if (upload(n, hw, &n->head_w)) return -1;
+    if (upload(n, hb, &n->head_b)) return -1;
+  }
+  n->params.clear();
+  n->finalized = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static void level_dims(const Net* n, int level, int* D, int* H, int* W) {
+  *H = n->H >> level;
+  *W = n->W >> level;
+  *D = n->dims == 3 ? (n->D >> level) : 1;
+}
+
+long long net_plan(Net* n, int B, int D, int H, int W) {
+  const int div = 1 << n->levels;
+  BIU_REQUIRE(B >= 1, "batch must be positive");
+  // unet/unet.py:62-67 raises 'concatenation failed: wrong dimensions' otherwise
+  BIU_REQUIRE(H % div == 0 && W % div == 0 && (n->dims == 2 || D % div == 0),
+              "concatenation failed: wrong dimensions (tile %dx%dx%d is not divisible by %d)", D, H, W, div);
+  n->B = B; n->D = n->dims == 3 ? D : 1; n->H = H; n->W = W;
+  size_t off = 0;
+  for (auto& b : n->bufs) {
+    int d, h, w;
+    level_dims(n, b.level, &d, &h, &w);
+    b.offset = off;
+    size_t bytes = (size_t)B * b.batch_mul * d * h * w * b.ctot * n->esz;
+    off += (bytes + 1023) & ~(size_t)1023;
+  }
+  n->ws_bytes = off;
+  return (long long)off;
+}
+
+__global__ void max_join_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                long long nvec, int esz) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    uint4 x = a[i], y = b[i], r;
+    if (esz == 2) {
+      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+      __nv_bfloat162* rp = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rp[k] = __hmax2(xp[k], yp[k]);
+    } else {
+      const float* xp = reinterpret_cast<const float*>(&x);
+      const float* yp = reinterpret_cast<const float*>(&y);
+      float* rp = reinterpret_cast<float*>(&r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rp[k] = fmaxf(xp[k], yp[k]);
+    }
+    out[i] = r;
+  }
+}
+
+int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out_val, uint8_t* out_u8,
+                void* workspace, cudaStream_t stream) {
+  BIU_REQUIRE(n->finalized, "network weights were not finalized");
+  BIU_REQUIRE(n->B > 0, "biu_net_plan must be called before biu_net_forward");
+  char* ws = reinterpret_cast<char*>(workspace);
+  const bool tc_allowed = n->precision != PREC_FP32 && !n->force_direct;
+  const int round_tf32 = n->precision == PREC_TF32 ? 1 : 0;
+  for (const Op& o : n->ops) {
+    int d, h, w;
+    level_dims(n, o.level, &d, &h, &w);
+    const int batch = n->B * o.batch_mul;
+    const Buf* sb = o.src >= 0 ? &n->bufs[o.src] : nullptr;
+    const Buf* db = o.dst >= 0 ? &n->bufs[o.dst] : nullptr;
+    const size_t img_in = sb ? (size_t)d * h * w * sb->ctot * n->esz : 0;
+    const char* src = sb ? ws + sb->offset + (size_t)o.src_img0 * n->B * img_in : nullptr;
+    auto dst_ptr = [&](int dd, int hh, int ww) -> char* {
+      return db ? ws + db->offset + (size_t)o.dst_img0 * n->B * ((size_t)dd * hh * ww * db->ctot * n->esz) : nullptr;
+    };
+    switch (o.kind) {
+      case OP_FIRST: {
+        const ConvLayer& L = n->layers[o.layer];
+        FirstConvArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in_kind = in_kind;
+        a.in = o.src == -1 ? in : in2;
+        BIU_REQUIRE(a.in != nullptr, "network input pointer is null");
+        a.cin = n->in_ch; a.W = w; a.H = h; a.D = d; a.B = n->B; a.kd = L.kd;
+        a.wgt = L.w_direct; a.cout = L.cout_pad; a.slope = 0.1f; a.scale = L.scale; a.shift = L.shift;
+        a.esz = n->esz; a.out = dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
+        a.cout_pad = L.cout_pad; a.round_tf32 = round_tf32;
+        if (int rc = launch_first_conv(a, stream)) return rc;
+        break;
+      }
+      case OP_CONV:
+      case OP_CONV_HEAD: {
+        const ConvLayer& L = n->layers[o.layer];
+        const bool head = o.kind == OP_CONV_HEAD;
+        ConvTcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.cin = L.cin_phys;
+        a.W = w; a.H = h; a.D = d; a.B = batch; a.kw = L.kw; a.kh = L.kh; a.kd = L.kd;
+        a.wgt = L.w_tc; a.n_total = L.cout_pad; a.mode = head ? EPI_HEAD : EPI_CONV; a.slope = 0.1f;
+        a.scale = L.scale; a.shift = L.shift;
+        a.out = head ? nullptr : dst_ptr(d, h, w);
+        a.out_ctot = head ? 0 : db->ctot; a.out_coff = o.dst_coff;
+        if (head) {
+          a.head_n = n->head_total; a.head_w = n->head_w; a.head_b = n->head_b;
+          int row = 0;
+          for (size_t hi = 0; hi < n->head_channels.size(); ++hi)
+            for (int c = 0; c < n->head_channels[hi]; ++c) a.head_act[row++] = n->head_acts[hi];
+          a.out_val = out_val; a.out_u8 = out_u8;
+        }
+        if (tc_allowed && L.w_tc && conv_tc_supported(a)) {
+          if (int rc = launch_conv_tc(a, stream)) return rc;
+        } else {
+          BIU_REQUIRE(!head || true, "unreachable");
+          DirectConvArgs da;
+          memset(&da, 0, sizeof(da));
+          da.esz = n->esz; da.in = src; da.in_ctot = sb->ctot; da.in_coff = o.src_coff; da.cin = L.cin_phys;
+          da.W = w; da.H = h; da.D = d; da.B = batch; da.kw = L.kw; da.kh = L.kh; da.kd = L.kd;
+          da.wgt = L.w_direct; da.cout = L.cout_pad; da.slope = 0.1f; da.scale = L.scale; da.shift = L.shift;
+          da.round_tf32 = round_tf32;
+          if (!head) {
+            da.out = dst_ptr(d, h, w); da.out_ctot = db->ctot; da.out_coff = o.dst_coff;
+            if (int rc = launch_direct_conv(da, stream)) return rc;
+          } else {
+            // reuse the (now dead) first encoder buffer of level 0 as scratch for the last activation
+            const Buf& scratch = n->bufs[0];
+            BIU_REQUIRE(scratch.level == 0 && scratch.ctot >= L.cout_pad, "no scratch buffer for the head");
+            da.out = ws + scratch.offset; da.out_ctot = scratch.ctot; da.out_coff = 0;
+            if (int rc = launch_direct_conv(da, stream)) return rc;
+            HeadArgs ha;
+            memset(&ha, 0, sizeof(ha));
+            ha.esz = n->esz; ha.in = da.out; ha.in_ctot = scratch.ctot; ha.in_coff = 0; ha.cin = L.cout_pad;
+            ha.npix_per_img = (long long)d * h * w; ha.B = batch; ha.head_n = n->head_total;
+            ha.w = n->head_w; ha.b = n->head_b;
+            int row = 0;
+            for (size_t hi = 0; hi < n->head_channels.size(); ++hi)
+              for (int c = 0; c < n->head_channels[hi]; ++c) ha.act[row++] = n->head_acts[hi];
+            ha.out_val = out_val; ha.out_u8 = out_u8;
+            if (int rc = launch_head(ha, stream)) return rc;
+          }
+        }
+        break;
+      }
+      case OP_UP: {
+        const ConvLayer& L = n->layers[o.layer];
+        const int od = n->dims == 3 ? 2 * d : d;
+        ConvTcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.cin = L.cin_phys;
+        a.W = w; a.H = h; a.D = d; a.B = batch; a.kw = a.kh = a.kd = 1;
+        a.wgt = L.w_tc; a.n_total = L.nq * L.cout_pad; a.mode = EPI_UP; a.slope = 1.f;
+        a.scale = L.scale; a.shift = L.shift;
+        a.out = dst_ptr(od, 2 * h, 2 * w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
+        a.up_cout = L.cout_pad; a.up_dims = n->dims;
+        if (tc_allowed && L.w_tc && conv_tc_supported(a)) {
+          if (int rc = launch_conv_tc(a, stream)) return rc;
+        } else {
+          DirectUpArgs da;
+          memset(&da, 0, sizeof(da));
+          da.esz = n->esz; da.in = src; da.in_ctot = sb->ctot; da.in_coff = o.src_coff; da.cin = L.cin_phys;
+          da.W = w; da.H = h; da.D = d; da.B = batch; da.dims = n->dims; da.wgt = L.w_direct; da.bias = L.shift;
+          da.cout = L.cout_pad; da.out = a.out; da.out_ctot = db->ctot; da.out_coff = o.dst_coff;
+          da.round_tf32 = round_tf32;
+          if (int rc = launch_direct_up(da, stream)) return rc;
+        }
+        break;
+      }
+      case OP_POOL: {
+        PoolArgs a;
+        memset(&a, 0, sizeof(a));
+        a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.c = o.c;
+        a.W = w; a.H = h; a.D = d; a.B = batch; a.dims = n->dims; a.mode = o.pool_mode;
+        a.out = dst_ptr(n->dims == 3 ? d / 2 : d, h / 2, w / 2); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
+        if (int rc = launch_pool2(a, stream)) return rc;
+        break;
+      }
+      case OP_UPNEAREST: {
+        UpNearestArgs a;
+        memset(&a, 0, sizeof(a));
+        a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.c = o.c;
+        a.W = w; a.H = h; a.D = d; a.B = batch; a.dims = n->dims;
+        a.out = dst_ptr(n->dims == 3 ? 2 * d : d, 2 * h, 2 * w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
+        if (int rc = launch_up_nearest(a, stream)) return rc;
+        break;
+      }
+      case OP_MAXJOIN: {
+        const size_t img = (size_t)d * h * w * sb->ctot * n->esz;
+        const long long nvec = (long long)(img * n->B / 16);
+        long long blocks = ceil_div_ll(nvec, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks < 1) blocks = 1;
+        max_join_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(ws + sb->offset),
+                                                         reinterpret_cast<const uint4*>(ws + sb->offset + img * n->B),
+                                                         reinterpret_cast<uint4*>(ws + db->offset), nvec, n->esz);
+        BIU_CHECK_CUDA(cudaGetLastError());
+        break;
+      }
+    }
+  }
+  return 0;
+}
+
+int net_debug_copy(Net* n, const char* buf_name, void* workspace, void* dst_host, long long max_bytes) {
+  for (auto& b : n->bufs) {
+    if (b.name == buf_name) {
+      int d, h, w;
+      level_dims(n, b.level, &d, &h, &w);
+      long long bytes = (long long)n->B * b.batch_mul * d * h * w * b.ctot * n->esz;
+      if (bytes > max_bytes) bytes = max_bytes;
+      BIU_CHECK_CUDA(cudaMemcpy(dst_host, reinterpret_cast<char*>(workspace) + b.offset, bytes, cudaMemcpyDeviceToHost));
+      return 0;
+    }
+  }
+  BIU_REQUIRE(false, "no activation buffer named '%s'", buf_name);
+}
+
+void net_destroy(Net* n) {
+  for (void* p : n->dev_allocs) cudaFree(p);
+  delete n;
+}
+
+}  // namespace biu

@@ -1,0 +1,92 @@
+// Network handle behind the C-ABI: holds the reference checkpoint's tensors (by state_dict name), folds
+// BatchNorm, packs weights for the tensor-core kernels and runs the layer program of one of the reference's
+// model families on a batch of tiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "launch.h"
+
+namespace biu {
+
+enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3 };
+enum Precision { PREC_BF16 = 0, PREC_TF32 = 1, PREC_FP32 = 2 };
+enum SiamMode { SIAM_CONCAT = 0, SIAM_MAX = 1, SIAM_CONTROL = 2, SIAM_CORR = 3 };
+
+struct HostTensor {
+  std::vector<long long> shape;
+  std::vector<float> data;
+};
+
+struct Segment {       // logical input channels [lstart, lstart+count) live at physical channel pstart
+  int lstart, count, pstart;
+};
+
+struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the head
+  std::string name;
+  int cin_log = 0, cout = 0, cin_phys = 0, cout_pad = 0;
+  int kd = 1, kh = 1, kw = 1;
+  bool is_up = false;
+  int nq = 1;
+  std::vector<Segment> segs;
+  void* w_tc = nullptr;      // packed [tap][n][cin_phys] bf16 / tf32
+  float* w_direct = nullptr; // fp32 [tap or q][cin_phys][cout_pad]
+  float* scale = nullptr;    // [n_total]
+  float* shift = nullptr;
+};
+
+enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN };
+
+struct Op {
+  OpKind kind;
+  int layer = -1;            // index into layers
+  int src = -1, dst = -1;    // buffer ids (-1: network input / output)
+  int src_coff = 0, dst_coff = 0, c = 0;
+  int src_img0 = 0, dst_img0 = 0;   // image offsets in units of the plan batch B
+  int batch_mul = 1;         // op runs on batch_mul * B images
+  int level = 0;
+  int pool_mode = 0;
+  int src2 = -1;             // OP_MAXJOIN second operand image offset
+};
+
+struct Buf {
+  std::string name;
+  int level = 0, ctot = 0, batch_mul = 1;
+  size_t offset = 0;
+};
+
+struct Net {
+  int kind = 0, dims = 2, nf = 32, in_ch = 1, precision = 0, esz = 2;
+  int siam_mode = 0, use_interp = 0;
+  int levels = 4;
+  std::vector<int> head_channels;   // per head
+  std::vector<int> head_acts;       // per head
+  std::vector<std::string> head_names;
+  int head_total = 0;
+  std::map<std::string, HostTensor> params;
+  bool finalized = false;
+
+  std::vector<ConvLayer> layers;
+  std::vector<Buf> bufs;
+  std::vector<Op> ops;
+  float* head_w = nullptr;
+  float* head_b = nullptr;
+  std::vector<void*> dev_allocs;
+
+  // plan
+  int B = 0, D = 1, H = 0, W = 0;
+  size_t ws_bytes = 0;
+
+  int force_direct = 0;             // debugging: run every conv on the CUDA-core kernels
+};
+
+int net_build(Net* n);                       // program + layer table from kind/nf/...
+int net_finalize(Net* n);                    // fold, pack, upload
+long long net_plan(Net* n, int B, int D, int H, int W);   // returns workspace bytes, <0 on error
+int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out_val, uint8_t* out_u8,
+                void* workspace, cudaStream_t stream);
+int net_debug_copy(Net* n, const char* buf_name, void* workspace, void* dst_host, long long max_bytes);
+void net_destroy(Net* n);
+
+}  // namespace biu

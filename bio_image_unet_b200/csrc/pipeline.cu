@@ -1,0 +1,459 @@
+// HBM-bound kernels either side of the network: intensity histogram, percentile-normalisation LUT,
+// LUT application, tile gather and the three overlap stitches. All integer / byte work is bit-exact
+// with the reference's numpy code (citations per kernel).
+#include "common.cuh"
+#include "launch.h"
+
+namespace biu {
+
+// ------------------------------------------------------------------------------------------------
+// Histogram of integer intensities, one 65536-bin table per frame (uint8 input uses bins 0..255).
+// Feeds np.percentile / np.min / np.max of unet/predict.py:125-128 without sorting.
+// Per-block privatised sub-histogram in shared memory for the low 16K bins (where microscopy data
+// lives), global atomics for the rest; 128-bit loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHistBins = 65536;
+constexpr int kSmemBins = 8192;
+
+template <typename T>
+__global__ void __launch_bounds__(512) histogram_kernel(const T* __restrict__ img, long long n_per_frame,
+                                                         unsigned int* __restrict__ hist, int blocks_per_frame) {
+  __shared__ unsigned int sh[kSmemBins];
+  const int frame = blockIdx.x / blocks_per_frame;
+  const int blk = blockIdx.x % blocks_per_frame;
+  for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const T* src = img + (long long)frame * n_per_frame;
+  unsigned int* h = hist + (long long)frame * kHistBins;
+  constexpr int VEC = 16 / sizeof(T);
+  const long long nvec = n_per_frame / VEC;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (aligned) {
+    const uint4* v = reinterpret_cast<const uint4*>(src);
+    for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < nvec; i += (long long)blocks_per_frame * blockDim.x) {
+      uint4 q = __ldg(v + i);
+      const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const unsigned int b = e[k];
+        if (b < kSmemBins) atomicAdd(&sh[b], 1u); else atomicAdd(&h[b], 1u);
+      }
+    }
+    for (long long i = nvec * VEC + (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame;
+         i += (long long)blocks_per_frame * blockDim.x) {
+      const unsigned int b = src[i];
+      if (b < kSmemBins) atomicAdd(&sh[b], 1u); else atomicAdd(&h[b], 1u);
+    }
+  } else {
+    for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame;
+         i += (long long)blocks_per_frame * blockDim.x) {
+      const unsigned int b = src[i];
+      if (b < kSmemBins) atomicAdd(&sh[b], 1u); else atomicAdd(&h[b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x)
+    if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+int launch_histogram(const void* img, int dtype_bytes, long long n_per_frame, int frames, unsigned int* hist,
+                     cudaStream_t stream) {
+  BIU_REQUIRE(dtype_bytes == 1 || dtype_bytes == 2, "histogram: only uint8/uint16 input (got %d-byte)", dtype_bytes);
+  BIU_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)frames * kHistBins * sizeof(unsigned int), stream));
+  long long work = ceil_div_ll(n_per_frame, 512LL * 16);
+  int bpf = (int)(work < 1 ? 1 : (work > 592 ? 592 : work));
+  if (frames * bpf < 148) bpf = ceil_div(148, frames) < work ? ceil_div(148, frames) : (int)(work < 1 ? 1 : work);
+  if (dtype_bytes == 2)
+    histogram_kernel<uint16_t><<<frames * bpf, 512, 0, stream>>>((const uint16_t*)img, n_per_frame, hist, bpf);
+  else
+    histogram_kernel<uint8_t><<<frames * bpf, 512, 0, stream>>>((const uint8_t*)img, n_per_frame, hist, bpf);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void hist_sum_kernel(const unsigned int* __restrict__ hist, int frames, unsigned int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= kHistBins) return;
+  unsigned long long s = 0;
+  for (int f = 0; f < frames; ++f) s += hist[(long long)f * kHistBins + b];
+  // 'all' mode totals can exceed 2^32 pixels only above 4 Gpx per call; the LUT kernel takes 64-bit counts
+  // from a 2-word table in that case, not supported here.
+  out[b] = (unsigned int)s;
+}
+int launch_hist_sum(const unsigned int* hist, int frames, unsigned int* out, cudaStream_t stream) {
+  hist_sum_kernel<<<kHistBins / 256, 256, 0, stream>>>(hist, frames, out);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Percentile bounds + normalisation look-up table from a histogram, in float64 with numpy's exact
+// operation order (no FMA contraction):
+//   lo = np.nanpercentile(img, q_lo), hi = np.percentile(img, q_hi)      unet/predict.py:125-126
+//   img = clip(img, lo, hi); img = img - min(img); img = img / max(img) * 255; [255 - img]   :125-130
+//   stored back with a truncating cast (:131) and cast to uint8 at the split (:175-181).
+// np.percentile(method='linear'): virtual index (n-1)*(q/100); a + (b-a)*g, or b - (b-a)*(1-g) when g >= 0.5
+// (numpy/lib/_function_base_impl.py _quantile/_lerp).
+// One block per frame. params[f] = {lo, hi, mn, mx}.
+// ------------------------------------------------------------------------------------------------
+__device__ double percentile_from_hist(const unsigned long long* cum_sh, const unsigned int* hist, long long n,
+                                       double q) {
+  // cum_sh: inclusive prefix counts over 256 coarse groups of 256 bins (shared); fine search inside a group.
+  const double quant = __ddiv_rn(q, 100.0);
+  const double vi = __dmul_rn((double)(n - 1), quant);
+  long long prev = (long long)floor(vi);
+  long long next = prev + 1;
+  double gamma;
+  if (vi >= (double)(n - 1)) {
+    prev = n - 1; next = n - 1;
+    gamma = __dsub_rn(vi, -1.0);  // numpy subtracts the (already replaced) index -1; the lerp is between equal values
+  } else if (vi < 0.0) {
+    prev = 0; next = 0;
+    gamma = vi;
+  } else {
+    gamma = __dsub_rn(vi, (double)prev);
+  }
+  // value of the k-th order statistic = smallest bin v with cumulative count > k
+  auto kth = [&](long long k) -> int {
+    int g = 0;
+    while (g < 255 && (long long)cum_sh[g] <= k) ++g;
+    long long c = g == 0 ? 0 : (long long)cum_sh[g - 1];
+    int b = g * 256;
+    for (; b < g * 256 + 255; ++b) {
+      c += hist[b];
+      if (c > k) break;
+    }
+    return b;
+  };
+  const double a = (double)kth(prev);
+  const double b = (double)kth(next);
+  const double diff = __dsub_rn(b, a);
+  double r = __dadd_rn(a, __dmul_rn(diff, gamma));
+  if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  return r;
+}
+
+__global__ void __launch_bounds__(256) norm_lut_kernel(const unsigned int* __restrict__ hist_bounds,
+                                                        const unsigned int* __restrict__ hist_range,
+                                                        long long bounds_stride, long long range_stride, double q_lo,
+                                                        double q_hi, int invert, uint8_t* __restrict__ lut,
+                                                        double* __restrict__ params) {
+  __shared__ unsigned long long cum[256];
+  __shared__ double sp[4];
+  __shared__ int s_vmin, s_vmax;
+  const int f = blockIdx.x;
+  const unsigned int* hb = hist_bounds + (long long)f * bounds_stride;
+  const unsigned int* hr = hist_range + (long long)f * range_stride;
+  // coarse counts: thread t sums bins [256 t, 256 t + 256)
+  {
+    unsigned long long s = 0;
+    for (int i = 0; i < 256; ++i) s += hb[threadIdx.x * 256 + i];
+    cum[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) { s_vmin = kHistBins; s_vmax = -1; }
+  __syncthreads();
+  // value range of the data that will be normalised
+  {
+    int lo_b = kHistBins, hi_b = -1;
+    for (int i = 0; i < 256; ++i) {
+      const int b = threadIdx.x * 256 + i;
+      if (hr[b]) { if (b < lo_b) lo_b = b; if (b > hi_b) hi_b = b; }
+    }
+    if (hi_b >= 0) { atomicMin(&s_vmin, lo_b); atomicMax(&s_vmax, hi_b); }
+  }
+  if (threadIdx.x == 0) {
+    for (int g = 1; g < 256; ++g) cum[g] += cum[g - 1];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long n = (long long)cum[255];
+    const double lo = percentile_from_hist(cum, hb, n, q_lo);
+    const double hi = percentile_from_hist(cum, hb, n, q_hi);
+    // np.clip = minimum(maximum(x, lo), hi)
+    const double cmin = fmin(fmax((double)s_vmin, lo), hi);
+    const double cmax = fmin(fmax((double)s_vmax, lo), hi);
+    const double mn = cmin;
+    const double mx = __dsub_rn(cmax, mn);
+    sp[0] = lo; sp[1] = hi; sp[2] = mn; sp[3] = mx;
+    if (params) { params[f * 4 + 0] = lo; params[f * 4 + 1] = hi; params[f * 4 + 2] = mn; params[f * 4 + 3] = mx; }
+  }
+  __syncthreads();
+  const double lo = sp[0], hi = sp[1], mn = sp[2], mx = sp[3];
+  uint8_t* out = lut + (long long)f * kHistBins;
+  for (int v = threadIdx.x; v < kHistBins; v += blockDim.x) {
+    double x = fmin(fmax((double)v, lo), hi);
+    x = __dsub_rn(x, mn);
+    x = __dmul_rn(__ddiv_rn(x, mx), 255.0);
+    if (invert) x = __dsub_rn(255.0, x);
+    // truncating float64 -> integer cast; NaN (constant image) -> 0 like the x86 cast numpy performs
+    int q = (x == x) ? (int)x : 0;
+    out[v] = (uint8_t)q;
+  }
+}
+
+int launch_norm_lut(const unsigned int* hist_bounds, const unsigned int* hist_range, long long bounds_stride,
+                    long long range_stride, int frames, double q_lo, double q_hi, int invert, uint8_t* lut,
+                    double* params, cudaStream_t stream) {
+  norm_lut_kernel<<<frames, 256, 0, stream>>>(hist_bounds, hist_range, bounds_stride, range_stride, q_lo, q_hi,
+                                              invert, lut, params);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LUT application: uint8 out[i] = lut[frame][img[i]]. 16-byte loads, 8/16-byte stores.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) apply_lut_kernel(const T* __restrict__ img, long long n_per_frame,
+                                                         const uint8_t* __restrict__ lut, long long lut_stride,
+                                                         uint8_t* __restrict__ out, int blocks_per_frame) {
+  const int frame = blockIdx.x / blocks_per_frame;
+  const int blk = blockIdx.x % blocks_per_frame;
+  const T* src = img + (long long)frame * n_per_frame;
+  uint8_t* dst = out + (long long)frame * n_per_frame;
+  const uint8_t* l = lut + (long long)frame * lut_stride;
+  constexpr int VEC = 16 / sizeof(T);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  const long long nvec = aligned ? n_per_frame / VEC : 0;
+  const long long stride = (long long)blocks_per_frame * blockDim.x;
+  for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const T* e = reinterpret_cast<const T*>(&q);
+    uint8_t r[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r[k] = __ldg(l + e[k]);
+    if (VEC == 8) *reinterpret_cast<uint2*>(dst + i * VEC) = *reinterpret_cast<uint2*>(r);
+    else *reinterpret_cast<uint4*>(dst + i * VEC) = *reinterpret_cast<uint4*>(r);
+  }
+  for (long long i = nvec * VEC + (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame; i += stride)
+    dst[i] = __ldg(l + src[i]);
+}
+
+int launch_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
+                     long long lut_stride, uint8_t* out, cudaStream_t stream) {
+  BIU_REQUIRE(dtype_bytes == 1 || dtype_bytes == 2, "apply_lut: only uint8/uint16 input");
+  long long work = ceil_div_ll(n_per_frame, 256LL * 16 * 4);
+  int bpf = (int)(work < 1 ? 1 : (work > 1184 ? 1184 : work));
+  if (dtype_bytes == 2)
+    apply_lut_kernel<uint16_t><<<frames * bpf, 256, 0, stream>>>((const uint16_t*)img, n_per_frame, lut, lut_stride, out, bpf);
+  else
+    apply_lut_kernel<uint8_t><<<frames * bpf, 256, 0, stream>>>((const uint8_t*)img, n_per_frame, lut, lut_stride, out, bpf);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile gather (unet/predict.py:152-182, siam_unet/predict.py:164-197, unet3d/predict.py:119-153):
+// tile n = ((f*nz + iz)*ny + iy)*nx + ix copies src[f, zs[iz]:+pd, ys[iy]:+ph, xs[ix]:+pw]; sources
+// smaller than the tile are padded at the far end by reflection (np.pad 'reflect') or zeros ('constant').
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i < n ? i : period - i;
+}
+
+__global__ void __launch_bounds__(256) gather_tiles_kernel(GatherArgs a) {
+  const long long tile_elems = (long long)a.pd * a.ph * a.pw;
+  const long long total = (long long)a.F * a.nz * a.ny * a.nx * tile_elems;
+  for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; idx < total;
+       idx += (long long)gridDim.x * blockDim.x * 4) {
+    // 4 consecutive x (pw is a multiple of 4 for every supported tile size)
+    long long r = idx;
+    const int x = (int)(r % a.pw); r /= a.pw;
+    const int y = (int)(r % a.ph); r /= a.ph;
+    const int z = (int)(r % a.pd); r /= a.pd;
+    const int ix = (int)(r % a.nx); r /= a.nx;
+    const int iy = (int)(r % a.ny); r /= a.ny;
+    const int iz = (int)(r % a.nz); r /= a.nz;
+    const int f = (int)r;
+    int sz = a.zs[iz] + z, sy = a.ys[iy] + y;
+    bool zero = false;
+    if (sz >= a.Z) { if (a.pad_mode == 0) sz = reflect_index(sz, a.Z); else zero = true; }
+    if (sy >= a.H) { if (a.pad_mode == 0) sy = reflect_index(sy, a.H); else zero = true; }
+    const uint8_t* row = a.src + (((long long)f * a.Z + sz) * a.H + sy) * a.W;
+    uint8_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int sx = a.xs[ix] + x + k;
+      bool zk = zero;
+      if (sx >= a.W) { if (a.pad_mode == 0) sx = reflect_index(sx, a.W); else zk = true; }
+      v[k] = zk ? 0 : __ldg(row + sx);
+    }
+    *reinterpret_cast<uchar4*>(a.dst + idx) = make_uchar4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+int launch_gather_tiles(const GatherArgs& a, cudaStream_t stream) {
+  BIU_REQUIRE(a.pw % 4 == 0, "gather_tiles: tile width must be a multiple of 4 (got %d)", a.pw);
+  const long long total = (long long)a.F * a.nz * a.ny * a.nx * a.pd * a.ph * a.pw / 4;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  if (blocks < 1) blocks = 1;
+  gather_tiles_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2D overlap stitch (unet/predict.py:204-229, siam_unet/predict.py:217-240): nanmean over the tiles
+// covering a pixel followed by a truncating uint8 cast == integer sum // count (checked exhaustively
+// in tests). Gather formulation: one thread per 4 output pixels, no atomics, deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_mean_kernel(StitchMeanArgs a) {
+  const int W4 = (a.W + 3) / 4;
+  const long long total = (long long)a.F * a.C * a.H * W4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int x4 = (int)(r % W4) * 4; r /= W4;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int c = (int)(r % a.C); r /= a.C;
+    const int f = (int)r;
+    unsigned int sum[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+    for (int j = 0; j < a.ny; ++j) {
+      const int ty = y - a.ys[j];
+      if (ty < 0 || ty >= a.ph) continue;
+      for (int k = 0; k < a.nx; ++k) {
+        const int tx0 = x4 - a.xs[k];
+        if (tx0 <= -4 || tx0 >= a.pw) continue;
+        const uint8_t* t = a.tiles + ((((long long)f * a.ny + j) * a.nx + k) * a.C + c) * a.ph * a.pw + (long long)ty * a.pw;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int tx = tx0 + q;
+          if (tx >= 0 && tx < a.pw) { sum[q] += __ldg(t + tx); cnt[q] += 1; }
+        }
+      }
+    }
+    uint8_t* o = a.out + (((long long)f * a.C + c) * a.H + y) * a.W + x4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (x4 + q < a.W) o[q] = cnt[q] ? (uint8_t)(sum[q] / cnt[q]) : 0;  // uncovered -> nanmean of nothing = nan -> 0
+  }
+}
+int launch_stitch_mean(const StitchMeanArgs& a, cudaStream_t stream) {
+  const long long total = (long long)a.F * a.C * a.H * ((a.W + 3) / 4);
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  stitch_mean_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D stitch (unet3d/predict.py:173-195): patch n is written into slot n % 3 of a float16 NaN buffer,
+// later patches overwrite earlier ones in the same slot; result = trunc(nanmean over the 3 slots).
+// Gather formulation: per voxel and slot keep the covering patch with the largest n; mean of <= 3 integers
+// evaluated as float16(sum)/count in float16 then truncated (== numpy's float16 nanmean path).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_mod3_kernel(StitchMod3Args a) {
+  const long long total = (long long)a.Z * a.H * a.W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int z = (int)r;
+    int best_n[3] = {-1, -1, -1};
+    int best_v[3] = {0, 0, 0};
+    for (int i = 0; i < a.nz; ++i) {
+      const int tz = z - a.zs[i];
+      if (tz < 0 || tz >= a.pd) continue;
+      for (int j = 0; j < a.ny; ++j) {
+        const int ty = y - a.ys[j];
+        if (ty < 0 || ty >= a.ph) continue;
+        for (int k = 0; k < a.nx; ++k) {
+          const int tx = x - a.xs[k];
+          if (tx < 0 || tx >= a.pw) continue;
+          const int n = (i * a.ny + j) * a.nx + k;
+          const int s = n % 3;
+          if (n > best_n[s]) {
+            best_n[s] = n;
+            best_v[s] = __ldg(a.tiles + (((long long)n * a.pd + tz) * a.ph + ty) * a.pw + tx);
+          }
+        }
+      }
+    }
+    int sum = 0, cnt = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+      if (best_n[s] >= 0) { sum += best_v[s]; cnt += 1; }
+    a.out[idx] = cnt ? (uint8_t)(sum / cnt) : 0;
+  }
+}
+int launch_stitch_mod3(const StitchMod3Args& a, cudaStream_t stream) {
+  const long long total = (long long)a.Z * a.H * a.W;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  stitch_mod3_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-output 3D blend (multi_output_unet3d/predict.py:203-307, blend_margin rules as written):
+// weight starts at 1; z rule, then y rule, then x rule overwrite (not multiply); the "far side" ramps all
+// land on index 0 with final value (margin-1)/margin. Accumulation order = patch order z -> y -> x in fp32.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ramp_weight(int z, int y, int x, int iz, int iy, int ix, int nz, int ny, int nx,
+                                             int margin) {
+  float w = 1.0f;
+  const int mz = margin < nz ? margin : nz;   // :254 uses min(blend_margin, self.N_z) — patch COUNT, as written
+  if (iz > 0 && z < mz) w = (float)z / (float)margin;
+  if (iz < nz - 1 && z == 0 && mz > 0) w = (float)(mz - 1) / (float)margin;
+  if (iy > 0 && y < margin) w = (float)y / (float)margin;
+  if (iy < ny - 1 && y == 0) w = (float)(margin - 1) / (float)margin;
+  if (ix > 0 && x < margin) w = (float)x / (float)margin;
+  if (ix < nx - 1 && x == 0) w = (float)(margin - 1) / (float)margin;
+  return w;
+}
+
+__global__ void __launch_bounds__(256) stitch_ramp_kernel(StitchRampArgs a) {
+  const long long vol = (long long)a.Z * a.H * a.W;
+  const long long total = (long long)a.V * a.C * vol;
+  const long long pvol = (long long)a.pd * a.ph * a.pw;
+  const int npv = a.nz * a.ny * a.nx;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int z = (int)(r % a.Z); r /= a.Z;
+    const int c = (int)(r % a.C); r /= a.C;
+    const int v = (int)r;
+    float acc = 0.f, wsum = 0.f;
+    for (int i = 0; i < a.nz; ++i) {
+      const int tz = z - a.zs[i];
+      if (tz < 0 || tz >= a.pd) continue;
+      for (int j = 0; j < a.ny; ++j) {
+        const int ty = y - a.ys[j];
+        if (ty < 0 || ty >= a.ph) continue;
+        for (int k = 0; k < a.nx; ++k) {
+          const int tx = x - a.xs[k];
+          if (tx < 0 || tx >= a.pw) continue;
+          const float w = ramp_weight(tz, ty, tx, i, j, k, a.nz, a.ny, a.nx, a.margin);
+          const long long n = (long long)v * npv + (i * a.ny + j) * a.nx + k;
+          const float p = __ldg(a.tiles + (n * a.C + c) * pvol + ((long long)tz * a.ph + ty) * a.pw + tx);
+          acc = __fadd_rn(acc, __fmul_rn(p, w));
+          wsum = __fadd_rn(wsum, w);
+        }
+      }
+    }
+    a.out[idx] = wsum > 0.f ? __fdiv_rn(acc, wsum) : 0.f;
+  }
+}
+int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream) {
+  const long long total = (long long)a.V * a.C * a.Z * a.H * a.W;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  stitch_ramp_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace biu

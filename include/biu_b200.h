@@ -1,0 +1,131 @@
+/* biu_b200 — C-ABI of the B200-native tiled U-Net prediction engine.
+ *
+ * Drop-in boundary for the prediction path of danihae/bio-image-unet. The reference has no FFI: its seam is
+ * the Python call `self.model(patch)` plus the numpy pre/post-processing around it. Each entry point below
+ * names the reference code it replaces (paths relative to bio_image_unet/ in the reference, v1.1.1).
+ *
+ * Conventions
+ *   - every function returns 0 on success (biu_net_create returns NULL, biu_net_plan a negative value, on error);
+ *     biu_last_error() returns the message of the last failure on the calling thread;
+ *   - all data pointers are DEVICE pointers unless the parameter name ends in `_host`; nothing returned by the
+ *     library has to be freed by the caller except the handle (biu_net_destroy);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered on it;
+ *   - a handle is not thread-safe.
+ */
+#ifndef BIU_B200_H
+#define BIU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums ---------------------------------------------------------------------------------------------- */
+enum { BIU_NET_UNET2D = 0,   /* unet/unet.py:5 Unet */
+       BIU_NET_SIAM2D = 1,   /* siam_unet/siam_unet.py:7 Siam_UNet */
+       BIU_NET_UNET3D = 2,   /* unet3d/unet3d.py:6 UNet3D */
+       BIU_NET_MO3D   = 3 }; /* multi_output_unet3d/multi_output_unet3d.py:7 MultiOutputUnet3D */
+enum { BIU_PREC_BF16 = 0,    /* bf16 operands on tcgen05, fp32 accumulate */
+       BIU_PREC_TF32 = 1,    /* tf32 operands on tcgen05, fp32 storage */
+       BIU_PREC_FP32 = 2 };  /* fp32 CUDA-core kernels */
+enum { BIU_SIAM_CONCAT = 0, BIU_SIAM_MAX = 1, BIU_SIAM_CONTROL = 2, BIU_SIAM_CORR = 3 }; /* siam_unet.py:114-124 */
+enum { BIU_ACT_NONE = 0, BIU_ACT_SIGMOID = 1, BIU_ACT_TANH = 2, BIU_ACT_RELU = 3 };      /* multi_output_unet3d.py:97-104 */
+enum { BIU_PAD_REFLECT = 0,  /* unet/predict.py:163-168, unet3d/predict.py:134-137 */
+       BIU_PAD_ZERO = 1 };   /* siam_unet/predict.py:169-180 */
+enum { BIU_IN_U8 = 0,        /* uint8 tiles, converted as float32(u8)/255 (unet/predict.py:192) */
+       BIU_IN_F32 = 1 };     /* float32 patches (multi_output_unet3d/predict.py:185) */
+
+const char* biu_last_error(void);
+int biu_version(void);
+
+/* ---- network handle: replaces network(...).to(device); load_state_dict; eval; self.model(patch) -----------
+ * unet/predict.py:98-101,197  siam_unet/predict.py:73-76,211  unet3d/predict.py:84-88,166
+ * multi_output_unet3d/predict.py:55-62,192 */
+typedef struct biu_net biu_net;
+
+/* n_heads/head_channels/head_acts/head_names describe the output layer(s): one sigmoid head of `out_channels`
+ * channels for Unet/Siam_UNet/UNet3D, the output_heads dict for MultiOutputUnet3D.
+ * siam_mode: BIU_SIAM_*; use_interpolation: constructor flag of UNet3D / MultiOutputUnet3D. */
+biu_net* biu_net_create(int kind, int n_filter, int in_channels, int n_heads, const int* head_channels,
+                        const int* head_acts, const char* const* head_names, int siam_mode, int use_interpolation,
+                        int precision);
+/* One call per state_dict entry (same key, fp32, C-contiguous, HOST memory; copied). Unknown keys are kept and
+ * ignored; missing ones are reported by biu_net_finalize. */
+int biu_net_set_param(biu_net* net, const char* name, const float* data_host, int ndim, const long long* shape);
+/* Fold BatchNorm (eps 1e-5) into per-channel scale/shift, repack weights, upload. */
+int biu_net_finalize(biu_net* net);
+/* Fix the batch and tile extents (d = 1 for 2D). Returns the workspace size in bytes. Tile extents must be
+ * divisible by 16 (2D) / 8 (3D): the reference raises 'concatenation failed: wrong dimensions' (unet/unet.py:67). */
+long long biu_net_plan(biu_net* net, int batch, int d, int h, int w);
+/* Forward of `batch` tiles. in: planar [batch][in_channels][d][h][w] (uint8 or float32 per in_kind);
+ * in2: previous-frame tiles for Siam_UNet (else NULL). Outputs are planar [batch][sum(head_channels)][d][h][w]:
+ * out_val = activated head output (float32, may be NULL), out_u8 = trunc(out_val*255) (may be NULL;
+ * unet/predict.py:200). workspace: biu_net_plan bytes, zero-initialised once by the caller. */
+int biu_net_forward(biu_net* net, const void* in, int in_kind, const void* in2, float* out_val, uint8_t* out_u8,
+                    void* workspace, void* stream);
+/* Test hook: copy a named intermediate activation (e.g. "e1", "cat4", "mid2") to host memory. */
+int biu_net_debug_copy(biu_net* net, const char* name, void* workspace, void* dst_host, long long max_bytes);
+/* Test hook: 1 = run every convolution on the CUDA-core kernels. */
+int biu_net_set_force_direct(biu_net* net, int on);
+void biu_net_destroy(biu_net* net);
+
+/* ---- intensity normalisation: replaces Predict.__preprocess ------------------------------------------------
+ * unet/predict.py:122-150  siam_unet/predict.py:125-162  unet3d/predict.py:109-117 */
+/* hist[frames][65536] (uint32): per-frame histogram of a uint8 (dtype_bytes 1) or uint16 (2) stack. */
+int biu_histogram(const void* img, int dtype_bytes, long long n_per_frame, int frames, uint32_t* hist, void* stream);
+/* out[65536] = sum over frames ('all' mode, 3D global percentiles). */
+int biu_hist_sum(const uint32_t* hist, int frames, uint32_t* out, void* stream);
+/* Per frame f: percentile bounds (np.nanpercentile/np.percentile, linear) from hist_bounds + f*bounds_stride,
+ * value range from hist_range + f*range_stride, then lut[f][v] = uint8(trunc(((clip(v,lo,hi)-mn)/mx)*255))
+ * [255 - . when invert], all in float64 in numpy's operation order. params (may be NULL): [frames][4] doubles
+ * {lo, hi, mn, mx}. Strides are in uint32 elements (0 = share one histogram). */
+int biu_norm_lut(const uint32_t* hist_bounds, const uint32_t* hist_range, long long bounds_stride,
+                 long long range_stride, int frames, double q_lo, double q_hi, int invert, uint8_t* lut,
+                 double* params, void* stream);
+/* out[f][i] = lut[f*lut_stride + img[f][i]] */
+int biu_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
+                  long long lut_stride, uint8_t* out, void* stream);
+
+/* ---- tiling: replaces Predict.__split -----------------------------------------------------------------------
+ * unet/predict.py:152-182  siam_unet/predict.py:164-197  unet3d/predict.py:119-153
+ * src [F][Z][H][W] uint8 -> dst [F*nz*ny*nx][pd][ph][pw]; starts are device int32 arrays. */
+int biu_gather_tiles(const uint8_t* src, int F, int Z, int H, int W, int pad_mode, const int* zs, const int* ys,
+                     const int* xs, int nz, int ny, int nx, int pd, int ph, int pw, uint8_t* dst, void* stream);
+
+/* ---- stitching: replaces Predict.__stitch -------------------------------------------------------------------*/
+/* unet/predict.py:204-229, siam_unet/predict.py:217-240: uint8(nanmean) == sum // count.
+ * tiles [F][ny*nx][C][ph][pw] -> out [F][C][H][W] */
+int biu_stitch_mean_u8(const uint8_t* tiles, int F, int C, int H, int W, const int* ys, const int* xs, int ny, int nx,
+                       int ph, int pw, uint8_t* out, void* stream);
+/* unet3d/predict.py:173-195: three slots, patch n -> slot n % 3, last writer wins, nanmean, uint8. */
+int biu_stitch_mod3_u8(const uint8_t* tiles, int Z, int H, int W, const int* zs, const int* ys, const int* xs, int nz,
+                       int ny, int nx, int pd, int ph, int pw, uint8_t* out, void* stream);
+/* multi_output_unet3d/predict.py:203-307: ramp-weighted blend, tiles [V][nz*ny*nx][C][pd][ph][pw] float32. */
+int biu_stitch_ramp_f32(const float* tiles, int V, int C, int Z, int H, int W, const int* zs, const int* ys,
+                        const int* xs, int nz, int ny, int nx, int pd, int ph, int pw, int margin, float* out,
+                        void* stream);
+
+/* ---- single layers (used by the parity tests; same kernels the network handle launches) ------------------- */
+/* Conv(k in {1,3}, pad k/2) + per-channel scale/shift + LeakyReLU(slope) on tcgen05.
+ * esz 2: bf16 activations/weights, 4: fp32 storage / tf32 math. in: NDHWC with channel stride in_ctot, offset
+ * in_coff; wgt: [kd*kh*kw][cout][cin]; out: NDHWC (out_ctot/out_coff). */
+int biu_conv_tc(int esz, const void* in, int in_ctot, int in_coff, int cin, int B, int D, int H, int W, int kd,
+                int kh, int kw, const void* wgt, int cout, const float* scale, const float* shift, float slope,
+                void* out, int out_ctot, int out_coff, void* stream);
+/* ConvTranspose(k=2,s=2) + bias on tcgen05; wgt: [2^dims * cout][cin], row q*cout+co with q = (az,ay,ax) bits. */
+int biu_up_tc(int esz, const void* in, int in_ctot, int in_coff, int cin, int B, int D, int H, int W, int dims,
+              const void* wgt, int cout, const float* bias_rep, void* out, int out_ctot, int out_coff, void* stream);
+/* fp32 CUDA-core convolution, wgt fp32 [taps][cin][cout]. */
+int biu_conv_direct(int esz, const void* in, int in_ctot, int in_coff, int cin, int B, int D, int H, int W, int kd,
+                    int kh, int kw, const float* wgt, int cout, const float* scale, const float* shift, float slope,
+                    void* out, int out_ctot, int out_coff, void* stream);
+int biu_pool2(int esz, const void* in, int in_ctot, int in_coff, int c, int B, int D, int H, int W, int dims,
+              int mode, void* out, int out_ctot, int out_coff, void* stream);
+/* Device fault word written by a kernel whose pipeline wait timed out (0 = none). */
+int biu_device_fault(unsigned int* code_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIU_B200_H */
