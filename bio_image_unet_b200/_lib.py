@@ -43,6 +43,9 @@ SIGNATURES = {
     'biu_pool2': (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int,
                           _P]),
     'biu_device_fault': (c_int, [POINTER(c_uint)]),
+    'biu_launch_count': (ctypes.c_ulonglong, []),
+    'biu_net_set_profile': (c_int, [_P, c_int]),
+    'biu_net_profile_read': (c_int, [_P, c_int, POINTER(c_int), POINTER(c_float), POINTER(c_int)]),
 }
 
 _lib = None

@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+unsigned long long g_launch_count = 0;
 }  // namespace biu
 
 using namespace biu;
@@ -166,5 +167,15 @@ int biu_pool2(int esz, const void* in, int in_ctot, int in_coff, int c, int B, i
   return launch_pool2(a, (cudaStream_t)stream);
 }
 int biu_device_fault(unsigned int* code_host) { return read_device_fault(code_host); }
+unsigned long long biu_launch_count(void) { return g_launch_count; }
+int biu_net_set_profile(biu_net* net, int on) {
+  BIU_REQUIRE(net && net->n, "null handle");
+  net->n->profile = on;
+  return 0;
+}
+int biu_net_profile_read(biu_net* net, int max_ops, int* kinds, float* ms, int* n_ops) {
+  BIU_REQUIRE(net && net->n, "null handle");
+  return net_profile_read(net->n, max_ops, kinds, ms, n_ops);
+}
 
 }  // extern "C"

@@ -168,6 +168,7 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
     conv_tc_kernel<4><<<grid, 192, smem, stream>>>(tmA, tmB, p);
   }
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -115,6 +115,7 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
   else BIU_REQUIRE(false, "first_conv: bad in_kind/esz");
 #undef BIU_FC
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -173,6 +174,7 @@ int launch_pool2(const PoolArgs& a, cudaStream_t stream) {
   if (a.esz == 2) pool2_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);
   else pool2_kernel<float, 4><<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -211,6 +213,7 @@ int launch_up_nearest(const UpNearestArgs& a, cudaStream_t stream) {
   if (a.esz == 2) up_nearest_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);
   else up_nearest_kernel<float, 4><<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -251,6 +254,7 @@ int launch_head(const HeadArgs& a, cudaStream_t stream) {
   if (a.esz == 2) head_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>(a);
   else head_kernel<float><<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -348,6 +352,7 @@ int launch_direct_conv(const DirectConvArgs& a, cudaStream_t stream) {
   if (a.esz == 2) direct_conv_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(a);
   else direct_conv_kernel<float><<<grid, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -389,6 +394,7 @@ int launch_direct_up(const DirectUpArgs& a, cudaStream_t stream) {
   if (a.esz == 2) direct_up_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, stream>>>(a);
   else direct_up_kernel<float><<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

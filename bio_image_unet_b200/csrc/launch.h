@@ -5,6 +5,10 @@
 
 namespace biu {
 
+// number of kernel launches issued by this library since load (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
 // ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) -------------------------------------------------------------
 struct ConvTcArgs {
   int esz;                      // 2 = bf16 operands, 4 = tf32 operands (fp32 storage)

@@ -435,7 +435,20 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
   char* ws = reinterpret_cast<char*>(workspace);
   const bool tc_allowed = n->precision != PREC_FP32 && !n->force_direct;
   const int round_tf32 = n->precision == PREC_TF32 ? 1 : 0;
+  if (n->profile && n->events.size() < 2 * n->ops.size()) {
+    while (n->events.size() < 2 * n->ops.size()) {
+      cudaEvent_t e;
+      BIU_CHECK_CUDA(cudaEventCreate(&e));
+      n->events.push_back(e);
+    }
+  }
+  n->op_kinds.assign(n->ops.size(), 0);
+  int op_index = -1;
   for (const Op& o : n->ops) {
+    ++op_index;
+    if (n->profile && op_index > 0) BIU_CHECK_CUDA(cudaEventRecord(n->events[2 * op_index - 1], stream));
+    if (n->profile) BIU_CHECK_CUDA(cudaEventRecord(n->events[2 * op_index], stream));
+    n->op_kinds[op_index] = (int)o.kind;
     int d, h, w;
     level_dims(n, o.level, &d, &h, &w);
     const int batch = n->B * o.batch_mul;
@@ -483,7 +496,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         if (tc_allowed && L.w_tc && conv_tc_supported(a)) {
           if (int rc = launch_conv_tc(a, stream)) return rc;
         } else {
-          BIU_REQUIRE(!head || true, "unreachable");
+          n->op_kinds[op_index] += 16;
           DirectConvArgs da;
           memset(&da, 0, sizeof(da));
           da.esz = n->esz; da.in = src; da.in_ctot = sb->ctot; da.in_coff = o.src_coff; da.cin = L.cin_phys;
@@ -527,6 +540,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         if (tc_allowed && L.w_tc && conv_tc_supported(a)) {
           if (int rc = launch_conv_tc(a, stream)) return rc;
         } else {
+          n->op_kinds[op_index] += 16;
           DirectUpArgs da;
           memset(&da, 0, sizeof(da));
           da.esz = n->esz; da.in = src; da.in_ctot = sb->ctot; da.in_coff = o.src_coff; da.cin = L.cin_phys;
@@ -565,10 +579,24 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
                                                          reinterpret_cast<const uint4*>(ws + sb->offset + img * n->B),
                                                          reinterpret_cast<uint4*>(ws + db->offset), nvec, n->esz);
         BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
         break;
       }
     }
   }
+  if (n->profile && !n->ops.empty()) BIU_CHECK_CUDA(cudaEventRecord(n->events[2 * n->ops.size() - 1], stream));
+  return 0;
+}
+
+int net_profile_read(Net* n, int max_ops, int* kinds, float* ms, int* n_ops) {
+  BIU_REQUIRE(n->profile && n->events.size() >= 2 * n->ops.size(), "profiling was not enabled for the last forward");
+  const int cnt = (int)n->ops.size() < max_ops ? (int)n->ops.size() : max_ops;
+  for (int i = 0; i < cnt; ++i) {
+    BIU_CHECK_CUDA(cudaEventSynchronize(n->events[2 * i + 1]));
+    BIU_CHECK_CUDA(cudaEventElapsedTime(&ms[i], n->events[2 * i], n->events[2 * i + 1]));
+    kinds[i] = n->op_kinds[i];
+  }
+  *n_ops = cnt;
   return 0;
 }
 
@@ -588,6 +616,7 @@ int net_debug_copy(Net* n, const char* buf_name, void* workspace, void* dst_host
 
 void net_destroy(Net* n) {
   for (void* p : n->dev_allocs) cudaFree(p);
+  for (cudaEvent_t e : n->events) cudaEventDestroy(e);
   delete n;
 }
 

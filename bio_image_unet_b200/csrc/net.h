@@ -79,6 +79,9 @@ struct Net {
   size_t ws_bytes = 0;
 
   int force_direct = 0;             // debugging: run every conv on the CUDA-core kernels
+  int profile = 0;                  // bracket every op with CUDA events
+  std::vector<cudaEvent_t> events;  // 2 per op
+  std::vector<int> op_kinds;        // kind (+16 if it ran on the CUDA-core fallback) of the last forward
 };
 
 int net_build(Net* n);                       // program + layer table from kind/nf/...
@@ -87,6 +90,7 @@ long long net_plan(Net* n, int B, int D, int H, int W);   // returns workspace b
 int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out_val, uint8_t* out_u8,
                 void* workspace, cudaStream_t stream);
 int net_debug_copy(Net* n, const char* buf_name, void* workspace, void* dst_host, long long max_bytes);
+int net_profile_read(Net* n, int max_ops, int* kinds, float* ms, int* n_ops);
 void net_destroy(Net* n);
 
 }  // namespace biu

@@ -68,6 +68,7 @@ int launch_histogram(const void* img, int dtype_bytes, long long n_per_frame, in
   else
     histogram_kernel<uint8_t><<<frames * bpf, 512, 0, stream>>>((const uint8_t*)img, n_per_frame, hist, bpf);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -83,6 +84,7 @@ __global__ void hist_sum_kernel(const unsigned int* __restrict__ hist, int frame
 int launch_hist_sum(const unsigned int* hist, int frames, unsigned int* out, cudaStream_t stream) {
   hist_sum_kernel<<<kHistBins / 256, 256, 0, stream>>>(hist, frames, out);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -197,6 +199,7 @@ int launch_norm_lut(const unsigned int* hist_bounds, const unsigned int* hist_ra
   norm_lut_kernel<<<frames, 256, 0, stream>>>(hist_bounds, hist_range, bounds_stride, range_stride, q_lo, q_hi,
                                               invert, lut, params);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -239,6 +242,7 @@ int launch_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, in
   else
     apply_lut_kernel<uint8_t><<<frames * bpf, 256, 0, stream>>>((const uint8_t*)img, n_per_frame, lut, lut_stride, out, bpf);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -294,6 +298,7 @@ int launch_gather_tiles(const GatherArgs& a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   gather_tiles_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -340,6 +345,7 @@ int launch_stitch_mean(const StitchMeanArgs& a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   stitch_mean_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -391,6 +397,7 @@ int launch_stitch_mod3(const StitchMod3Args& a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   stitch_mod3_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 
@@ -453,6 +460,7 @@ int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   stitch_ramp_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

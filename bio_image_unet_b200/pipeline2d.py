@@ -1,0 +1,104 @@
+"""Device pipeline shared by the 2D predictors: normalise -> split -> batched forward -> stitch.
+
+Reference: unet/predict.py:115-229 (and the per-pair variant siam_unet/predict.py:125-240). All heavy steps run
+as CUDA kernels through the C-ABI; this module only sequences them and does the (tiny) index arithmetic.
+"""
+import numpy as np
+import torch
+
+from . import engine as E
+from . import tiling
+
+
+def to_device_stack(frames_np, device):
+    """(F, H, W) uint8/uint16 host array -> device tensor, through pinned staging."""
+    if frames_np.dtype not in (np.uint8, np.uint16):
+        raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got {frames_np.dtype}. '
+                        f'Convert the stack (e.g. to uint16) before calling Predict.')
+    host = torch.from_numpy(np.ascontiguousarray(frames_np))
+    try:
+        host = host.pin_memory()
+    except RuntimeError:
+        pass
+    return host.to(device, non_blocking=True)
+
+
+class Normalizer2D:
+    """Percentile normalisation of a (F, H, W) integer stack to uint8 on the device
+    (unet/predict.py:122-150). ``stats_reduce`` lets the multi-GPU driver all-reduce the stack-wide histogram."""
+
+    def __init__(self, mode, clip_threshold, invert, stats_reduce=None, first_frame_hist=None):
+        if mode not in ('single', 'first', 'all'):
+            raise ValueError(f'normalization_mode {mode} not valid!')
+        self.mode, self.clip, self.invert = mode, clip_threshold, invert
+        self.stats_reduce = stats_reduce
+        self.first_frame_hist = first_frame_hist
+        self.params = None
+
+    def __call__(self, frames_dev):
+        f = frames_dev.shape[0]
+        hist = E.histogram(frames_dev)
+        if self.mode == 'single':
+            lut, self.params = E.norm_lut(hist, hist, f, self.clip[0], self.clip[1], self.invert)
+        else:
+            total = E.hist_sum(hist)
+            if self.stats_reduce is not None:
+                total = self.stats_reduce(total)
+            if self.mode == 'all':
+                bounds = total
+            else:
+                bounds = self.first_frame_hist(hist) if self.first_frame_hist is not None else hist[0:1].contiguous()
+            lut, self.params = E.norm_lut(bounds, total, 1, self.clip[0], self.clip[1], self.invert)
+        return E.apply_lut(frames_dev, lut)
+
+
+def run_tiles(eng, tiles, tile_batch, prev_tiles=None, want_val=False):
+    """Forward all tiles in batches of the planned size (the tail batch is zero-padded)."""
+    n = tiles.shape[0]
+    outs_u8, outs_val = [], []
+    for s in range(0, n, tile_batch):
+        t = tiles[s:s + tile_batch]
+        p = None if prev_tiles is None else prev_tiles[s:s + tile_batch]
+        cnt = t.shape[0]
+        if cnt < tile_batch:
+            pad = torch.zeros((tile_batch - cnt, *t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat((t, pad))
+            if p is not None:
+                p = torch.cat((p, pad))
+        val, u8 = eng.forward(t.contiguous(), None if p is None else p.contiguous(), want_val=want_val, want_u8=True)
+        outs_u8.append(u8[:cnt])
+        if want_val:
+            outs_val.append(val[:cnt])
+    u8 = outs_u8[0] if len(outs_u8) == 1 else torch.cat(outs_u8)
+    val = None if not want_val else (outs_val[0] if len(outs_val) == 1 else torch.cat(outs_val))
+    return u8, val
+
+
+def pick_tile_batch(eng, tile, total_tiles, budget_bytes):
+    per_tile = eng.plan(1, tile)
+    batch = int(max(1, min(total_tiles, budget_bytes // max(per_tile, 1))))
+    eng.plan(batch, tile)
+    return batch
+
+
+def check_starts(starts, tile, extent):
+    """The reference wraps negative uint16 starts when an undersized image is split into more than one tile and
+    then fails on the slice assignment; report that as the same ValueError class up front."""
+    for s in starts:
+        if int(s) + tile > max(extent, tile):
+            raise ValueError(f'could not broadcast tile: start {int(s)} + tile {tile} exceeds extent {extent} '
+                             f'(image smaller than resize_dim with add_tile > 0)')
+
+
+def predict_frames_2d(eng, norm_u8, resize_dim, add_tile, out_channels, tile_batch, pad_mode=0):
+    """norm_u8: (F, H, W) uint8 device tensor (already normalised). Returns ((F, C, H, W) uint8 device tensor,
+    grid, tiles, result_tiles)."""
+    f, h, w = norm_u8.shape
+    th, tw = resize_dim
+    n_x, n_y, xs, ys = tiling.grid_2d(h, w, resize_dim, add_tile)
+    check_starts(xs, th, h)
+    check_starts(ys, tw, w)
+    tiles = E.gather_tiles(norm_u8.view(f, 1, h, w), [0], xs, ys, (1, th, tw), pad_mode)      # (F*N, 1, th, tw)
+    res_u8, _ = run_tiles(eng, tiles, tile_batch)
+    out = E.stitch_mean_u8(res_u8, f, out_channels, (h, w), xs, ys, (th, tw))
+    return out, (n_x, n_y, xs, ys), tiles, res_u8

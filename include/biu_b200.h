@@ -124,6 +124,14 @@ int biu_pool2(int esz, const void* in, int in_ctot, int in_coff, int c, int B, i
               int mode, void* out, int out_ctot, int out_coff, void* stream);
 /* Device fault word written by a kernel whose pipeline wait timed out (0 = none). */
 int biu_device_fault(unsigned int* code_host);
+/* Kernel launches issued by the library since it was loaded. */
+unsigned long long biu_launch_count(void);
+/* Measurement hooks: with profiling on, biu_net_forward brackets every layer with CUDA events on the caller's
+ * stream; biu_net_profile_read synchronises those events and returns, for the most recent forward, the op kind
+ * (0 first conv, 1 conv block [tcgen05], 2 conv block + head [tcgen05], 3 transposed conv [tcgen05], 4 pool,
+ * 5 nearest upsample, 6 max join; +16 when the op ran on the CUDA-core fallback) and its duration in ms. */
+int biu_net_set_profile(biu_net* net, int on);
+int biu_net_profile_read(biu_net* net, int max_ops, int* kinds, float* ms, int* n_ops);
 
 #ifdef __cplusplus
 }
