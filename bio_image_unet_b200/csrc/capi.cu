@@ -104,6 +104,20 @@ int biu_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int f
                   long long lut_stride, uint8_t* out, void* stream) {
   return launch_apply_lut(img, dtype_bytes, n_per_frame, frames, lut, lut_stride, out, (cudaStream_t)stream);
 }
+int biu_norm_lut_f32(const uint32_t* hist_bounds, const uint32_t* hist_range, long long bounds_stride,
+                     long long range_stride, int frames, double q_lo, double q_hi, int mode, float* lut,
+                     double* params, void* stream) {
+  return launch_norm_lut_f32(hist_bounds, hist_range, bounds_stride, range_stride, frames, q_lo, q_hi, mode, lut,
+                             params, (cudaStream_t)stream);
+}
+int biu_apply_lut_f32(const void* img, int dtype_bytes, long long n_per_frame, int frames, const float* lut,
+                      long long lut_stride, float* out, void* stream) {
+  return launch_apply_lut_f32(img, dtype_bytes, n_per_frame, frames, lut, lut_stride, out, (cudaStream_t)stream);
+}
+int biu_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int* zs, const int* ys, const int* xs,
+                         int nz, int ny, int nx, int pd, int ph, int pw, float* dst, void* stream) {
+  return launch_gather_tiles_f32(src, F, Z, H, W, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst, (cudaStream_t)stream);
+}
 int biu_gather_tiles(const uint8_t* src, int F, int Z, int H, int W, int pad_mode, const int* zs, const int* ys,
                      const int* xs, int nz, int ny, int nx, int pd, int ph, int pw, uint8_t* dst, void* stream) {
   GatherArgs a{src, F, Z, H, W, pad_mode, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst};

@@ -172,6 +172,13 @@ struct StitchRampArgs {         // multi_output_unet3d/predict.py:203-307
   float* out;                   // [V][C][Z][H][W]
 };
 int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream);
+int launch_norm_lut_f32(const unsigned int* hist_bounds, const unsigned int* hist_range, long long bounds_stride,
+                        long long range_stride, int frames, double q_lo, double q_hi, int mode, float* lut,
+                        double* params, cudaStream_t stream);
+int launch_apply_lut_f32(const void* img, int dtype_bytes, long long n_per_frame, int frames, const float* lut,
+                         long long lut_stride, float* out, cudaStream_t stream);
+int launch_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int* zs, const int* ys, const int* xs,
+                            int nz, int ny, int nx, int pd, int ph, int pw, float* dst, cudaStream_t stream);
 
 
 

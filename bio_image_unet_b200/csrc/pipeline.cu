@@ -465,3 +465,192 @@ int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace biu
+
+// ================================================================================================
+// Multi-output 3D variants (multi_output_unet3d/predict.py:104-125, 127-174): float32 normalisation
+// of an integer-valued stack and float32 patch gather.
+// ================================================================================================
+namespace biu {
+
+// np.percentile on a float32 array with a python-float q: quantile, virtual index, gamma and the lerp are float32.
+__device__ float percentile_from_hist_f32(const unsigned long long* cum_sh, const unsigned int* hist, long long n,
+                                          float q) {
+  const float quant = __fdiv_rn(q, 100.0f);
+  const float vi = __fmul_rn((float)(n - 1), quant);
+  long long prev = (long long)floorf(vi);
+  long long next = prev + 1;
+  float gamma;
+  if (vi >= (float)(n - 1)) {
+    prev = n - 1; next = n - 1;
+    gamma = __fsub_rn(vi, -1.0f);
+  } else if (vi < 0.0f) {
+    prev = 0; next = 0;
+    gamma = vi;
+  } else {
+    gamma = __fsub_rn(vi, (float)prev);
+  }
+  auto kth = [&](long long k) -> int {
+    int g = 0;
+    while (g < 255 && (long long)cum_sh[g] <= k) ++g;
+    long long c = g == 0 ? 0 : (long long)cum_sh[g - 1];
+    int b = g * 256;
+    for (; b < g * 256 + 255; ++b) {
+      c += hist[b];
+      if (c > k) break;
+    }
+    return b;
+  };
+  const float a = (float)kth(prev);
+  const float b = (float)kth(next);
+  const float diff = __fsub_rn(b, a);
+  float r = __fadd_rn(a, __fmul_rn(diff, gamma));
+  if (gamma >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, gamma)));
+  return r;
+}
+
+// lut[f][v] = float32 of the float64 expression the reference evaluates for a voxel of value v:
+//   mode 0 ('single'):      (clip(v, lo, hi) - min) / (ptp + 1e-8)         :108-112
+//   mode 1 ('first'/'all'): (clip(v, lo, hi) - lo) / (hi - lo + 1e-8)      :114-120
+// np.clip of the float32 stack with np.float64 bounds promotes to float64 (NEP 50), the store back into the
+// float32 stack rounds once.
+__global__ void __launch_bounds__(256) norm_lut_f32_kernel(const unsigned int* __restrict__ hist_bounds,
+                                                            const unsigned int* __restrict__ hist_range,
+                                                            long long bounds_stride, long long range_stride,
+                                                            double q_lo, double q_hi, int mode,
+                                                            float* __restrict__ lut, double* __restrict__ params) {
+  __shared__ unsigned long long cum[256];
+  __shared__ double sp[4];
+  __shared__ int s_vmin, s_vmax;
+  const int f = blockIdx.x;
+  const unsigned int* hb = hist_bounds + (long long)f * bounds_stride;
+  const unsigned int* hr = hist_range + (long long)f * range_stride;
+  {
+    unsigned long long s = 0;
+    for (int i = 0; i < 256; ++i) s += hb[threadIdx.x * 256 + i];
+    cum[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) { s_vmin = kHistBins; s_vmax = -1; }
+  __syncthreads();
+  {
+    int lo_b = kHistBins, hi_b = -1;
+    for (int i = 0; i < 256; ++i) {
+      const int b = threadIdx.x * 256 + i;
+      if (hr[b]) { if (b < lo_b) lo_b = b; if (b > hi_b) hi_b = b; }
+    }
+    if (hi_b >= 0) { atomicMin(&s_vmin, lo_b); atomicMax(&s_vmax, hi_b); }
+  }
+  if (threadIdx.x == 0)
+    for (int g = 1; g < 256; ++g) cum[g] += cum[g - 1];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long n = (long long)cum[255];
+    double lo, hi, sub, den;
+    if (mode == 0) {
+      // 'single' (:108-112): np.percentile(float32 array, python float) runs entirely in float32 (the quantile is
+      // divided by np.float32(100)), and so do the clip, min, ptp and the division.
+      const float lo_f = percentile_from_hist_f32(cum, hb, n, (float)q_lo);
+      const float hi_f = percentile_from_hist_f32(cum, hb, n, (float)q_hi);
+      const float cmin = fminf(fmaxf((float)s_vmin, lo_f), hi_f);
+      const float cmax = fminf(fmaxf((float)s_vmax, lo_f), hi_f);
+      lo = lo_f; hi = hi_f; sub = cmin;
+      den = __fadd_rn(__fsub_rn(cmax, cmin), 1e-8f);
+    } else {
+      lo = percentile_from_hist(cum, hb, n, q_lo);
+      hi = percentile_from_hist(cum, hb, n, q_hi);
+      sub = lo;
+      den = __dadd_rn(__dsub_rn(hi, lo), 1e-8);
+    }
+    sp[0] = lo; sp[1] = hi; sp[2] = sub; sp[3] = den;
+    if (params) { params[f * 4 + 0] = lo; params[f * 4 + 1] = hi; params[f * 4 + 2] = sub; params[f * 4 + 3] = den; }
+  }
+  __syncthreads();
+  const double lo = sp[0], hi = sp[1], sub = sp[2], den = sp[3];
+  float* out = lut + (long long)f * kHistBins;
+  for (int v = threadIdx.x; v < kHistBins; v += blockDim.x) {
+    if (mode == 0) {
+      const float x = fminf(fmaxf((float)v, (float)lo), (float)hi);
+      out[v] = __fdiv_rn(__fsub_rn(x, (float)sub), (float)den);
+    } else {
+      const double x = fmin(fmax((double)v, lo), hi);
+      out[v] = __double2float_rn(__ddiv_rn(__dsub_rn(x, sub), den));
+    }
+  }
+}
+
+int launch_norm_lut_f32(const unsigned int* hist_bounds, const unsigned int* hist_range, long long bounds_stride,
+                        long long range_stride, int frames, double q_lo, double q_hi, int mode, float* lut,
+                        double* params, cudaStream_t stream) {
+  norm_lut_f32_kernel<<<frames, 256, 0, stream>>>(hist_bounds, hist_range, bounds_stride, range_stride, q_lo, q_hi,
+                                                  mode, lut, params);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) apply_lut_f32_kernel(const T* __restrict__ img, long long n_per_frame,
+                                                             const float* __restrict__ lut, long long lut_stride,
+                                                             float* __restrict__ out, int blocks_per_frame) {
+  const int frame = blockIdx.x / blocks_per_frame;
+  const int blk = blockIdx.x % blocks_per_frame;
+  const T* src = img + (long long)frame * n_per_frame;
+  float* dst = out + (long long)frame * n_per_frame;
+  const float* l = lut + (long long)frame * lut_stride;
+  const long long stride = (long long)blocks_per_frame * blockDim.x;
+  const long long n4 = (((uintptr_t)src & 7) == 0 && ((uintptr_t)dst & 15) == 0) ? n_per_frame / 4 : 0;
+  for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    T e[4];
+    if (sizeof(T) == 2) *reinterpret_cast<uint2*>(e) = __ldg(reinterpret_cast<const uint2*>(src) + i);
+    else *reinterpret_cast<uint32_t*>(e) = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+    *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(__ldg(l + e[0]), __ldg(l + e[1]), __ldg(l + e[2]), __ldg(l + e[3]));
+  }
+  for (long long i = n4 * 4 + (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame; i += stride)
+    dst[i] = __ldg(l + src[i]);
+}
+
+int launch_apply_lut_f32(const void* img, int dtype_bytes, long long n_per_frame, int frames, const float* lut,
+                         long long lut_stride, float* out, cudaStream_t stream) {
+  BIU_REQUIRE(dtype_bytes == 1 || dtype_bytes == 2, "apply_lut_f32: only uint8/uint16 input");
+  long long work = ceil_div_ll(n_per_frame, 256LL * 4 * 4);
+  int bpf = (int)(work < 1 ? 1 : (work > 1184 ? 1184 : work));
+  if (dtype_bytes == 2)
+    apply_lut_f32_kernel<uint16_t><<<frames * bpf, 256, 0, stream>>>((const uint16_t*)img, n_per_frame, lut, lut_stride, out, bpf);
+  else
+    apply_lut_f32_kernel<uint8_t><<<frames * bpf, 256, 0, stream>>>((const uint8_t*)img, n_per_frame, lut, lut_stride, out, bpf);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// float32 patch gather, patches always inside the volume (patch = min(volume, max_patch), :129-131)
+__global__ void __launch_bounds__(256) gather_tiles_f32_kernel(const float* __restrict__ src, int F, int Z, int H, int W,
+                                                               const int* __restrict__ zs, const int* __restrict__ ys,
+                                                               const int* __restrict__ xs, int nz, int ny, int nx, int pd,
+                                                               int ph, int pw, float* __restrict__ dst) {
+  const long long total = (long long)F * nz * ny * nx * pd * ph * pw;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int x = (int)(r % pw); r /= pw;
+    const int y = (int)(r % ph); r /= ph;
+    const int z = (int)(r % pd); r /= pd;
+    const int ix = (int)(r % nx); r /= nx;
+    const int iy = (int)(r % ny); r /= ny;
+    const int iz = (int)(r % nz); r /= nz;
+    const int f = (int)r;
+    dst[idx] = __ldg(src + (((long long)f * Z + zs[iz] + z) * H + ys[iy] + y) * W + xs[ix] + x);
+  }
+}
+int launch_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int* zs, const int* ys, const int* xs,
+                            int nz, int ny, int nx, int pd, int ph, int pw, float* dst, cudaStream_t stream) {
+  const long long total = (long long)F * nz * ny * nx * pd * ph * pw;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  gather_tiles_f32_kernel<<<(int)blocks, 256, 0, stream>>>(src, F, Z, H, W, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace biu

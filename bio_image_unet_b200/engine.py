@@ -244,3 +244,43 @@ def stitch_ramp_f32(tiles, vols, channels, out_zhw, zs, ys, xs, tile, margin=16)
                                            tile[0], tile[1], tile[2], int(margin), _lib.ptr(out), _lib.stream_ptr()),
                    'biu_stitch_ramp_f32')
     return out
+
+
+def norm_lut_f32(hist_bounds, hist_range, frames, q_lo, q_hi, mode):
+    """float32 LUTs (frames, 65536) of multi_output_unet3d's normalisation; mode 0 'single', 1 'first'/'all'."""
+    lib = _lib.load()
+    dev = hist_bounds.device
+    lut = torch.empty((frames, HIST_BINS), dtype=torch.float32, device=dev)
+    params = torch.empty((frames, 4), dtype=torch.float64, device=dev)
+    bs = HIST_BINS if hist_bounds.shape[0] > 1 else 0
+    rs = HIST_BINS if hist_range.shape[0] > 1 else 0
+    with torch.cuda.device(dev):
+        _lib.check(lib.biu_norm_lut_f32(_lib.ptr(hist_bounds), _lib.ptr(hist_range), bs, rs, frames, float(q_lo),
+                                        float(q_hi), int(mode), _lib.ptr(lut), _lib.ptr(params), _lib.stream_ptr()),
+                   'biu_norm_lut_f32')
+    return lut, params
+
+
+def apply_lut_f32(frames, lut):
+    lib = _lib.load()
+    out = torch.empty(frames.shape, dtype=torch.float32, device=frames.device)
+    stride = HIST_BINS if lut.shape[0] > 1 else 0
+    with torch.cuda.device(frames.device):
+        _lib.check(lib.biu_apply_lut_f32(_lib.ptr(frames), frames.element_size(), frames[0].numel(), frames.shape[0],
+                                         _lib.ptr(lut), stride, _lib.ptr(out), _lib.stream_ptr()), 'biu_apply_lut_f32')
+    return out
+
+
+def gather_tiles_f32(src, zs, ys, xs, tile):
+    """src (F, Z, H, W) float32 -> (F*nz*ny*nx, pd, ph, pw) float32 (patches lie inside the volume)."""
+    lib = _lib.load()
+    f, z, h, w = src.shape
+    pd, ph, pw = tile
+    dev = src.device
+    dzs, dys, dxs = _dev_i32(zs, dev), _dev_i32(ys, dev), _dev_i32(xs, dev)
+    out = torch.empty((f * len(zs) * len(ys) * len(xs), pd, ph, pw), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.biu_gather_tiles_f32(_lib.ptr(src), f, z, h, w, _lib.ptr(dzs), _lib.ptr(dys), _lib.ptr(dxs),
+                                            len(zs), len(ys), len(xs), pd, ph, pw, _lib.ptr(out), _lib.stream_ptr()),
+                   'biu_gather_tiles_f32')
+    return out

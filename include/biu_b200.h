@@ -87,6 +87,17 @@ int biu_norm_lut(const uint32_t* hist_bounds, const uint32_t* hist_range, long l
 int biu_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
                   long long lut_stride, uint8_t* out, void* stream);
 
+/* multi_output_unet3d/predict.py:104-125 on an integer-valued stack: float32 LUT of the float64 expression
+ * (clip(v,lo,hi) - min) / (ptp + 1e-8) [mode 0, 'single'] or (clip(v,lo,hi) - lo) / (hi - lo + 1e-8) [mode 1]. */
+int biu_norm_lut_f32(const uint32_t* hist_bounds, const uint32_t* hist_range, long long bounds_stride,
+                     long long range_stride, int frames, double q_lo, double q_hi, int mode, float* lut,
+                     double* params, void* stream);
+int biu_apply_lut_f32(const void* img, int dtype_bytes, long long n_per_frame, int frames, const float* lut,
+                      long long lut_stride, float* out, void* stream);
+/* multi_output_unet3d/predict.py:127-174: float32 patches, src [F][Z][H][W] -> dst [F*nz*ny*nx][pd][ph][pw]. */
+int biu_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int* zs, const int* ys, const int* xs,
+                         int nz, int ny, int nx, int pd, int ph, int pw, float* dst, void* stream);
+
 /* ---- tiling: replaces Predict.__split -----------------------------------------------------------------------
  * unet/predict.py:152-182  siam_unet/predict.py:164-197  unet3d/predict.py:119-153
  * src [F][Z][H][W] uint8 -> dst [F*nz*ny*nx][pd][ph][pw]; starts are device int32 arrays. */

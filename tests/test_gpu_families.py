@@ -1,0 +1,170 @@
+"""GPU parity of the Siamese, 3D and multi-output 3D predictors against the golden fixtures produced by the
+unmodified reference, plus bit-exactness of the 3D / ramp stitch kernels against the CPU oracle.
+
+Integer stages (tile indices, uint8 / float32 tiles, stitches) are bit-exact. The network forward is compared in
+the exact-fp32 mode at +-1 LSB of the reference's uint8 quantisation (float heads: 2e-4), and in the tf32 / bf16
+tensor-core modes within the bounds their arithmetic allows on these stress-initialised nets (see test_gpu_unet).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as opipe
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+
+LSB = {'fp32': 1, 'tf32': 4, 'bf16': 25}
+LSB_SIAM = {'fp32': 1, 'tf32': 10, 'bf16': 70}     # measured 7 / 61 on the siam_concat net (23 + 9 layers, logit sigma ~ 8)
+FLOAT_TOL = {'fp32': 2e-4, 'tf32': 2e-2, 'bf16': 1.5e-1}
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('name', ['siam_concat', 'siam_max', 'siam_control_small'])
+def test_siam_predict_matches_reference_golden(name, precision, tmp_path):
+    from bio_image_unet_b200 import tiff
+    from bio_image_unet_b200.siam_unet import Predict
+    g = _golden.load(name)
+    ckpt = str(tmp_path / 'model.pt')
+    torch.save({'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'mode': str(g['siam_mode'])}, ckpt)
+    movie_file = str(tmp_path / 'movie.tif')
+    tiff.imwrite(movie_file, g['movie'])
+    res_file = str(tmp_path / 'res.tif')
+    p = Predict(movie_file, res_file, ckpt, resize_dim=tuple(int(v) for v in g['resize_dim']),
+                normalization_mode=str(g['norm_mode']), clip_threshold=tuple(g['clip']), add_tile=int(g['add_tile']),
+                show_progress=False, device='cuda:0', precision=precision, keep_intermediates=True)
+    assert (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
+    assert np.array_equal(p.X_start, g['X_start']) and np.array_equal(p.Y_start, g['Y_start'])
+    assert np.array_equal(p.patches, g['patches'])                    # (T, N, 2, th, tw): ch0 current, ch1 previous
+    d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
+    assert d.max() <= LSB_SIAM[precision], d.max()
+    assert (d > 1).mean() < {'fp32': 1e-9, 'tf32': 0.02, 'bf16': 0.3}[precision]
+    out = tiff.imread(res_file)
+    assert out.dtype == np.uint8 and out.shape == g['result'].shape
+    assert np.abs(out.astype(np.int16) - g['result'].astype(np.int16)).max() <= LSB_SIAM[precision]
+    # stitch exact from the engine's own tiles
+    grid = (p.N_x, p.N_y, p.X_start, p.Y_start)
+    for t in range(out.shape[0]):
+        st = opipe.stitch_mean_2d(p.result_patches[t], 1, g['movie'].shape[1:], tuple(int(v) for v in g['resize_dim']), grid)
+        assert np.array_equal(out[t], st)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('name', ['unet3d_overlap', 'unet3d_disjoint'])
+def test_unet3d_predict_matches_reference_golden(name, precision, tmp_path):
+    from bio_image_unet_b200 import tiff
+    from bio_image_unet_b200.unet3d import Predict
+    g = _golden.load(name)
+    ckpt = str(tmp_path / 'model.pt')
+    torch.save({'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1,
+                'out_channels': 1}, ckpt)
+    res_file = str(tmp_path / 'res.tif')
+    rd = tuple(int(v) for v in g['resize_dim'])
+    p = Predict(g['vol'].copy(), res_file, ckpt, resize_dim=rd, clip_threshold=tuple(g['clip']),
+                add_patch=int(g['add_patch']), progress_bar=False, device='cuda:0', precision=precision,
+                keep_intermediates=True)
+    assert (p.N_z, p.N_x, p.N_y) == (int(g['N_z']), int(g['N_x']), int(g['N_y']))
+    for a, b in ((p.Z_start, g['Z_start']), (p.X_start, g['X_start']), (p.Y_start, g['Y_start'])):
+        assert np.array_equal(a, b) and a.dtype == np.uint16
+    assert np.array_equal(p.patches, g['patches'])
+    d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
+    assert d.max() <= LSB[precision], d.max()
+    out = tiff.imread(res_file)
+    assert out.dtype == np.float16
+    grid = (p.N_z, p.N_x, p.N_y, p.Z_start, p.X_start, p.Y_start)
+    assert np.array_equal(out, opipe.stitch_mod3(p.result_patches, g['vol'].shape, rd, grid).astype('float16'))
+    assert np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= LSB[precision]
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('name', ['mo3d_interp', 'mo3d_convt'])
+def test_mo3d_predict_matches_reference_golden(name, precision, tmp_path):
+    from bio_image_unet_b200.multi_output_unet3d import Predict
+    g = _golden.load(name)
+    ckpt = str(tmp_path / 'model.pt')
+    torch.save({'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1,
+                'output_heads': _golden.MO3D_HEADS, 'use_interpolation': bool(g['interp'])}, ckpt)
+    p = Predict(g['imgs'].copy(), ckpt, result_path=None, max_patch_size=tuple(int(v) for v in g['max_patch']),
+                overlap_factor=float(g['overlap']), batch_size=2, normalization_mode=str(g['norm_mode']),
+                clip_threshold=tuple(g['clip']), show_progress=False, device='cuda:0', precision=precision,
+                keep_intermediates=True)
+    assert p.patch_size == tuple(int(v) for v in g['patch_size'])
+    assert list(p.Z_start) == list(g['Z_start']) and list(p.Y_start) == list(g['Y_start']) and list(p.X_start) == list(g['X_start'])
+    assert np.array_equal(p.patches, g['patches'])          # float32 normalisation + patch gather: bit-exact
+    ref = _golden.sub(g, 'result')
+    assert list(p.result.keys()) == list(_golden.MO3D_HEADS.keys())
+    for k in ref:
+        assert p.result[k].shape == ref[k].shape
+        err = np.abs(p.result[k] - ref[k]).max()
+        assert err <= FLOAT_TOL[precision], (k, err)
+
+
+def test_norm_f32_single_mode_bit_exact():
+    from bio_image_unet_b200 import engine as E
+    rng = np.random.default_rng(8)
+    vols = rng.integers(0, 3000, (3, 6, 20, 24)).astype('uint16')
+    vols[1] = (rng.normal(500, 60, vols[1].shape).clip(0, 65535)).astype('uint16')
+    for mode in ('single', 'first', 'all'):
+        for clip in ((0., 99.98), (1., 99.)):
+            ref = opipe.mo3d_preprocess(vols.astype('float32'), mode, clip)
+            dev = torch.from_numpy(vols).cuda().reshape(3, -1)
+            hist = E.histogram(dev)
+            if mode == 'single':
+                lut, _ = E.norm_lut_f32(hist, hist, 3, clip[0], clip[1], 0)
+            else:
+                b = E.hist_sum(hist) if mode == 'all' else hist[0:1].contiguous()
+                lut, _ = E.norm_lut_f32(b, b, 1, clip[0], clip[1], 1)
+            got = E.apply_lut_f32(dev, lut).cpu().numpy().reshape(vols.shape)
+            assert np.array_equal(got, ref), (mode, clip, np.abs(got - ref).max())
+
+
+def test_stitch_mod3_bit_exact():
+    from bio_image_unet_b200 import engine as E
+    from bio_image_unet_b200 import tiling
+    rng = np.random.default_rng(5)
+    for vol_shape, rd, add in [((12, 40, 40), (8, 16, 16), 1), ((16, 32, 32), (8, 16, 16), 0), ((8, 24, 24), (8, 16, 16), 1),
+                               ((5, 20, 36), (8, 16, 16), 0), ((20, 33, 47), (8, 16, 16), 2)]:
+        grid = tiling.grid_3d(vol_shape, rd, add)
+        n = grid[0] * grid[1] * grid[2]
+        tiles = rng.integers(0, 256, (n, *rd)).astype('uint8')
+        ref = opipe.stitch_mod3(tiles, vol_shape, rd, grid)
+        got = E.stitch_mod3_u8(torch.from_numpy(tiles).cuda(), vol_shape, grid[3], grid[4], grid[5], rd).cpu().numpy()
+        assert np.array_equal(np.squeeze(got), ref), (vol_shape, rd, add)
+
+
+def test_stitch_ramp_bit_exact():
+    from bio_image_unet_b200 import engine as E
+    from bio_image_unet_b200 import tiling
+    rng = np.random.default_rng(6)
+    for shape, max_patch, ov, c in [((2, 12, 40, 40), (8, 32, 32), 0.25, 2), ((1, 20, 24, 24), (8, 16, 16), 0.1, 1),
+                                    ((1, 24, 50, 70), (8, 32, 32), 0.5, 3), ((1, 6, 30, 30), (8, 32, 32), 0.1, 1)]:
+        ps = tuple(min(a, b) for a, b in zip(shape[1:], max_patch))
+        zs, ys, xs = (tiling.strided_starts(shape[i + 1], ps[i], ov) for i in range(3))
+        n = shape[0] * len(zs) * len(ys) * len(xs)
+        tiles = rng.normal(0, 1, (n, c, *ps)).astype('float32')
+        ref = opipe.mo3d_stitch(tiles, shape, (ps, zs, ys, xs)).reshape(shape[0], c, *shape[1:])
+        got = E.stitch_ramp_f32(torch.from_numpy(tiles).cuda(), shape[0], c, shape[1:], zs, ys, xs, ps).cpu().numpy()
+        assert np.array_equal(got, ref), (shape, np.abs(got - ref).max())
+
+
+def test_modules_eval_forward_on_gpu():
+    """nn.Module surface: eval-mode CUDA forward goes through the engine; CPU eval raises (no CPU fallback)."""
+    from bio_image_unet_b200.siam_unet import Siam_UNet
+    from bio_image_unet_b200.unet import Unet
+    from oracle import models as om
+    torch.manual_seed(3)
+    m = Unet(n_filter=8).eval()
+    m.precision = 'fp32'
+    x = torch.rand(2, 1, 32, 32)
+    with torch.no_grad():
+        ref, ref_logits = om.unet_forward(m.state_dict(), x)
+        with pytest.raises(RuntimeError):
+            m(x)
+        sig, logits = m.cuda()(x.cuda())
+    assert (logits.cpu() - ref_logits).abs().max() < 1e-4 and (sig.cpu() - ref).abs().max() < 1e-4
+    s = Siam_UNet(n_filter=8, mode='concat').eval().cuda()
+    s.precision = 'fp32'
+    with torch.no_grad():
+        ref, _ = om.siam_forward({k: v.cpu() for k, v in s.state_dict().items()}, x, x.flip(0), 'concat')
+        sig, _ = s(x.cuda(), x.flip(0).cuda())
+    assert (sig.cpu() - ref).abs().max() < 1e-4
