@@ -1,7 +1,9 @@
 // Host-side launcher for the tcgen05 implicit-GEMM convolution: builds the TMA tensor maps for the
 // activation tensor and the packed weights, picks the pixel box / pipeline depth, launches.
 #include "conv_tc.cuh"
+#include "conv_halo.cuh"
 #include "launch.h"
+#include <cstdlib>
 
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -101,6 +103,111 @@ bool conv_tc_supported(const ConvTcArgs& a) {
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Halo-tile kernel (conv_halo.cuh): eligibility, tiling choice and launch
+// ---------------------------------------------------------------------------------------------------------------
+static bool halo_disabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BIU_CONV_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+struct HaloPlan { int mt, a_bufs, b_stages, ck; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
+
+static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
+  HaloPlan pl{};
+  pl.ok = false;
+  if (halo_disabled() || a.mode == EPI_UP || a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return pl;
+  if (a.H < 16 || a.W < 8) return pl;                      // tiny planes: the per-tap kernel packs the batch instead
+  if (n_blk > 256) return pl;
+  const int budget = 224 * 1024;
+  const int taps = 9 * a.kd;
+  const int ck0 = pick_ck(a.cin, a.esz);
+  for (int ck = ck0; ck >= 32 / a.esz; ck >>= 1) {
+    if (a.cin % ck) continue;
+    const int rb = ck * a.esz;
+    const int chunks = a.cin / ck;
+    int mt_max = 256 / n_blk;                              // two accumulator stages of mt * n_blk TMEM columns
+    if (mt_max > 8) mt_max = 8;
+    const int w8 = (a.W + 7) / 8;
+    if (mt_max > w8) mt_max = w8;
+    for (int mt = mt_max; mt >= 1; --mt) {
+      if (mt != mt_max && (mt & (mt - 1))) continue;       // after the first try only powers of two
+      const uint32_t halo = ((uint32_t)(a.kd * kHaloRows * (8 * mt + 2) * rb) + 1023u) & ~1023u;
+      const uint32_t bst = ((uint32_t)(n_blk * rb) + 1023u) & ~1023u;
+      for (int abufs = 2; abufs >= 1; --abufs) {
+        int stages = (budget - (int)(abufs * halo) - 2048) / (int)bst;
+        if (stages > kMaxBStages) stages = kMaxBStages;
+        if (stages > taps * chunks) stages = taps * chunks;
+        if (stages >= (abufs == 2 ? 3 : 2)) {
+          pl.mt = mt; pl.a_bufs = abufs; pl.b_stages = stages; pl.ck = ck;
+          pl.a_buf_bytes = halo; pl.b_stage_bytes = bst;
+          pl.smem = (int)(abufs * halo + stages * bst) + 1024;
+          pl.ok = true;
+          return pl;
+        }
+      }
+    }
+  }
+  return pl;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, cudaStream_t stream) {
+  ConvHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
+  p.mt = pl.mt;
+  p.tiles_x = ceil_div(a.W, 8 * pl.mt);
+  p.tiles_y = ceil_div(a.H, 16);
+  p.n_blocks = a.n_total / n_blk;
+  p.total_tiles = p.tiles_x * p.tiles_y * a.D * a.B * p.n_blocks;
+  p.kd = a.kd;
+  p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
+  p.n_blk = n_blk;
+  p.a_bufs = pl.a_bufs; p.b_stages = pl.b_stages; p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
+  p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out; p.out_ctot = a.out_ctot; p.out_coff = a.out_coff;
+  p.head_n = a.head_n; p.head_w = a.head_w; p.head_b = a.head_b;
+  for (int i = 0; i < kMaxHead; ++i) p.head_act[i] = a.head_act[i];
+  p.out_val = a.out_val; p.out_u8 = a.out_u8;
+
+  CUtensorMap tmA, tmB;
+  const char* in_base = reinterpret_cast<const char*>(a.in) + (size_t)a.in_coff * a.esz;
+  if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, 8 * pl.mt + 2, 2, 1, 1))
+    return rc;
+  if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, 9 * a.kd, pl.ck, n_blk)) return rc;
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  if (a.esz == 2) {
+    static int max_set = 0;
+    if (pl.smem > max_set) {
+      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+      max_set = pl.smem;
+    }
+    conv_halo_kernel<2><<<grid, kHaloThreads, pl.smem, stream>>>(tmA, tmB, p);
+  } else {
+    static int max_set = 0;
+    if (pl.smem > max_set) {
+      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
+      max_set = pl.smem;
+    }
+    conv_halo_kernel<4><<<grid, kHaloThreads, pl.smem, stream>>>(tmA, tmB, p);
+  }
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(conv_tc_supported(a), "conv_tc: unsupported configuration (cin=%d n=%d esz=%d mode=%d)", a.cin,
               a.n_total, a.esz, a.mode);
@@ -123,6 +230,10 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
     while (a.n_total % n_blk != 0) n_blk -= 16;
   }
   if (a.mode == EPI_UP && n_blk > a.up_cout && n_blk % a.up_cout != 0) n_blk = a.up_cout;
+  {
+    const HaloPlan pl = plan_halo(a, n_blk);
+    if (pl.ok) return launch_conv_halo(a, n_blk, pl, stream);
+  }
   p.n_blk = n_blk;
   p.mode = a.mode;
   p.slope = a.slope;

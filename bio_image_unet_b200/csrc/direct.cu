@@ -91,6 +91,90 @@ __global__ void __launch_bounds__(256) first_conv_kernel(FirstConvArgs a) {
   }
 }
 
+// Fast path for a single input channel (every reference model): one thread per pixel gathers the 9 / 27 taps once
+// into registers, then produces all output channels 8 at a time (broadcast weight reads from shared memory,
+// 16-byte stores; a warp writes 32 consecutive pixels = one contiguous run of the NHWC buffer).
+template <typename TIN, typename TOUT, int TAPS>
+__global__ void __launch_bounds__(256) first_conv1_kernel(FirstConvArgs a) {
+  extern __shared__ float sw[];  // [TAPS][cout_pad], scale[cout_pad], shift[cout_pad]
+  float* s_scale = sw + TAPS * a.cout_pad;
+  float* s_shift = s_scale + a.cout_pad;
+  for (int i = threadIdx.x; i < TAPS * a.cout_pad; i += blockDim.x) {
+    const int co = i % a.cout_pad, k = i / a.cout_pad;
+    sw[i] = co < a.cout ? a.wgt[k * a.cout + co] : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.cout_pad; i += blockDim.x) {
+    s_scale[i] = i < a.cout ? a.scale[i] : 0.f;
+    s_shift[i] = i < a.cout ? a.shift[i] : 0.f;
+  }
+  __syncthreads();
+  const long long npix = (long long)a.B * a.D * a.H * a.W;
+  const long long plane = (long long)a.D * a.H * a.W;
+  const TIN* in = reinterpret_cast<const TIN*>(a.in);
+  TOUT* out = reinterpret_cast<TOUT*>(a.out);
+  constexpr int KD = TAPS / 9;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (long long)gridDim.x * blockDim.x) {
+    long long r = pix;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int z = (int)(r % a.D); r /= a.D;
+    const TIN* img = in + r * plane;
+    float v[TAPS];
+#pragma unroll
+    for (int dz = 0; dz < KD; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int zz = z + dz - (KD >> 1), yy = y + dy - 1, xx = x + dx - 1;
+          float t = 0.f;
+          if (zz >= 0 && zz < a.D && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+            const TIN raw = __ldg(img + ((long long)zz * a.H + yy) * a.W + xx);
+            t = sizeof(TIN) == 1 ? __fdiv_rn((float)raw, 255.0f) : (float)raw;
+          }
+          v[(dz * 3 + dy) * 3 + dx] = t;
+        }
+    TOUT* o = out + pix * a.out_ctot + a.out_coff;
+    for (int g = 0; g < a.cout_pad; g += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + t * a.cout_pad + g);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + t * a.cout_pad + g + 4);
+        acc[0] = fmaf(v[t], w0.x, acc[0]); acc[1] = fmaf(v[t], w0.y, acc[1]);
+        acc[2] = fmaf(v[t], w0.z, acc[2]); acc[3] = fmaf(v[t], w0.w, acc[3]);
+        acc[4] = fmaf(v[t], w1.x, acc[4]); acc[5] = fmaf(v[t], w1.y, acc[5]);
+        acc[6] = fmaf(v[t], w1.z, acc[6]); acc[7] = fmaf(v[t], w1.w, acc[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(acc[j], s_scale[g + j], s_shift[g + j]);
+        acc[j] = t > 0.f ? t : t * a.slope;
+      }
+      if (sizeof(TOUT) == 2) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(o + g) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+        float* of = reinterpret_cast<float*>(o + g);
+        if (a.round_tf32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = to_tf32(acc[j]);
+        }
+        *reinterpret_cast<float4*>(of) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(of + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      }
+    }
+  }
+}
+
 int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(a.cout_pad % 8 == 0 && a.cout_pad >= a.cout, "first_conv: cout_pad must be a multiple of 8");
   BIU_REQUIRE(a.cin >= 1 && a.cin <= 16, "first_conv: 1..16 input channels supported (got %d)", a.cin);
@@ -108,7 +192,24 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     first_conv_kernel<TIN, TOUT><<<(int)blocks, 256, smem, stream>>>(a);                                       \
   } while (0)
-  if (a.in_kind == 0 && a.esz == 2) BIU_FC(uint8_t, __nv_bfloat16);
+  const bool fast = a.cin == 1 && a.out_ctot % 8 == 0 && a.out_coff % 8 == 0 && smem <= 48 * 1024;
+  if (fast) {
+    long long fb = ceil_div_ll((long long)a.B * a.D * a.H * a.W, 256);
+    if (fb > 148LL * 16) fb = 148LL * 16;
+    if (fb < 1) fb = 1;
+#define BIU_FC1(TIN, TOUT)                                                                               \
+  do {                                                                                                   \
+    if (a.kd == 1) first_conv1_kernel<TIN, TOUT, 9><<<(int)fb, 256, smem, stream>>>(a);                  \
+    else first_conv1_kernel<TIN, TOUT, 27><<<(int)fb, 256, smem, stream>>>(a);                           \
+  } while (0)
+    if (a.in_kind == 0 && a.esz == 2) BIU_FC1(uint8_t, __nv_bfloat16);
+    else if (a.in_kind == 0 && a.esz == 4) BIU_FC1(uint8_t, float);
+    else if (a.in_kind == 1 && a.esz == 2) BIU_FC1(float, __nv_bfloat16);
+    else if (a.in_kind == 1 && a.esz == 4) BIU_FC1(float, float);
+    else BIU_REQUIRE(false, "first_conv: bad in_kind/esz");
+#undef BIU_FC1
+  }
+  else if (a.in_kind == 0 && a.esz == 2) BIU_FC(uint8_t, __nv_bfloat16);
   else if (a.in_kind == 0 && a.esz == 4) BIU_FC(uint8_t, float);
   else if (a.in_kind == 1 && a.esz == 2) BIU_FC(float, __nv_bfloat16);
   else if (a.in_kind == 1 && a.esz == 4) BIU_FC(float, float);

@@ -1,0 +1,165 @@
+"""CPU tests of the host-side logic: tile-grid arithmetic against the oracle, TIFF I/O, the C-ABI library's
+exported symbols, the nn.Module state_dict layouts, and the absence of any CPU inference fallback."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from bio_image_unet_b200 import _lib, tiff, tiling
+from oracle import pipeline as opipe
+from tests import _golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(1, 3000), st.integers(1, 3000), st.sampled_from([16, 32, 64, 256, 512]),
+       st.sampled_from([16, 48, 128, 512]), st.integers(0, 3))
+def test_grid_2d_matches_oracle(h, w, th, tw, add):
+    n_x, n_y, xs, ys = tiling.grid_2d(h, w, (th, tw), add)
+    o = opipe.grid_2d((h, w), (th, tw), add)
+    assert (n_x, n_y) == o[:2] and np.array_equal(xs, o[2]) and np.array_equal(ys, o[3])
+    assert xs.dtype == np.uint16 and ys.dtype == np.uint16
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.tuples(st.integers(1, 300), st.integers(1, 1200), st.integers(1, 1200)),
+       st.tuples(st.sampled_from([8, 16, 64]), st.sampled_from([16, 64, 128]), st.sampled_from([16, 64, 128])),
+       st.integers(0, 2))
+def test_grid_3d_matches_oracle(shape, rd, add):
+    a, b = tiling.grid_3d(shape, rd, add), opipe.grid_3d(shape, rd, add)
+    assert a[:3] == b[:3]
+    for i in range(3, 6):
+        assert np.array_equal(a[i], b[i])
+
+
+def test_grid_known_answers():
+    # cfg 1 and cfg 2 tile starts, and the unet3d N_x quirk (appendix B)
+    assert list(tiling.grid_2d(1024, 1024, (256, 256), 1)[2]) == [0, 192, 384, 576, 768]
+    assert list(tiling.grid_2d(2048, 2048, (512, 512), 1)[3]) == [0, 384, 768, 1152, 1536]
+    g = tiling.grid_3d((8, 24, 24), (8, 16, 16), 1)
+    assert g[:3] == (2, 5, 4) and list(g[3]) == [0, 0]
+    assert tiling.grid_3d((256, 1024, 1024), (64, 128, 128), 1)[:3] == (5, 11, 10)
+    assert tiling.strided_starts(512, 256, 0.1) == [0, 230, 256]
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(1, 700), st.integers(1, 300), st.floats(0.0, 0.9))
+def test_strided_starts_matches_oracle(extent, max_patch, ov):
+    patch = min(extent, max_patch)
+    assert tiling.strided_starts(extent, patch, ov) == opipe.mo3d_starts(extent, patch, ov)
+
+
+@given(st.integers(0, 5000), st.integers(1, 16))
+def test_shard_range_partitions(n, world):
+    parts = [tiling.shard_range(n, r, world) for r in range(world)]
+    assert parts[0][0] == 0 and parts[-1][1] == n
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in parts]
+    assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize('dtype', ['uint8', 'uint16', 'float16', 'float32'])
+@pytest.mark.parametrize('shape', [(5, 7), (3, 6, 9), (1, 4, 4)])
+def test_tiff_roundtrip(tmp_path, dtype, shape):
+    rng = np.random.default_rng(0)
+    a = (rng.random(shape) * 200).astype(dtype)
+    f = str(tmp_path / 'a.tif')
+    tiff.imwrite(f, a)
+    b = tiff.imread(f)
+    assert b.dtype == a.dtype and np.array_equal(np.squeeze(b), np.squeeze(a))
+    n, page = tiff.page_count_and_shape(f)
+    assert page == shape[-2:] and n == (shape[0] if len(shape) == 3 else 1)
+    if len(shape) == 3:
+        assert np.array_equal(tiff.imread(f, key=shape[0] - 1), a[-1])
+
+
+def test_tiff_writer_appends_pages_and_bigtiff(tmp_path):
+    f = str(tmp_path / 'w.tif')
+    frames = [np.full((4, 6), i, dtype='uint8') for i in range(5)]
+    with tiff.TiffWriter(f, bigtiff=True) as tw:
+        for fr in frames:
+            tw.write(fr, contiguous=True)
+    assert np.array_equal(tiff.imread(f), np.stack(frames))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'biu_b200.h')).read()
+    declared = set(re.findall(r'\b(biu_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert os.path.exists(_lib.LIB_PATH), 'build the extension first: python -c "import __graft_entry__ as g; g.build()"'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().biu_version() >= 100
+
+
+def test_no_cpu_fallback():
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.unet import Unet
+    m = Unet(n_filter=4).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 16, 16))
+    with pytest.raises(RuntimeError):
+        Engine('unet2d', m.state_dict(), 4, device='cpu')
+    # product modules never import the oracle
+    import bio_image_unet_b200
+    pkg = os.path.dirname(bio_image_unet_b200.__file__)
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert 'oracle' not in re.findall(r'^\s*(?:from|import)\s+([a-zA-Z_\.]+)', src, re.M), fn
+
+
+def test_training_mode_forward_matches_oracle_cpu():
+    """train()-mode forward is plain torch (training is out of scope); in eval-equivalent conditions (BN in eval)
+    it must agree with the oracle restatement — this pins parameter naming and concat order of the modules."""
+    from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
+    from bio_image_unet_b200.siam_unet import Siam_UNet
+    from bio_image_unet_b200.unet import Unet
+    from bio_image_unet_b200.unet3d import UNet3D
+    from oracle import models as om
+    torch.manual_seed(0)
+    x2, x3 = torch.rand(1, 1, 32, 32), torch.rand(1, 1, 8, 16, 16)
+
+    def bn_eval(m):
+        m.train()
+        for mod in m.modules():
+            if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+                mod.eval()
+        return m
+
+    with torch.no_grad():
+        u = bn_eval(Unet(n_filter=4))
+        assert torch.allclose(u(x2)[1], om.unet_forward(u.state_dict(), x2)[1], atol=1e-5)
+        for mode in ('concat', 'max', 'control', 'corr'):
+            s = bn_eval(Siam_UNet(4, mode))
+            assert torch.allclose(s(x2, x2.flip(2))[1], om.siam_forward(s.state_dict(), x2, x2.flip(2), mode)[1], atol=1e-5)
+        v = bn_eval(UNet3D(n_filter=4))
+        assert torch.allclose(v(x3)[1], om.unet3d_forward(v.state_dict(), x3)[1], atol=1e-5)
+        for interp in (True, False):
+            m = bn_eval(MultiOutputUnet3D(1, _golden.MO3D_HEADS, 4, interp))
+            out, ref = m(x3), om.mo3d_forward(m.state_dict(), x3, _golden.MO3D_HEADS, interp)
+            assert all(torch.allclose(out[k], ref[k], atol=1e-5) for k in ref)
+
+
+def test_state_dict_layouts_match_reference():
+    from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
+    from bio_image_unet_b200.siam_unet import Siam_UNet
+    from bio_image_unet_b200.unet import Unet
+    from bio_image_unet_b200.unet3d import UNet3D
+    cases = [('unet_single', Unet(n_filter=4), 136), ('siam_concat', Siam_UNet(4, 'concat'), 143),
+             ('siam_max', Siam_UNet(4, 'max'), 136), ('unet3d_overlap', UNet3D(n_filter=4), 106),
+             ('mo3d_interp', MultiOutputUnet3D(1, _golden.MO3D_HEADS, 4, True), 125)]
+    for name, model, count in cases:
+        ref = _golden.state_dict(_golden.load(name))
+        sd = model.state_dict()
+        assert list(sd.keys()) == list(ref.keys()) and len(sd) == count
+        assert all(sd[k].shape == ref[k].shape for k in ref)
+        model.load_state_dict(ref)      # strict
