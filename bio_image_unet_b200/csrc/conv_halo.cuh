@@ -64,7 +64,7 @@ __device__ __forceinline__ HaloTile halo_decode(const ConvHaloParams& p, int t) 
   return r;
 }
 
-template <int ESZ>
+template <int ESZ, int KS>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const ConvHaloParams p) {
@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // ================================== halo (A) producer ===================================
     if (elect_one()) {
       const uint32_t halo_tx = (uint32_t)(p.kd * kHaloRows * pw) * rb;
-      int hi = 0;
+      int ab = 0;
+      uint32_t aph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HaloTile tl = halo_decode(p, t);
-        for (int ch = 0; ch < p.cin_chunks; ++ch, ++hi) {
-          const int ab = hi % p.a_bufs;
-          mbar_wait(&a_empty[ab], ((hi / p.a_bufs) & 1) ^ 1, 0x400 + ab);
+        for (int ch = 0; ch < p.cin_chunks; ++ch) {
+          mbar_wait(&a_empty[ab], aph ^ 1, 0x400 + ab);
           mbar_arrive_expect_tx(&a_full[ab], halo_tx);
           // The halo is fetched as 2-row boxes issued back to back: one TMA operation keeps only a few dozen L2
           // requests in flight, many concurrent ones are needed to cover the L2 / HBM latency.
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                   "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[ab])), "r"(ch * p.ck), "r"(tl.x0 - 1),
                   "r"(tl.y0 - 1 + 2 * r2), "r"(tl.z0 - (p.kd >> 1) + dz), "r"(tl.b0)
                   : "memory");
+          if (++ab == p.a_bufs) { ab = 0; aph ^= 1; }
         }
       }
     }
@@ -133,13 +134,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // ================================= weight (B) producer ==================================
     if (elect_one()) {
       const uint32_t b_tx = (uint32_t)p.n_blk * rb;
-      int kb = 0;
+      int s = 0;
+      uint32_t bph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const HaloTile tl = halo_decode(p, t);
         for (int ch = 0; ch < p.cin_chunks; ++ch)
-          for (int tap = 0; tap < taps; ++tap, ++kb) {
-            const int s = kb % p.b_stages;
-            mbar_wait(&b_empty[s], ((kb / p.b_stages) & 1) ^ 1, 0x500 + s);
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(&b_empty[s], bph ^ 1, 0x500 + s);
             mbar_arrive_expect_tx(&b_full[s], b_tx);
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&b_full[s])), "r"(ch * p.ck), "r"(tl.n0),
                 "r"(tap)
                 : "memory");
+            if (++s == p.b_stages) { s = 0; bph ^= 1; }
           }
       }
     }
@@ -155,49 +157,54 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (elect_one()) {
       const uint32_t layout = rb == 128 ? 2u : (rb == 64 ? 4u : 6u);
       const uint32_t idesc = make_idesc(ESZ == 2 ? 1u : 2u, (uint32_t)p.n_blk);
-      const int ksteps = rb / 32;
       // Descriptors: only the 14-bit start-address field (low word, address >> 4) changes between MMAs and it
       // never carries out of the field (shared memory < 256 KB), so they are advanced with 32-bit adds.
       const uint64_t a_tmpl = make_smem_desc(0, (uint32_t)pw * rb, layout);
       const uint64_t b_tmpl = make_smem_desc(0, 8u * rb, layout);
       const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
-      const uint32_t a_lo0 = (uint32_t)a_tmpl, b_lo0 = (uint32_t)b_tmpl;
+      const uint32_t a_lo0 = (uint32_t)a_tmpl + ((smem_base & 0x3FFFF) >> 4);
+      const uint32_t b_lo0 = (uint32_t)b_tmpl + ((b_base & 0x3FFFF) >> 4);
       const uint32_t j_step = (8u * rb) >> 4;        // next MMA tile: 8 pixels further
-      int hi = 0, kb = 0, it = 0;
+      const uint32_t px_step = rb >> 4;              // one pixel
+      const uint32_t row_step = ((uint32_t)pw * rb) >> 4;
+      const uint32_t abuf_step = p.a_buf_bytes >> 4, bst_step = p.b_stage_bytes >> 4;
+      int ab = 0, bs = 0, it = 0;
+      uint32_t aph = 0, bph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1, 0x900 + as);     // epilogue has drained this stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * acc_cols;
         uint32_t accum = 0;                                             // first k-block of a tile overwrites
-        for (int ch = 0; ch < p.cin_chunks; ++ch, ++hi) {
-          const int ab = hi % p.a_bufs;
-          mbar_wait(&a_full[ab], (hi / p.a_bufs) & 1, 0x600 + ab);
-          const uint32_t a_addr = smem_base + ab * p.a_buf_bytes;
-          for (int dz = 0; dz < p.kd; ++dz)
-            for (int dy = 0; dy < 3; ++dy)
-              for (int dx = 0; dx < 3; ++dx, ++kb) {
-                const int s = kb % p.b_stages;
-                mbar_wait(&b_full[s], (kb / p.b_stages) & 1, 0x700 + s);
-                tc_fence_after();
-                const uint32_t b_lo = b_lo0 + (((b_base + s * p.b_stage_bytes) & 0x3FFFF) >> 4);
-                uint32_t a_lo = a_lo0 + (((a_addr + (uint32_t)((dz * kHaloRows + dy) * pw + dx) * rb) & 0x3FFFF) >> 4);
-                uint32_t tcol = tacc;
-                for (int j = 0; j < p.mt; ++j, a_lo += j_step, tcol += p.n_blk) {
-                  // k = 0 (may overwrite), then k = 1.. (always accumulate); +32 bytes = +2 in the address field
-                  const uint64_t ad0 = ((uint64_t)a_hi << 32) | a_lo;
-                  const uint64_t bd0 = ((uint64_t)b_hi << 32) | b_lo;
-                  if (ESZ == 2) tc_mma_f16(tcol, ad0, bd0, idesc, accum); else tc_mma_tf32(tcol, ad0, bd0, idesc, accum);
-                  for (int k = 1; k < ksteps; ++k) {
-                    const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + 2 * k);
-                    const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + 2 * k);
-                    if (ESZ == 2) tc_mma_f16(tcol, ad, bd, idesc, 1u); else tc_mma_tf32(tcol, ad, bd, idesc, 1u);
-                  }
+        for (int ch = 0; ch < p.cin_chunks; ++ch) {
+          mbar_wait(&a_full[ab], aph, 0x600 + ab);
+          const uint32_t a_buf_lo = a_lo0 + ab * abuf_step;
+          for (int r = 0; r < 3 * p.kd; ++r) {                          // r = dz*3 + dy
+            const int dz = r / 3, dy = r - 3 * dz;
+            const uint32_t a_row_lo = a_buf_lo + (uint32_t)(dz * kHaloRows + dy) * row_step;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              mbar_wait(&b_full[bs], bph, 0x700 + bs);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + bs * bst_step;
+              uint32_t a_lo = a_row_lo + dx * px_step;
+              uint32_t tcol = tacc;
+              for (int j = 0; j < p.mt; ++j, a_lo += j_step, tcol += p.n_blk) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                  const uint64_t ad = ((uint64_t)a_hi << 32) | (a_lo + 2 * k);   // +32 bytes per k-step
+                  const uint64_t bd = ((uint64_t)b_hi << 32) | (b_lo + 2 * k);
+                  const uint32_t acc = k == 0 ? accum : 1u;
+                  if (ESZ == 2) tc_mma_f16(tcol, ad, bd, idesc, acc); else tc_mma_tf32(tcol, ad, bd, idesc, acc);
                 }
-                accum = 1;
-                tc_commit(&b_empty[s]);
               }
+              accum = 1;
+              tc_commit(&b_empty[bs]);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
           tc_commit(&a_empty[ab]);
+          if (++ab == p.a_bufs) { ab = 0; aph ^= 1; }
         }
         tc_commit(&acc_full[as]);
       }

@@ -188,21 +188,23 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
     return rc;
   if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, 9 * a.kd, pl.ck, n_blk)) return rc;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+#define BIU_HALO_LAUNCH(E, K)                                                                                  \
+  do {                                                                                                          \
+    static int max_set = 0;                                                                                     \
+    if (pl.smem > max_set) {                                                                                    \
+      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<E, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                          pl.smem));                                                            \
+      max_set = pl.smem;                                                                                        \
+    }                                                                                                           \
+    conv_halo_kernel<E, K><<<grid, kHaloThreads, pl.smem, stream>>>(tmA, tmB, p);                               \
+  } while (0)
+  const int ks = p.row_bytes / 32;
   if (a.esz == 2) {
-    static int max_set = 0;
-    if (pl.smem > max_set) {
-      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-      max_set = pl.smem;
-    }
-    conv_halo_kernel<2><<<grid, kHaloThreads, pl.smem, stream>>>(tmA, tmB, p);
+    if (ks == 4) BIU_HALO_LAUNCH(2, 4); else if (ks == 2) BIU_HALO_LAUNCH(2, 2); else BIU_HALO_LAUNCH(2, 1);
   } else {
-    static int max_set = 0;
-    if (pl.smem > max_set) {
-      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
-      max_set = pl.smem;
-    }
-    conv_halo_kernel<4><<<grid, kHaloThreads, pl.smem, stream>>>(tmA, tmB, p);
+    if (ks == 4) BIU_HALO_LAUNCH(4, 4); else if (ks == 2) BIU_HALO_LAUNCH(4, 2); else BIU_HALO_LAUNCH(4, 1);
   }
+#undef BIU_HALO_LAUNCH
   BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
