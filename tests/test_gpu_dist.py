@@ -1,0 +1,20 @@
+"""2-GPU NCCL run of every predictor with distributed=True (skipped on boxes with a single GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_distributed_predictors_match_single_process(tmp_path):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+           '127.0.0.1', '--master-port', '29517', os.path.join(ROOT, 'tests', 'run_dist_gpu.py'), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0
+    assert os.path.exists(tmp_path / 'DIST_OK')
