@@ -205,11 +205,11 @@ def main():
     tc_ms = sum(ms[i] for i in range(n_ops.value) if kinds[i] in (1, 2, 3))
     tc_launches = sum(1 for i in range(n_ops.value) if kinds[i] in (1, 2, 3))
     all_ms = sum(ms[i] for i in range(n_ops.value))
-    fallback_ops = sum(1 for i in range(n_ops.value) if kinds[i] >= 16)
+    fallback_ops = sum(1 for i in range(n_ops.value) if 16 <= kinds[i] < 32)
     if rank == 0 and os.environ.get('BIU_BENCH_VERBOSE'):
         names = {0: 'first_conv', 1: 'conv_tc', 2: 'conv_tc+head', 3: 'up_tc', 4: 'pool', 5: 'up_nearest', 6: 'max_join'}
         for i in range(n_ops.value):
-            print(f'[op {i:2d}] {names.get(kinds[i] % 16, "?"):14s}{" (cuda-core)" if kinds[i] >= 16 else "":12s} {ms[i]:8.3f} ms',
+            print(f'[op {i:2d}] {names.get(kinds[i] % 16, "?"):14s}{" (cuda-core)" if 16 <= kinds[i] < 32 else (" (fused)" if kinds[i] >= 32 else ""):12s} {ms[i]:8.3f} ms',
                   file=sys.stderr)
     tiles_last_fwd = f * tiles_per_frame - (fwd_per_step - 1) * ses.tile_batch
     flops_last_fwd = FLOP_PER_TILE_PX_TC * ses.tile_batch * TILE[0] * TILE[1]   # the padded tail batch computes full batches

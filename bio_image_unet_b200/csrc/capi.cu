@@ -82,6 +82,12 @@ int biu_net_set_force_direct(biu_net* net, int on) {
   net->n->force_direct = on;
   return 0;
 }
+
+int biu_net_set_fuse_pool(biu_net* net, int on) {
+  BIU_REQUIRE(net && net->n, "null handle");
+  net->n->no_fuse = on ? 0 : 1;
+  return 0;
+}
 void biu_net_destroy(biu_net* net) {
   if (!net) return;
   if (net->n) net_destroy(net->n);

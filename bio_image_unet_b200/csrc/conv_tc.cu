@@ -112,43 +112,68 @@ static bool halo_disabled() {
   return v == 1;
 }
 
-struct HaloPlan { int mt, a_bufs, b_stages, ck; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
+#ifdef BIU_DBG_KNOBS
+int g_halo_dbg = 0;
+int g_halo_force_mt = 0;
+int g_halo_force_ck = 0;
+#endif
+
+struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
+
+// can the halo kernel take this layer? (3x3(x3) blocks, and transposed convolutions as a 1-tap GEMM)
+static bool halo_shape_ok(const ConvTcArgs& a) {
+  if (halo_disabled()) return false;
+  if (a.mode == EPI_UP) { if (a.kw != 1 || a.kh != 1 || a.kd != 1) return false; }
+  else if (a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return false;
+  if (a.H < 16 || a.W < 8) return false;                 // tiny planes: the per-tap kernel packs the batch instead
+  return true;
+}
 
 static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
   HaloPlan pl{};
   pl.ok = false;
-  if (halo_disabled() || a.mode == EPI_UP || a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return pl;
-  if (a.H < 16 || a.W < 8) return pl;                      // tiny planes: the per-tap kernel packs the batch instead
-  if (n_blk > 256) return pl;
-  const int budget = 224 * 1024;
-  const int taps = 9 * a.kd;
+  if (!halo_shape_ok(a) || n_blk > 256) return pl;
+  const int halo = a.mode == EPI_UP ? 0 : 1;
+  const int rows = 16 + 2 * halo;
+  const int taps = halo ? 9 * a.kd : 1;
+  const int extra = (2 * a.n_total + (a.mode == EPI_HEAD ? a.head_n * n_blk : 0)) * 4 + 64;   // scale/shift/head
+  const int budget = 225 * 1024 - extra;
   const int ck0 = pick_ck(a.cin, a.esz);
-  for (int ck = ck0; ck >= 32 / a.esz; ck >>= 1) {
-    if (a.cin % ck) continue;
-    const int rb = ck * a.esz;
-    const int chunks = a.cin / ck;
-    int mt_max = 256 / n_blk;                              // two accumulator stages of mt * n_blk TMEM columns
-    if (mt_max > 8) mt_max = 8;
-    const int w8 = (a.W + 7) / 8;
-    if (mt_max > w8) mt_max = w8;
-    for (int mt = mt_max; mt >= 1; --mt) {
-      if (mt != mt_max && (mt & (mt - 1))) continue;       // after the first try only powers of two
-      const uint32_t halo = ((uint32_t)(a.kd * kHaloRows * (8 * mt + 2) * rb) + 1023u) & ~1023u;
-      const uint32_t bst = ((uint32_t)(n_blk * rb) + 1023u) & ~1023u;
-      for (int abufs = 2; abufs >= 1; --abufs) {
-        int stages = (budget - (int)(abufs * halo) - 2048) / (int)bst;
+  int mt_max = 256 / n_blk;                                // two accumulator stages of mt * n_blk TMEM columns
+  if (mt_max > 8) mt_max = 8;
+  const int w8 = (a.W + 7) / 8;
+  if (mt_max > w8) mt_max = w8;
+#ifdef BIU_DBG_KNOBS
+  if (g_halo_force_mt > 0 && mt_max > g_halo_force_mt) mt_max = g_halo_force_mt;
+#endif
+  while (mt_max & (mt_max - 1)) --mt_max;                  // the kernel is instantiated for mt = 1, 2, 4, 8
+  // Preference: two A buffers (load of tile i+1 overlaps the MMAs of tile i) before wide chunks / wide tiles.
+  for (int abufs = 2; abufs >= 1; --abufs)
+    for (int ck = ck0; ck >= 32 / a.esz; ck >>= 1) {
+      if (a.cin % ck) continue;
+#ifdef BIU_DBG_KNOBS
+      if (g_halo_force_ck > 0 && ck != g_halo_force_ck) continue;
+#endif
+      const int rb = ck * a.esz;
+      const int chunks = a.cin / ck;
+      for (int mt = mt_max; mt >= 1; --mt) {
+        if (mt != mt_max && (mt & (mt - 1))) continue;     // after the first try only powers of two
+        if (abufs == 2 && mt < mt_max && 2 * mt < mt_max) break;   // do not shrink tiles below half for the 2nd buffer
+        const uint32_t tile = ((uint32_t)(a.kd * rows * (8 * mt + 2 * halo) * rb) + 1023u) & ~1023u;
+        const uint32_t bst = ((uint32_t)(n_blk * rb) + 1023u) & ~1023u;
+        int stages = (budget - (int)(abufs * tile) - 2048) / (int)bst;
         if (stages > kMaxBStages) stages = kMaxBStages;
+        const bool resident = stages >= taps * chunks && a.n_total == n_blk;
         if (stages > taps * chunks) stages = taps * chunks;
-        if (stages >= (abufs == 2 ? 3 : 2)) {
-          pl.mt = mt; pl.a_bufs = abufs; pl.b_stages = stages; pl.ck = ck;
-          pl.a_buf_bytes = halo; pl.b_stage_bytes = bst;
-          pl.smem = (int)(abufs * halo + stages * bst) + 1024;
+        if (stages >= (abufs == 2 ? 3 : 2) || stages == taps * chunks) {
+          pl.mt = mt; pl.a_bufs = abufs; pl.b_stages = stages; pl.ck = ck; pl.b_resident = resident ? 1 : 0;
+          pl.a_buf_bytes = tile; pl.b_stage_bytes = bst;
+          pl.smem = (int)(abufs * tile + stages * bst) + 1024 + extra;
           pl.ok = true;
           return pl;
         }
       }
     }
-  }
   return pl;
 }
 
@@ -173,41 +198,52 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   p.n_blocks = a.n_total / n_blk;
   p.total_tiles = p.tiles_x * p.tiles_y * a.D * a.B * p.n_blocks;
   p.kd = a.kd;
+  p.halo = a.mode == EPI_UP ? 0 : 1;
   p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
-  p.n_blk = n_blk;
+  p.n_blk = n_blk; p.n_total = a.n_total;
   p.a_bufs = pl.a_bufs; p.b_stages = pl.b_stages; p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
+  p.b_resident = pl.b_resident;
+  p.up_cout = a.up_cout; p.up_dims = a.up_dims;
+  p.pool_out = a.pool_out; p.pool_ctot = a.pool_ctot; p.pool_coff = a.pool_coff;
   p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;
   p.out = a.out; p.out_ctot = a.out_ctot; p.out_coff = a.out_coff;
   p.head_n = a.head_n; p.head_w = a.head_w; p.head_b = a.head_b;
   for (int i = 0; i < kMaxHead; ++i) p.head_act[i] = a.head_act[i];
   p.out_val = a.out_val; p.out_u8 = a.out_u8;
+#ifdef BIU_DBG_KNOBS
+  p.dbg = g_halo_dbg;
+#endif
 
   CUtensorMap tmA, tmB;
   const char* in_base = reinterpret_cast<const char*>(a.in) + (size_t)a.in_coff * a.esz;
-  if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, 8 * pl.mt + 2, 2, 1, 1))
+  if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, 8 * pl.mt + 2 * p.halo, 2, 1, 1))
     return rc;
-  if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, 9 * a.kd, pl.ck, n_blk)) return rc;
+  if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, p.halo ? 9 * a.kd : 1, pl.ck, n_blk)) return rc;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-#define BIU_HALO_LAUNCH(E, K)                                                                                  \
-  do {                                                                                                          \
-    static int max_set = 0;                                                                                     \
-    if (pl.smem > max_set) {                                                                                    \
-      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<E, K>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          pl.smem));                                                            \
-      max_set = pl.smem;                                                                                        \
-    }                                                                                                           \
-    conv_halo_kernel<E, K><<<grid, kHaloThreads, pl.smem, stream>>>(tmA, tmB, p);                               \
-  } while (0)
-  const int ks = p.row_bytes / 32;
-  if (a.esz == 2) {
-    if (ks == 4) BIU_HALO_LAUNCH(2, 4); else if (ks == 2) BIU_HALO_LAUNCH(2, 2); else BIU_HALO_LAUNCH(2, 1);
-  } else {
-    if (ks == 4) BIU_HALO_LAUNCH(4, 4); else if (ks == 2) BIU_HALO_LAUNCH(4, 2); else BIU_HALO_LAUNCH(4, 1);
-  }
-#undef BIU_HALO_LAUNCH
+  BIU_REQUIRE(pl.mt == 1 || pl.mt == 2 || pl.mt == 4 || pl.mt == 8, "halo kernel: mt must be 1, 2, 4 or 8 (got %d)", pl.mt);
+  // the kernel instantiations live in their own translation units (conv_halo_bf16.cu / conv_halo_tf32.cu)
+  if (int rc = a.esz == 2 ? halo_dispatch_bf16(tmA, tmB, p, grid, pl.smem, stream)
+                          : halo_dispatch_tf32(tmA, tmB, p, grid, pl.smem, stream))
+    return rc;
   BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+static int choose_n_blk(const ConvTcArgs& a) {
+  // N per CTA: whole N when it fits one accumulator, otherwise the largest divisor <= 256
+  int n_blk = a.n_total;
+  if (n_blk > 256) {
+    n_blk = 256;
+    while (a.n_total % n_blk != 0) n_blk -= 16;
+  }
+  if (a.mode == EPI_UP && n_blk > a.up_cout && n_blk % a.up_cout != 0) n_blk = a.up_cout;
+  return n_blk;
+}
+
+bool conv_tc_can_fuse_pool(const ConvTcArgs& a) {
+  if (!conv_tc_supported(a) || a.mode != EPI_CONV || a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1)) return false;
+  return plan_halo(a, choose_n_blk(a)).ok;
 }
 
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
@@ -225,17 +261,12 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
   p.ck = pick_ck(a.cin, a.esz);
   p.cin_chunks = a.cin / p.ck;
   p.row_bytes = p.ck * a.esz;
-  // N per CTA: whole N when it fits one accumulator, otherwise the largest divisor <= 256
-  int n_blk = a.n_total;
-  if (n_blk > 256) {
-    n_blk = 256;
-    while (a.n_total % n_blk != 0) n_blk -= 16;
-  }
-  if (a.mode == EPI_UP && n_blk > a.up_cout && n_blk % a.up_cout != 0) n_blk = a.up_cout;
+  const int n_blk = choose_n_blk(a);
   {
     const HaloPlan pl = plan_halo(a, n_blk);
     if (pl.ok) return launch_conv_halo(a, n_blk, pl, stream);
   }
+  BIU_REQUIRE(a.pool_out == nullptr, "conv_tc: the fused max-pool needs the halo-tile kernel (check conv_tc_can_fuse_pool)");
   p.n_blk = n_blk;
   p.mode = a.mode;
   p.slope = a.slope;

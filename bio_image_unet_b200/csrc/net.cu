@@ -444,11 +444,14 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
   }
   n->op_kinds.assign(n->ops.size(), 0);
   int op_index = -1;
+  bool skip_pool = false;           // the previous convolution wrote the pooled tensor from its epilogue
   for (const Op& o : n->ops) {
     ++op_index;
     if (n->profile && op_index > 0) BIU_CHECK_CUDA(cudaEventRecord(n->events[2 * op_index - 1], stream));
     if (n->profile) BIU_CHECK_CUDA(cudaEventRecord(n->events[2 * op_index], stream));
     n->op_kinds[op_index] = (int)o.kind;
+    if (skip_pool && o.kind == OP_POOL) { skip_pool = false; n->op_kinds[op_index] += 32; continue; }
+    skip_pool = false;
     int d, h, w;
     level_dims(n, o.level, &d, &h, &w);
     const int batch = n->B * o.batch_mul;
@@ -494,6 +497,18 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
           a.out_val = out_val; a.out_u8 = out_u8;
         }
         if (tc_allowed && L.w_tc && conv_tc_supported(a)) {
+          // MaxPool2d(2) directly after this block (unet/unet.py:73-74 etc.): fused into the epilogue
+          if (!head && n->dims == 2 && !n->no_fuse && op_index + 1 < (int)n->ops.size()) {
+            const Op& nx = n->ops[op_index + 1];
+            if (nx.kind == OP_POOL && nx.pool_mode == 0 && nx.src == o.dst && nx.src_coff == o.dst_coff &&
+                nx.c == L.cout_pad && nx.batch_mul == o.batch_mul && nx.src_img0 == 0 && nx.dst_img0 == 0 &&
+                o.dst_img0 == 0 && nx.level == o.level) {
+              const Buf& pb = n->bufs[nx.dst];
+              a.pool_out = ws + pb.offset; a.pool_ctot = pb.ctot; a.pool_coff = nx.dst_coff;
+              if (conv_tc_can_fuse_pool(a)) skip_pool = true;
+              else a.pool_out = nullptr;
+            }
+          }
           if (int rc = launch_conv_tc(a, stream)) return rc;
         } else {
           n->op_kinds[op_index] += 16;

@@ -79,6 +79,7 @@ struct Net {
   size_t ws_bytes = 0;
 
   int force_direct = 0;             // debugging: run every conv on the CUDA-core kernels
+  int no_fuse = 0;                  // debugging: keep the max-pool as its own kernel
   int profile = 0;                  // bracket every op with CUDA events
   std::vector<cudaEvent_t> events;  // 2 per op
   std::vector<int> op_kinds;        // kind (+16 if it ran on the CUDA-core fallback) of the last forward

@@ -125,6 +125,9 @@ class Engine:
     def set_force_direct(self, on):
         _lib.check(self.lib.biu_net_set_force_direct(self.handle, int(on)))
 
+    def set_fuse_pool(self, on):
+        _lib.check(self.lib.biu_net_set_fuse_pool(self.handle, int(on)))
+
     def close(self):
         if getattr(self, 'handle', None):
             self.lib.biu_net_destroy(self.handle)

@@ -68,6 +68,9 @@ int biu_net_forward(biu_net* net, const void* in, int in_kind, const void* in2, 
 int biu_net_debug_copy(biu_net* net, const char* name, void* workspace, void* dst_host, long long max_bytes);
 /* Test hook: 1 = run every convolution on the CUDA-core kernels. */
 int biu_net_set_force_direct(biu_net* net, int on);
+/* Test hook: 0 = run MaxPool2d as its own kernel instead of fusing it into the preceding block's epilogue
+ * (default 1; both give bit-identical activations). */
+int biu_net_set_fuse_pool(biu_net* net, int on);
 void biu_net_destroy(biu_net* net);
 
 /* ---- intensity normalisation: replaces Predict.__preprocess ------------------------------------------------
@@ -140,7 +143,8 @@ unsigned long long biu_launch_count(void);
 /* Measurement hooks: with profiling on, biu_net_forward brackets every layer with CUDA events on the caller's
  * stream; biu_net_profile_read synchronises those events and returns, for the most recent forward, the op kind
  * (0 first conv, 1 conv block [tcgen05], 2 conv block + head [tcgen05], 3 transposed conv [tcgen05], 4 pool,
- * 5 nearest upsample, 6 max join; +16 when the op ran on the CUDA-core fallback) and its duration in ms. */
+ * 5 nearest upsample, 6 max join; +16 when the op ran on the CUDA-core fallback, +32 when it was fused into the
+ * previous op and launched nothing) and its duration in ms. */
 int biu_net_set_profile(biu_net* net, int on);
 int biu_net_profile_read(biu_net* net, int max_ops, int* kinds, float* ms, int* n_ops);
 

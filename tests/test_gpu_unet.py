@@ -215,3 +215,26 @@ def test_stitch_mean_bit_exact():
         ref = opipe.stitch_mean_2d(tiles, f, (h, w), (th, tw), (n_x, n_y, xs, ys)).reshape(f, c, h, w)
         got = E.stitch_mean_u8(torch.from_numpy(tiles).cuda(), f, c, (h, w), xs, ys, (th, tw)).cpu().numpy()
         assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+@pytest.mark.parametrize('tile', [(64, 64), (48, 80), (128, 32)])
+def test_fused_maxpool_is_bit_identical(precision, tile):
+    """MaxPool2d(2) fused into the preceding block's epilogue (warp shuffles over the stored values) vs the
+    standalone pool kernel: pooled tensors m1..m4 and the network output must be bit-identical."""
+    from bio_image_unet_b200.engine import Engine
+    sd = stress_state_dict(32, seed=9)
+    tiles = torch.randint(0, 256, (3, 1, *tile), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
+    eng = Engine('unet2d', sd, 32, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
+    eng.plan(3, tile)
+    names = [('m1', 32, 1), ('m2', 64, 2), ('m3', 128, 3), ('m4', 256, 4)]
+    v_fused, u_fused = eng.forward(tiles, want_val=True)
+    a_fused = {n: eng.debug_activation(n, c, l).copy() for n, c, l in names}
+    eng.set_fuse_pool(0)
+    eng.workspace.zero_()
+    v_plain, u_plain = eng.forward(tiles, want_val=True)
+    a_plain = {n: eng.debug_activation(n, c, l).copy() for n, c, l in names}
+    for n, _, _ in names:
+        assert np.array_equal(a_fused[n], a_plain[n]), n
+    assert torch.equal(v_fused, v_plain) and torch.equal(u_fused, u_plain)
+    eng.close()
