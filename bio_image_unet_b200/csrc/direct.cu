@@ -175,6 +175,132 @@ __global__ void __launch_bounds__(256) first_conv1_kernel(FirstConvArgs a) {
   }
 }
 
+// 2D, single input channel, second generation: a warp walks down a strip of (32/G pixels) x kFcRows rows, lane =
+// (pixel x, channel group g of 8). The 72 weights of the group stay in registers for the whole kernel, the 3x3
+// window slides down the strip (3 new input values per output row, fetched one row ahead), u8 ->
+// float32(u8)/255 comes from a 256-entry shared LUT (exact division, unet/predict.py:192), and for every row the
+// warp's 16-byte stores cover one contiguous run of the NHWC buffer (full sectors, not 16 B pieces of 32 pixels).
+constexpr int kFcRows = 64;
+template <typename TIN, typename TOUT, int G>
+__global__ void __launch_bounds__(256, 2) first_conv1_2d_kernel(FirstConvArgs a) {
+  __shared__ float lut[256];
+  __shared__ __align__(16) float s_sc[64], s_sh[64];
+  if (sizeof(TIN) == 1) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  if (threadIdx.x < 64) {
+    s_sc[threadIdx.x] = threadIdx.x < a.cout ? a.scale[threadIdx.x] : 0.f;
+    s_sh[threadIdx.x] = threadIdx.x < a.cout ? a.shift[threadIdx.x] : 0.f;
+  }
+  constexpr int PXW = 32 / G;                   // pixels per warp row
+  const int lane = threadIdx.x & 31;
+  const int g = lane % G, lx = lane / G;
+  float w[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[t][j] = (g * 8 + j) < a.cout ? __ldg(a.wgt + t * a.cout + g * 8 + j) : 0.f;
+  __syncthreads();
+  const int tiles_x = (a.W + PXW - 1) / PXW, tiles_y = (a.H + kFcRows - 1) / kFcRows;
+  const int total = a.B * tiles_y * tiles_x;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const TIN* in = reinterpret_cast<const TIN*>(a.in);
+  TOUT* out = reinterpret_cast<TOUT*>(a.out);
+  const int W = a.W, H = a.H;
+  for (int tile = warp0; tile < total; tile += nwarps) {
+    int r = tile;
+    const int tx = r % tiles_x; r /= tiles_x;
+    const int ty = r % tiles_y; r /= tiles_y;
+    const int x = tx * PXW + lx, y0 = ty * kFcRows;
+    const int y1 = min(y0 + kFcRows, H);
+    const bool c0 = x >= 1 && x - 1 < W, c1 = x < W, c2 = x + 1 < W;
+    const TIN* p = in + ((long long)r * H + y0) * W + x;          // input pixel (y0, x) of image r
+    auto cvt = [&](TIN raw) -> float { return sizeof(TIN) == 1 ? lut[(int)raw] : (float)raw; };
+    float v0[3] = {0.f, 0.f, 0.f}, v1[3], v2[3];
+    if (y0 > 0) {
+      v0[0] = c0 ? cvt(__ldg(p - W - 1)) : 0.f;
+      v0[1] = c1 ? cvt(__ldg(p - W)) : 0.f;
+      v0[2] = c2 ? cvt(__ldg(p - W + 1)) : 0.f;
+    }
+    v1[0] = c0 ? cvt(__ldg(p - 1)) : 0.f;
+    v1[1] = c1 ? cvt(__ldg(p)) : 0.f;
+    v1[2] = c2 ? cvt(__ldg(p + 1)) : 0.f;
+    TIN nraw[3] = {0, 0, 0};                                       // row y + 1, fetched one iteration ahead
+    bool nvalid = y0 + 1 < H;
+    if (nvalid) {
+      if (c0) nraw[0] = __ldg(p + W - 1);
+      if (c1) nraw[1] = __ldg(p + W);
+      if (c2) nraw[2] = __ldg(p + W + 1);
+    }
+    TOUT* o = out + (((long long)r * H + y0) * W + x) * a.out_ctot + a.out_coff + g * 8;
+    const long long o_step = (long long)W * a.out_ctot;
+    for (int y = y0; y < y1; ++y, p += W, o += o_step) {
+      v2[0] = (nvalid && c0) ? cvt(nraw[0]) : 0.f;
+      v2[1] = (nvalid && c1) ? cvt(nraw[1]) : 0.f;
+      v2[2] = (nvalid && c2) ? cvt(nraw[2]) : 0.f;
+      nvalid = y + 2 < H;
+      if (nvalid) {
+        if (c0) nraw[0] = __ldg(p + 2 * W - 1);
+        if (c1) nraw[1] = __ldg(p + 2 * W);
+        if (c2) nraw[2] = __ldg(p + 2 * W + 1);
+      }
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = fmaf(v0[dx], w[dx][j], acc[j]);
+          acc[j] = fmaf(v1[dx], w[3 + dx][j], acc[j]);
+          acc[j] = fmaf(v2[dx], w[6 + dx][j], acc[j]);
+        }
+      const float4 sc0 = *reinterpret_cast<const float4*>(s_sc + g * 8), sc1 = *reinterpret_cast<const float4*>(s_sc + g * 8 + 4);
+      const float4 sh0 = *reinterpret_cast<const float4*>(s_sh + g * 8), sh1 = *reinterpret_cast<const float4*>(s_sh + g * 8 + 4);
+      const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+      const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(acc[j], scv[j], shv[j]);
+        acc[j] = t > 0.f ? t : t * a.slope;
+      }
+      if (c1) {
+        if (sizeof(TOUT) == 2) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        } else {
+          float* of = reinterpret_cast<float*>(o);
+          if (a.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = to_tf32(acc[j]);
+          }
+          *reinterpret_cast<float4*>(of) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(of + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) { v0[dx] = v1[dx]; v1[dx] = v2[dx]; }
+    }
+  }
+}
+
+template <typename TIN, typename TOUT>
+static void launch_first_conv1_2d(const FirstConvArgs& a, cudaStream_t stream) {
+  const int G = a.cout_pad / 8;
+  const long long tiles = (long long)a.B * ((a.H + kFcRows - 1) / kFcRows) * ((a.W + 32 / G - 1) / (32 / G));
+  long long blocks = ceil_div_ll(tiles, 8);      // 8 warps per block
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  if (blocks < 1) blocks = 1;
+  if (G == 1) first_conv1_2d_kernel<TIN, TOUT, 1><<<(int)blocks, 256, 0, stream>>>(a);
+  else if (G == 2) first_conv1_2d_kernel<TIN, TOUT, 2><<<(int)blocks, 256, 0, stream>>>(a);
+  else if (G == 4) first_conv1_2d_kernel<TIN, TOUT, 4><<<(int)blocks, 256, 0, stream>>>(a);
+  else first_conv1_2d_kernel<TIN, TOUT, 8><<<(int)blocks, 256, 0, stream>>>(a);
+}
+
 int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(a.cout_pad % 8 == 0 && a.cout_pad >= a.cout, "first_conv: cout_pad must be a multiple of 8");
   BIU_REQUIRE(a.cin >= 1 && a.cin <= 16, "first_conv: 1..16 input channels supported (got %d)", a.cin);
@@ -193,7 +319,14 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
     first_conv_kernel<TIN, TOUT><<<(int)blocks, 256, smem, stream>>>(a);                                       \
   } while (0)
   const bool fast = a.cin == 1 && a.out_ctot % 8 == 0 && a.out_coff % 8 == 0 && smem <= 48 * 1024;
-  if (fast) {
+  const int groups = a.cout_pad / 8;
+  if (fast && a.kd == 1 && a.D == 1 && (groups == 1 || groups == 2 || groups == 4 || groups == 8)) {
+    if (a.in_kind == 0 && a.esz == 2) launch_first_conv1_2d<uint8_t, __nv_bfloat16>(a, stream);
+    else if (a.in_kind == 0 && a.esz == 4) launch_first_conv1_2d<uint8_t, float>(a, stream);
+    else if (a.in_kind == 1 && a.esz == 2) launch_first_conv1_2d<float, __nv_bfloat16>(a, stream);
+    else if (a.in_kind == 1 && a.esz == 4) launch_first_conv1_2d<float, float>(a, stream);
+    else BIU_REQUIRE(false, "first_conv: bad in_kind/esz");
+  } else if (fast) {
     long long fb = ceil_div_ll((long long)a.B * a.D * a.H * a.W, 256);
     if (fb > 148LL * 16) fb = 148LL * 16;
     if (fb < 1) fb = 1;

@@ -36,6 +36,7 @@ class Session:
         self.tile_batch = None
         self.fixed_lut = None          # set for 'first' / 'all' (stack-wide statistics)
         self.last = {}
+        self._pin, self._streams, self._dev_in = {}, None, None
 
     def _ensure_plan(self, total_tiles):
         if self.tile_batch is None or (total_tiles < self.tile_batch):
@@ -64,18 +65,88 @@ class Session:
         return out
 
     def predict(self, frames):
-        """Host stack in, host result out (H2D and D2H inside)."""
+        """Host stack in, host result out (H2D and D2H inside, pipelined against the compute)."""
+        return self.predict_movie(frames)[0]
+
+    def _pinned(self, key, shape, dtype):
+        """Reusable pinned host buffer (grown on demand)."""
+        n = int(np.prod(shape))
+        buf = self._pin.get(key)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(n, dtype=dtype, pin_memory=True)
+            self._pin[key] = buf
+        return buf[:n].view(*shape)
+
+    def predict_movie(self, frames, chunk_frames=None, want_norm=False):
+        """Pipelined prediction of a host (F, H, W) uint8/uint16 stack (numpy array or torch tensor, ideally
+        pinned): the frames go through the device in chunks, and the H2D copy of chunk i+1 and the D2H copy of
+        chunk i-1 run on their own streams while chunk i computes. Returns (result (F, C, H, W) uint8 numpy
+        array backed by a pinned buffer that the next call reuses, normalised frames (F, H, W) uint8 or None)."""
         if isinstance(frames, np.ndarray):
-            frames_dev = P.to_device_stack(frames, self.device)
+            if frames.dtype not in (np.uint8, np.uint16):
+                raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got '
+                                f'{frames.dtype}. Convert the stack (e.g. to uint16) before calling Predict.')
+            host = torch.from_numpy(np.ascontiguousarray(frames))
         else:
-            frames_dev = frames.to(self.device, non_blocking=True)
-        out = self.predict_device(frames_dev)
-        return out.cpu().numpy()
+            if frames.dtype not in (torch.uint8, torch.uint16):
+                raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got {frames.dtype}')
+            host = frames.contiguous()
+        f, h, w = host.shape
+        n_x, n_y, _, _ = P.tiling.grid_2d(h, w, self.resize_dim, self.add_tile)
+        self._ensure_plan(f * n_x * n_y)
+        if chunk_frames is None:
+            chunk_frames = max(1, min(f, self.tile_batch // (n_x * n_y)))
+        dev = self.device
+        with torch.cuda.device(dev):
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_in, s_comp, s_out = self._streams
+            cur = torch.cuda.current_stream(dev)
+            for st in self._streams:
+                st.wait_stream(cur)
+            out_host = self._pinned('out', (f, self.out_channels, h, w), torch.uint8)
+            norm_host = self._pinned('norm', (f, h, w), torch.uint8) if want_norm else None
+            pinned_in = host.is_pinned()
+            key = (chunk_frames, h, w, host.dtype)
+            if self._dev_in is None or self._dev_in[0] != key:
+                self._dev_in = (key, [torch.empty((chunk_frames, h, w), dtype=host.dtype, device=dev) for _ in range(2)])
+            dev_in = self._dev_in[1]
+            stage = None if pinned_in else [self._pinned(f'stage{b}', (chunk_frames, h, w), host.dtype) for b in range(2)]
+            ev_in = [torch.cuda.Event() for _ in range(2)]
+            ev_done = [torch.cuda.Event() for _ in range(2)]
+            for i, s0 in enumerate(range(0, f, chunk_frames)):
+                b = i & 1
+                n = min(chunk_frames, f - s0)
+                src = host[s0:s0 + n]
+                if not pinned_in:
+                    ev_in[b].synchronize()                      # the copy that last read this staging buffer is done
+                    stage[b][:n].copy_(src)
+                    src = stage[b][:n]
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_done[b])                 # the compute that last read dev_in[b] is done
+                    dev_in[b][:n].copy_(src, non_blocking=True)
+                    ev_in[b].record(s_in)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(ev_in[b])
+                    res = self.predict_device(dev_in[b][:n])
+                    norm = self.last['norm'] if want_norm else None
+                    ev_done[b].record(s_comp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[b])
+                    out_host[s0:s0 + n].copy_(res, non_blocking=True)
+                    res.record_stream(s_out)
+                    if want_norm:
+                        norm_host[s0:s0 + n].copy_(norm, non_blocking=True)
+                        norm.record_stream(s_out)
+            s_out.synchronize()
+            cur.wait_stream(s_comp)
+        return out_host.numpy(), (norm_host.numpy() if want_norm else None)
 
     def close(self):
         if self.engine is not None:
             self.engine.close()
             self.engine = None
+        self._pin, self._dev_in = {}, None
 
 
 class Predict:
@@ -191,18 +262,27 @@ class Predict:
         if self.normalization_mode in ('first', 'all'):
             ses.fixed_lut = self.__global_lut(imgs, lo, hi, chunk)
         out = np.zeros((n_local, out_channels, h, w), dtype='uint8')
-        starts = range(lo, hi, chunk)
+        # super-chunks bound the pinned host buffers; inside one, copies and compute are pipelined
+        frames_per_call = max(chunk, min(max(n_local, 1), (1 << 30) // max(h * w * max(out_channels, 2), 1)))
+        starts = range(lo, hi, frames_per_call)
         it = progress_notifier.iterator(starts) if (self.show_progress and self.dist.rank == 0) else starts
+        want_norm = ses.fixed_lut is None and mutate_input
         for s in it:
-            e = min(s + chunk, hi)
-            frames = P.to_device_stack(imgs[s:e], self.device)
-            res = ses.predict_device(frames, keep=self._keep is not None)
-            if ses.fixed_lut is None and mutate_input:
-                imgs[s:e] = ses.last['norm'].cpu().numpy()      # unet/predict.py:131 (cast back to the input dtype)
-            out[s - lo:e - lo] = res.cpu().numpy()
-            if self._keep is not None:
-                self._keep['patches'].append(ses.last['tiles'].cpu().numpy())
-                self._keep['result_patches'].append(ses.last['result_tiles'].cpu().numpy())
+            e = min(s + frames_per_call, hi)
+            if self._keep is not None:     # test hook: one chunk at a time, tiles copied out
+                for c in range(s, e, chunk):
+                    ce = min(c + chunk, e)
+                    res = ses.predict_device(P.to_device_stack(imgs[c:ce], self.device), keep=True)
+                    if want_norm:
+                        imgs[c:ce] = ses.last['norm'].cpu().numpy()
+                    out[c - lo:ce - lo] = res.cpu().numpy()
+                    self._keep['patches'].append(ses.last['tiles'].cpu().numpy())
+                    self._keep['result_patches'].append(ses.last['result_tiles'].cpu().numpy())
+                continue
+            res, norm = ses.predict_movie(imgs[s:e], chunk_frames=chunk, want_norm=want_norm)
+            if want_norm:
+                imgs[s:e] = norm                                # unet/predict.py:131 (cast back to the input dtype)
+            out[s - lo:e - lo] = res
         if self._keep is not None:   # test hook: what the reference's __split / __predict return
             self.patches = np.concatenate(self._keep['patches'])
             self.result_patches = np.concatenate(self._keep['result_patches'])
