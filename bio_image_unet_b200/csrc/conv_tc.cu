@@ -123,8 +123,9 @@ struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident; uint32_t a_buf_bytes
 // can the halo kernel take this layer? (3x3(x3) blocks, and transposed convolutions as a 1-tap GEMM)
 static bool halo_shape_ok(const ConvTcArgs& a) {
   if (halo_disabled()) return false;
-  if (a.mode == EPI_UP) { if (a.kw != 1 || a.kh != 1 || a.kd != 1) return false; }
-  else if (a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return false;
+  const bool one = a.kw == 1 && a.kh == 1 && a.kd == 1;      // transposed convolution / 1x1 gate as a plain GEMM
+  const bool three = a.kw == 3 && a.kh == 3 && (a.kd == 1 || a.kd == 3);
+  if (a.mode == EPI_UP ? !one : !(one || three)) return false;
   if (a.H < 16 || a.W < 8) return false;                 // tiny planes: the per-tap kernel packs the batch instead
   return true;
 }
@@ -133,7 +134,7 @@ static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
   HaloPlan pl{};
   pl.ok = false;
   if (!halo_shape_ok(a) || n_blk > 256) return pl;
-  const int halo = a.mode == EPI_UP ? 0 : 1;
+  const int halo = a.kw == 3 ? 1 : 0;
   const int rows = 16 + 2 * halo;
   const int taps = halo ? 9 * a.kd : 1;
   const int extra = (2 * a.n_total + (a.mode == EPI_HEAD ? a.head_n * n_blk : 0)) * 4 + 64;   // scale/shift/head
@@ -198,7 +199,7 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   p.n_blocks = a.n_total / n_blk;
   p.total_tiles = p.tiles_x * p.tiles_y * a.D * a.B * p.n_blocks;
   p.kd = a.kd;
-  p.halo = a.mode == EPI_UP ? 0 : 1;
+  p.halo = a.kw == 3 ? 1 : 0;
   p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
   p.n_blk = n_blk; p.n_total = a.n_total;
   p.a_bufs = pl.a_bufs; p.b_stages = pl.b_stages; p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;

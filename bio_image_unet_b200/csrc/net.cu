@@ -66,6 +66,18 @@ struct Builder {
     n->layers.push_back(L);
     return (int)n->layers.size() - 1;
   }
+  // AttentionBlock(F_g = F_l = c, n_coefficients = nc) reading the concat buffer [up (gate) | skip]
+  int gate_layer(const std::string& name, int c, int nc) {
+    ConvLayer L;
+    L.name = name;
+    L.segs = {{0, c, 0}, {c, c, pad16(c)}};
+    L.cin_log = 2 * c; L.cin_phys = 2 * pad16(c);
+    L.cout = nc; L.cout_pad = pad16(nc);
+    L.is_gate = true;
+    L.slope = 0.f;
+    n->layers.push_back(L);
+    return (int)n->layers.size() - 1;
+  }
   void op(OpKind kind, int layer, int src, int src_coff, int dst, int dst_coff, int c, int level, int batch_mul = 1,
           int src_img0 = 0, int dst_img0 = 0, int pool_mode = 0) {
     Op o;
@@ -97,10 +109,13 @@ int net_build(Net* n) {
               kMaxHead, n->head_total);
   BIU_REQUIRE(nf >= 2 && nf % 2 == 0, "n_filter must be even (got %d)", nf);
 
-  if (n->kind == NET_UNET2D || n->kind == NET_SIAM2D) {
+  if (n->kind == NET_UNET2D || n->kind == NET_SIAM2D || n->kind == NET_UNET2D_V0 || n->kind == NET_ATTUNET2D) {
     n->dims = 2;
     n->levels = 4;
     const bool siam = n->kind == NET_SIAM2D;
+    const bool v0 = n->kind == NET_UNET2D_V0;       // unet/unet_v0.py: ReLU blocks, skips after the first conv, decode9
+    const bool att = n->kind == NET_ATTUNET2D;      // unet/attention_unet.py: gated skips, cat((attention, up))
+    BIU_REQUIRE(!att || nf % 2 == 0, "AttentionUnet needs an even n_filter");
     BIU_REQUIRE(!(siam && n->siam_mode == SIAM_CORR), "Siam_UNet mode='corr' is not implemented by this engine");
     // 'control' ignores the previous frame (siam_unet.py:122-123): its encoder pass is dead work and is skipped
     const int bm = (siam && n->siam_mode != SIAM_CONTROL) ? 2 : 1;
@@ -116,26 +131,36 @@ int net_build(Net* n) {
     if (siam && n->siam_mode != SIAM_CONTROL) join = b.buf("join", 4, pad16(ch[3]));
     int mid1 = b.buf("mid1", 4, pad16(ch[4]));
     int mid2 = b.buf("mid2", 4, pad16(ch[4]));
+    int psi[4] = {-1, -1, -1, -1}, gate_scratch = -1;
     for (int l = 3; l >= 0; --l) {
       d_a[l] = b.buf("d" + std::to_string(2 * (3 - l) + 1), l, pad16(ch[l]));
-      d_b[l] = l > 0 ? b.buf("d" + std::to_string(2 * (3 - l) + 2), l, pad16(ch[l])) : -1;
+      d_b[l] = (l > 0 || v0) ? b.buf("d" + std::to_string(2 * (3 - l) + 2), l, pad16(ch[l])) : -1;
+      if (att) psi[l] = b.buf("psi" + std::to_string(4 - l), l, 4 / n->esz);      // one float per pixel
     }
+    if (att) gate_scratch = b.buf("gate_scratch", 0, pad16(nf / 2));              // CUDA-core fallback only
+    n->gate_scratch = gate_scratch;
     // encoder
     for (int l = 0; l < 4; ++l) {
       const std::string n1 = "encode" + std::to_string(2 * l + 1), n2 = "encode" + std::to_string(2 * l + 2);
+      // the skip tensor lives in the upper half of the level's concat buffer: the second conv's output
+      // (unet/unet.py:72-83), or the FIRST conv's for Unet_v0 (unet/unet_v0.py:91-103)
+      const int c1_dst = v0 ? cat[l] : e_a[l], c1_coff = v0 ? pad16(ch[l]) : 0;
       if (l == 0) {
         int L = b.conv_layer(n1, {{0, n->in_ch, 0}}, n->in_ch, ch[0], 3);
-        b.op(OP_FIRST, L, -1, 0, e_a[0], 0, n->in_ch, 0, 1, 0, 0);
-        if (bm == 2) b.op(OP_FIRST, L, -2, 0, e_a[0], 0, n->in_ch, 0, 1, 0, 1);
+        b.op(OP_FIRST, L, -1, 0, c1_dst, c1_coff, n->in_ch, 0, 1, 0, 0);
+        if (bm == 2) b.op(OP_FIRST, L, -2, 0, c1_dst, c1_coff, n->in_ch, 0, 1, 0, 1);
       } else {
         int L = b.conv_layer(n1, {{0, ch[l - 1], 0}}, pad16(ch[l - 1]), ch[l], 3);
-        b.op(OP_CONV, L, m[l - 1], 0, e_a[l], 0, pad16(ch[l - 1]), l, bm);
+        b.op(OP_CONV, L, m[l - 1], 0, c1_dst, c1_coff, pad16(ch[l - 1]), l, bm);
       }
       {
         int L = b.conv_layer(n2, {{0, ch[l], 0}}, pad16(ch[l]), ch[l], 3);
-        b.op(OP_CONV, L, e_a[l], 0, cat[l], pad16(ch[l]), pad16(ch[l]), l, bm);
+        if (v0) b.op(OP_CONV, L, cat[l], pad16(ch[l]), e_a[l], 0, pad16(ch[l]), l, bm);
+        else b.op(OP_CONV, L, e_a[l], 0, cat[l], pad16(ch[l]), pad16(ch[l]), l, bm);
       }
-      if (l < 3 || !siam || n->siam_mode == SIAM_MAX || n->siam_mode == SIAM_CONTROL) {
+      if (v0) {
+        b.op(OP_POOL, -1, e_a[l], 0, m[l], 0, pad16(ch[l]), l, bm);
+      } else if (l < 3 || !siam || n->siam_mode == SIAM_MAX || n->siam_mode == SIAM_CONTROL) {
         b.op(OP_POOL, -1, cat[l], pad16(ch[l]), m[l], 0, pad16(ch[l]), l, bm);
       } else {  // concat join: pooled current -> channels [0, 8nf), pooled previous -> [8nf, 16nf)
         b.op(OP_POOL, -1, cat[l], pad16(ch[l]), joincat, 0, pad16(ch[l]), l, 1, 0, 0);
@@ -160,14 +185,30 @@ int net_build(Net* n) {
       const int k = 3 - l;  // 0..3
       int U = b.up_layer("up" + std::to_string(k + 1), prev_c, ch[l]);
       b.op(OP_UP, U, prev, 0, cat[l], 0, pad16(prev_c), l + 1);
-      b.block_cat("decode" + std::to_string(2 * k + 1), cat[l], ch[l], ch[l], d_a[l], ch[l], l);
-      if (l > 0) {
+      if (att) {
+        // a = skip * psi(up, skip) in place, then decode(cat((a, up))) (unet/attention_unet.py:88-90): the
+        // block's logical channels [0, C) are the gated skip (physical upper half), [C, 2C) the up-sampled tensor
+        int G = b.gate_layer("attention" + std::to_string(k + 1), ch[l], ch[l] / 2);
+        b.op(OP_GATE, G, cat[l], 0, psi[l], 0, 2 * pad16(ch[l]), l);
+        b.op(OP_MULPSI, -1, psi[l], 0, cat[l], pad16(ch[l]), pad16(ch[l]), l);
+        int L = b.conv_layer("decode" + std::to_string(2 * k + 1), {{0, ch[l], pad16(ch[l])}, {ch[l], ch[l], 0}},
+                             2 * pad16(ch[l]), ch[l], 3);
+        b.op(OP_CONV, L, cat[l], 0, d_a[l], 0, 2 * pad16(ch[l]), l);
+      } else {
+        b.block_cat("decode" + std::to_string(2 * k + 1), cat[l], ch[l], ch[l], d_a[l], ch[l], l);
+      }
+      if (l > 0 || v0) {
         b.block("decode" + std::to_string(2 * k + 2), d_a[l], ch[l], d_b[l], 0, ch[l], l);
         prev = d_b[l]; prev_c = ch[l];
       } else {
         int L = b.conv_layer("decode8", {{0, ch[0], 0}}, pad16(ch[0]), ch[0], 3);
         b.op(OP_CONV_HEAD, L, d_a[0], 0, -1, 0, pad16(ch[0]), 0);
       }
+    }
+    if (v0) {     // decode9: 3x3 block n_filter -> 1, then the 1x1 head 1 -> 1 (unet/unet_v0.py:49-52,104-105)
+      int L = b.conv_layer("decode9", {{0, ch[0], 0}}, pad16(ch[0]), 1, 3);
+      b.op(OP_CONV_HEAD, L, d_b[0], 0, -1, 0, pad16(ch[0]), 0);
+      for (auto& L2 : n->layers) L2.slope = 0.f;                       // every block of Unet_v0 is Conv-BN-ReLU
     }
   } else if (n->kind == NET_UNET3D || n->kind == NET_MO3D) {
     n->dims = 3;
@@ -254,6 +295,73 @@ static int upload(Net* n, const std::vector<T>& h, T** dptr) {
 int net_finalize(Net* n) {
   for (auto& L : n->layers) {
     const int taps = L.kd * L.kh * L.kw;
+    if (L.is_gate) {
+      // AttentionBlock (unet/attention_unet.py:143-181): g1 + x1 = BN(conv1x1(gate)) + BN(conv1x1(skip)) is one GEMM
+      // over the concat buffer with the BatchNorm scales folded into the weights (fp64 on the host), ReLU, then
+      // psi = sigmoid(BN(conv1x1)) as a 1x1 head with BatchNorm(1) folded into its weight and bias.
+      const int c = L.cin_log / 2;
+      const char* br[2] = {".W_gate", ".W_x"};
+      std::vector<float> wd((size_t)L.cin_phys * L.cout_pad, 0.f);
+      std::vector<float> scale(L.cout_pad, 1.f), shift(L.cout_pad, 0.f);
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const std::string base = L.name + br[s2];
+        const HostTensor* w = find_param(n, base + ".0.weight");
+        const HostTensor* bias = find_param(n, base + ".0.bias");
+        const HostTensor* g = find_param(n, base + ".1.weight");
+        const HostTensor* be = find_param(n, base + ".1.bias");
+        const HostTensor* mu = find_param(n, base + ".1.running_mean");
+        const HostTensor* var = find_param(n, base + ".1.running_var");
+        BIU_REQUIRE(w && bias && g && be && mu && var, "state_dict is missing parameters of '%s'", base.c_str());
+        BIU_REQUIRE((long long)w->data.size() == (long long)L.cout * c, "'%s.0.weight' has %lld elements, expected %lld",
+                    base.c_str(), (long long)w->data.size(), (long long)L.cout * c);
+        for (int co = 0; co < L.cout; ++co) {
+          const double sc = (double)g->data[co] / std::sqrt((double)var->data[co] + 1e-5);
+          shift[co] += (float)((double)be->data[co] + ((double)bias->data[co] - (double)mu->data[co]) * sc);
+          for (int ci = 0; ci < c; ++ci)
+            wd[(size_t)(L.segs[s2].pstart + ci) * L.cout_pad + co] = (float)(sc * (double)w->data[(size_t)co * c + ci]);
+        }
+      }
+      if (upload(n, wd, &L.w_direct)) return -1;
+      if (upload(n, scale, &L.scale)) return -1;
+      if (upload(n, shift, &L.shift)) return -1;
+      if (n->precision != PREC_FP32) {
+        const size_t cnt = (size_t)L.cout_pad * L.cin_phys;
+        if (n->esz == 2) {
+          std::vector<uint16_t> wp(cnt, 0);
+          for (int co = 0; co < L.cout; ++co)
+            for (int ci = 0; ci < L.cin_phys; ++ci) wp[(size_t)co * L.cin_phys + ci] = host_bf16(wd[(size_t)ci * L.cout_pad + co]);
+          uint16_t* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_tc = d;
+        } else {
+          std::vector<float> wp(cnt, 0.f);
+          for (int co = 0; co < L.cout; ++co)
+            for (int ci = 0; ci < L.cin_phys; ++ci) wp[(size_t)co * L.cin_phys + ci] = host_round_tf32(wd[(size_t)ci * L.cout_pad + co]);
+          float* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_tc = d;
+        }
+      }
+      {
+        const std::string base = L.name + ".psi";
+        const HostTensor* w = find_param(n, base + ".0.weight");
+        const HostTensor* bias = find_param(n, base + ".0.bias");
+        const HostTensor* g = find_param(n, base + ".1.weight");
+        const HostTensor* be = find_param(n, base + ".1.bias");
+        const HostTensor* mu = find_param(n, base + ".1.running_mean");
+        const HostTensor* var = find_param(n, base + ".1.running_var");
+        BIU_REQUIRE(w && bias && g && be && mu && var, "state_dict is missing parameters of '%s'", base.c_str());
+        BIU_REQUIRE((long long)w->data.size() == (long long)L.cout, "'%s.0.weight' has %lld elements, expected %d",
+                    base.c_str(), (long long)w->data.size(), L.cout);
+        const double sc = (double)g->data[0] / std::sqrt((double)var->data[0] + 1e-5);
+        std::vector<float> gw(L.cout_pad, 0.f), gb(1, 0.f);
+        for (int co = 0; co < L.cout; ++co) gw[co] = (float)(sc * (double)w->data[co]);
+        gb[0] = (float)((double)be->data[0] + ((double)bias->data[0] - (double)mu->data[0]) * sc);
+        if (upload(n, gw, &L.gate_w)) return -1;
+        if (upload(n, gb, &L.gate_b)) return -1;
+      }
+      continue;
+    }
     if (!L.is_up) {
       const HostTensor* w = find_param(n, L.name + ".0.weight");
       const HostTensor* bias = find_param(n, L.name + ".0.bias");
@@ -428,6 +536,37 @@ __global__ void max_join_kernel(const uint4* __restrict__ a, const uint4* __rest
   }
 }
 
+// skip[pix][c] *= psi[pix] on one half of a concat buffer (AttentionBlock: out = skip_connection * psi)
+__global__ void mul_psi_kernel(void* act, int ctot, int coff, int c, const float* __restrict__ psi, long long npix,
+                               int esz, int round_tf32) {
+  const int vec = 16 / esz, cv = c / vec;
+  const long long total = npix * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const float s = __ldg(psi + pix);
+    uint4* ptr = reinterpret_cast<uint4*>(reinterpret_cast<char*>(act) + ((pix * ctot + coff) * esz + (long long)v * 16));
+    uint4 x = *ptr;
+    if (esz == 2) {
+      __nv_bfloat162* xp = reinterpret_cast<__nv_bfloat162*>(&x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 f = __bfloat1622float2(xp[k]);
+        xp[k] = __floats2bfloat162_rn(f.x * s, f.y * s);
+      }
+    } else {
+      float* xp = reinterpret_cast<float*>(&x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t = xp[k] * s;
+        if (round_tf32) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t)); t = __uint_as_float(u); }
+        xp[k] = t;
+      }
+    }
+    *ptr = x;
+  }
+}
+
 int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out_val, uint8_t* out_u8,
                 void* workspace, cudaStream_t stream) {
   BIU_REQUIRE(n->finalized, "network weights were not finalized");
@@ -471,7 +610,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         a.in = o.src == -1 ? in : in2;
         BIU_REQUIRE(a.in != nullptr, "network input pointer is null");
         a.cin = n->in_ch; a.W = w; a.H = h; a.D = d; a.B = n->B; a.kd = L.kd;
-        a.wgt = L.w_direct; a.cout = L.cout_pad; a.slope = 0.1f; a.scale = L.scale; a.shift = L.shift;
+        a.wgt = L.w_direct; a.cout = L.cout_pad; a.slope = L.slope; a.scale = L.scale; a.shift = L.shift;
         a.esz = n->esz; a.out = dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
         a.cout_pad = L.cout_pad; a.round_tf32 = round_tf32;
         if (int rc = launch_first_conv(a, stream)) return rc;
@@ -485,7 +624,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         memset(&a, 0, sizeof(a));
         a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.cin = L.cin_phys;
         a.W = w; a.H = h; a.D = d; a.B = batch; a.kw = L.kw; a.kh = L.kh; a.kd = L.kd;
-        a.wgt = L.w_tc; a.n_total = L.cout_pad; a.mode = head ? EPI_HEAD : EPI_CONV; a.slope = 0.1f;
+        a.wgt = L.w_tc; a.n_total = L.cout_pad; a.mode = head ? EPI_HEAD : EPI_CONV; a.slope = L.slope;
         a.scale = L.scale; a.shift = L.shift;
         a.out = head ? nullptr : dst_ptr(d, h, w);
         a.out_ctot = head ? 0 : db->ctot; a.out_coff = o.dst_coff;
@@ -516,7 +655,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
           memset(&da, 0, sizeof(da));
           da.esz = n->esz; da.in = src; da.in_ctot = sb->ctot; da.in_coff = o.src_coff; da.cin = L.cin_phys;
           da.W = w; da.H = h; da.D = d; da.B = batch; da.kw = L.kw; da.kh = L.kh; da.kd = L.kd;
-          da.wgt = L.w_direct; da.cout = L.cout_pad; da.slope = 0.1f; da.scale = L.scale; da.shift = L.shift;
+          da.wgt = L.w_direct; da.cout = L.cout_pad; da.slope = L.slope; da.scale = L.scale; da.shift = L.shift;
           da.round_tf32 = round_tf32;
           if (!head) {
             da.out = dst_ptr(d, h, w); da.out_ctot = db->ctot; da.out_coff = o.dst_coff;
@@ -582,6 +721,54 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         a.W = w; a.H = h; a.D = d; a.B = batch; a.dims = n->dims;
         a.out = dst_ptr(n->dims == 3 ? 2 * d : d, 2 * h, 2 * w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
         if (int rc = launch_up_nearest(a, stream)) return rc;
+        break;
+      }
+      case OP_GATE: {
+        const ConvLayer& L = n->layers[o.layer];
+        float* psi = reinterpret_cast<float*>(ws + db->offset);
+        ConvTcArgs a;
+        memset(&a, 0, sizeof(a));
+        a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.cin = L.cin_phys;
+        a.W = w; a.H = h; a.D = d; a.B = batch; a.kw = a.kh = a.kd = 1;
+        a.wgt = L.w_tc; a.n_total = L.cout_pad; a.mode = EPI_HEAD; a.slope = 0.f;
+        a.scale = L.scale; a.shift = L.shift; a.out = nullptr;
+        a.head_n = 1; a.head_w = L.gate_w; a.head_b = L.gate_b; a.head_act[0] = ACT_SIGMOID;
+        a.out_val = psi; a.out_u8 = nullptr;
+        if (tc_allowed && L.w_tc && conv_tc_supported(a)) {
+          if (int rc = launch_conv_tc(a, stream)) return rc;
+        } else {
+          n->op_kinds[op_index] += 16;
+          BIU_REQUIRE(n->gate_scratch >= 0, "no scratch buffer for the attention gate");
+          const Buf& scratch = n->bufs[n->gate_scratch];
+          DirectConvArgs da;
+          memset(&da, 0, sizeof(da));
+          da.esz = n->esz; da.in = src; da.in_ctot = sb->ctot; da.in_coff = o.src_coff; da.cin = L.cin_phys;
+          da.W = w; da.H = h; da.D = d; da.B = batch; da.kw = da.kh = da.kd = 1;
+          da.wgt = L.w_direct; da.cout = L.cout_pad; da.slope = 0.f; da.scale = L.scale; da.shift = L.shift;
+          da.round_tf32 = 0;
+          da.out = ws + scratch.offset; da.out_ctot = L.cout_pad; da.out_coff = 0;
+          if (int rc = launch_direct_conv(da, stream)) return rc;
+          HeadArgs ha;
+          memset(&ha, 0, sizeof(ha));
+          ha.esz = n->esz; ha.in = da.out; ha.in_ctot = L.cout_pad; ha.in_coff = 0; ha.cin = L.cout_pad;
+          ha.npix_per_img = (long long)d * h * w; ha.B = batch; ha.head_n = 1;
+          ha.w = L.gate_w; ha.b = L.gate_b; ha.act[0] = ACT_SIGMOID;
+          ha.out_val = psi; ha.out_u8 = nullptr;
+          if (int rc = launch_head(ha, stream)) return rc;
+        }
+        break;
+      }
+      case OP_MULPSI: {
+        const long long npix = (long long)batch * d * h * w;
+        const int vec = 16 / n->esz;
+        long long blocks = ceil_div_ll(npix * (o.c / vec), 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks < 1) blocks = 1;
+        mul_psi_kernel<<<(int)blocks, 256, 0, stream>>>(ws + db->offset, db->ctot, o.dst_coff, o.c,
+                                                        reinterpret_cast<const float*>(ws + sb->offset), npix, n->esz,
+                                                        round_tf32);
+        BIU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
         break;
       }
       case OP_MAXJOIN: {

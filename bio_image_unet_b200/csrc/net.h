@@ -10,7 +10,7 @@
 
 namespace biu {
 
-enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3 };
+enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3, NET_UNET2D_V0 = 4, NET_ATTUNET2D = 5 };
 enum Precision { PREC_BF16 = 0, PREC_TF32 = 1, PREC_FP32 = 2 };
 enum SiamMode { SIAM_CONCAT = 0, SIAM_MAX = 1, SIAM_CONTROL = 2, SIAM_CORR = 3 };
 
@@ -28,7 +28,11 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   int cin_log = 0, cout = 0, cin_phys = 0, cout_pad = 0;
   int kd = 1, kh = 1, kw = 1;
   bool is_up = false;
+  bool is_gate = false;      // AttentionBlock: 1x1 convs of gate + skip folded into one GEMM, psi as its 1x1 head
   int nq = 1;
+  float slope = 0.1f;        // LeakyReLU slope of the block (0 = ReLU: Unet_v0, attention gate)
+  float* gate_w = nullptr;   // is_gate: psi weights [cout_pad] and bias [1] (BatchNorm(1) folded)
+  float* gate_b = nullptr;
   std::vector<Segment> segs;
   void* w_tc = nullptr;      // packed [tap][n][cin_phys] bf16 / tf32
   float* w_direct = nullptr; // fp32 [tap or q][cin_phys][cout_pad]
@@ -36,7 +40,7 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   float* shift = nullptr;
 };
 
-enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN };
+enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN, OP_GATE, OP_MULPSI };
 
 struct Op {
   OpKind kind;
@@ -72,6 +76,7 @@ struct Net {
   std::vector<Op> ops;
   float* head_w = nullptr;
   float* head_b = nullptr;
+  int gate_scratch = -1;            // AttentionUnet: buffer for the CUDA-core fallback of the gate GEMM
   std::vector<void*> dev_allocs;
 
   // plan

@@ -10,7 +10,8 @@ import torch
 
 from . import _lib
 
-KIND = {'unet2d': 0, 'siam2d': 1, 'unet3d': 2, 'mo3d': 3}
+KIND = {'unet2d': 0, 'siam2d': 1, 'unet3d': 2, 'mo3d': 3, 'unet2d_v0': 4, 'attunet2d': 5}
+KIND_2D = ('unet2d', 'siam2d', 'unet2d_v0', 'attunet2d')
 PRECISION = {'bf16': 0, 'tf32': 1, 'fp32': 2}
 SIAM_MODE = {'concat': 0, 'max': 1, 'control': 2, 'corr': 3}
 ACT = {None: 0, 'none': 0, 'sigmoid': 1, 'tanh': 2, 'relu': 3}
@@ -95,7 +96,7 @@ class Engine:
             raise TypeError('tiles must be uint8 or float32')
         d, h, w = self.tile
         assert tiles.numel() == self.batch * self.in_channels * d * h * w, (tiles.shape, self.batch, self.tile)
-        spatial = (h, w) if self.kind in ('unet2d', 'siam2d') else (d, h, w)
+        spatial = (h, w) if self.kind in KIND_2D else (d, h, w)
         shape = (self.batch, self.head_total, *spatial)
         val = torch.empty(shape, dtype=torch.float32, device=self.device) if want_val else None
         u8 = torch.empty(shape, dtype=torch.uint8, device=self.device) if want_u8 else None

@@ -21,8 +21,11 @@ class Session:
     ``Predict`` (the reference's constructor-runs-everything class) is a thin wrapper around this.
     """
 
+    KINDS = {'Unet': 'unet2d', 'AttentionUnet': 'attunet2d', 'Unet_v0': 'unet2d_v0'}
+
     def __init__(self, model_params, resize_dim=(512, 512), invert=False, normalization_mode='single',
-                 clip_threshold=(0., 99.8), add_tile=0, device='cuda:0', precision='tf32', workspace_gb=24.0):
+                 clip_threshold=(0., 99.8), add_tile=0, device='cuda:0', precision='tf32', workspace_gb=24.0,
+                 network='Unet'):
         if normalization_mode not in ('single', 'first', 'all'):
             raise ValueError(f'normalization_mode {normalization_mode} not valid!')
         params = torch.load(model_params, map_location='cpu') if isinstance(model_params, str) else model_params
@@ -31,7 +34,9 @@ class Session:
         self.normalization_mode, self.clip_threshold = normalization_mode, clip_threshold
         self.out_channels = params['out_channels']
         self.workspace_bytes = int(workspace_gb * 2 ** 30)
-        self.engine = Engine('unet2d', params['state_dict'], params['n_filter'], params['in_channels'],
+        if network not in self.KINDS:
+            raise ValueError(f"unknown network '{network}'")
+        self.engine = Engine(self.KINDS[network], params['state_dict'], params['n_filter'], params['in_channels'],
                              [('', self.out_channels, 'sigmoid')], precision=precision, device=self.device)
         self.tile_batch = None
         self.fixed_lut = None          # set for 'first' / 'all' (stack-wide statistics)
@@ -160,7 +165,7 @@ class Predict:
     imgs : ndarray or str      images to predict; a string is read as a TIFF file
     result_name : str          path of the result TIFF
     model_params : str         path of the checkpoint (.pt) written by the reference's Trainer
-    network                    'Unet' (string or class); None reads model_params['network']
+    network                    'Unet' | 'AttentionUnet' | 'Unet_v0' (string or class); None reads model_params['network']
     resize_dim                 tile size (multiples of 16)
     invert, normalization_mode ('single' | 'first' | 'all'), clip_threshold, add_tile, normalize_result,
     show_progress, device, progress_notifier : as in the reference
@@ -211,18 +216,20 @@ class Predict:
                 network = self.model_params['network']
             else:
                 raise ValueError('network is not defined')
+        # strings as in unet/predict.py:89-97, or a class (the reference's or this package's) identified by name
         name = network if isinstance(network, str) else getattr(network, '__name__', str(network))
-        if name in ('AttentionUnet', 'Unet_v0'):
-            raise NotImplementedError(f"network '{name}' is not implemented by the B200 engine yet (Unet is)")
-        if name != 'Unet':
+        if name not in Session.KINDS:
             raise ValueError(f"unknown network '{name}'")
+        if name == 'Unet_v0' and 'in_channels' not in self.model_params.keys():
+            self.model_params['in_channels'] = 1          # old checkpoints, unet/predict.py:95-97
+            self.model_params['out_channels'] = 1
         out_channels = self.model_params['out_channels']
         if self.model_params['in_channels'] != 1:
             # the reference's tile array has a single channel (unet/predict.py:158) and its .view() fails otherwise
             raise RuntimeError("shape '[1, %d, %d, %d]' is invalid for input of size %d" % (
                 self.model_params['in_channels'], resize_dim[0], resize_dim[1], resize_dim[0] * resize_dim[1]))
         self.session = Session(self.model_params, resize_dim, invert, normalization_mode, clip_threshold, add_tile,
-                               self.device, precision, workspace_gb)
+                               self.device, precision, workspace_gb, network=name)
 
         # frames of this rank
         t_total = self.imgs_shape[0]

@@ -25,7 +25,9 @@ extern "C" {
 enum { BIU_NET_UNET2D = 0,   /* unet/unet.py:5 Unet */
        BIU_NET_SIAM2D = 1,   /* siam_unet/siam_unet.py:7 Siam_UNet */
        BIU_NET_UNET3D = 2,   /* unet3d/unet3d.py:6 UNet3D */
-       BIU_NET_MO3D   = 3 }; /* multi_output_unet3d/multi_output_unet3d.py:7 MultiOutputUnet3D */
+       BIU_NET_MO3D   = 3,   /* multi_output_unet3d/multi_output_unet3d.py:7 MultiOutputUnet3D */
+       BIU_NET_UNET2D_V0 = 4, /* unet/unet_v0.py:5 Unet_v0 (ReLU blocks, early skips, decode9) */
+       BIU_NET_ATTUNET2D = 5 }; /* unet/attention_unet.py:5 AttentionUnet (gated skip connections) */
 enum { BIU_PREC_BF16 = 0,    /* bf16 operands on tcgen05, fp32 accumulate */
        BIU_PREC_TF32 = 1,    /* tf32 operands on tcgen05, fp32 storage */
        BIU_PREC_FP32 = 2 };  /* fp32 CUDA-core kernels */

@@ -44,6 +44,67 @@ def unet_forward(sd, x, collect=None):
     return torch.sigmoid(logits), logits
 
 
+def _block_relu(sd, name, x):
+    """Unet_v0's block: Conv(k=3,pad=1) -> BatchNorm(eval) -> ReLU -> Dropout (identity in eval),
+    unet/unet_v0.py:56-63."""
+    w, b = sd[f'{name}.0.weight'], sd[f'{name}.0.bias']
+    y = F.conv2d(x, w, b, padding=1)
+    y = F.batch_norm(y, sd[f'{name}.1.running_mean'], sd[f'{name}.1.running_var'], sd[f'{name}.1.weight'],
+                     sd[f'{name}.1.bias'], training=False, eps=1e-5)
+    return F.relu(y)
+
+
+def unet_v0_forward(sd, x):
+    """Unet_v0.forward, unet/unet_v0.py:72-106: ReLU blocks, skips taken after the FIRST conv of each level
+    (e7/e5/e3/e1), an extra 3x3 block decode9 (n_filter -> 1) before the 1x1 head."""
+    B = _block_relu
+    e1 = B(sd, 'encode1', x); e2 = B(sd, 'encode2', e1); m1 = F.max_pool2d(e2, 2, 2)
+    e3 = B(sd, 'encode3', m1); e4 = B(sd, 'encode4', e3); m2 = F.max_pool2d(e4, 2, 2)
+    e5 = B(sd, 'encode5', m2); e6 = B(sd, 'encode6', e5); m3 = F.max_pool2d(e6, 2, 2)
+    e7 = B(sd, 'encode7', m3); e8 = B(sd, 'encode8', e7); m4 = F.max_pool2d(e8, 2, 2)
+    mid2 = B(sd, 'middle_conv2', B(sd, 'middle_conv1', m4))
+    d2 = B(sd, 'decode2', B(sd, 'decode1', torch.cat((_up(sd, 'up1', mid2), e7), 1)))
+    d4 = B(sd, 'decode4', B(sd, 'decode3', torch.cat((_up(sd, 'up2', d2), e5), 1)))
+    d6 = B(sd, 'decode6', B(sd, 'decode5', torch.cat((_up(sd, 'up3', d4), e3), 1)))
+    d8 = B(sd, 'decode8', B(sd, 'decode7', torch.cat((_up(sd, 'up4', d6), e1), 1)))
+    d9 = B(sd, 'decode9', d8)
+    logits = F.conv2d(d9, sd['final.0.weight'], sd['final.0.bias'])
+    return torch.sigmoid(logits), logits
+
+
+def _attention(sd, name, gate, skip):
+    """AttentionBlock.forward, unet/attention_unet.py:163-181: psi = sigmoid(BN(conv1x1(relu(BN(conv1x1(gate)) +
+    BN(conv1x1(skip)))))), out = skip * psi."""
+    def cb(prefix, t):
+        y = F.conv2d(t, sd[f'{prefix}.0.weight'], sd[f'{prefix}.0.bias'])
+        return F.batch_norm(y, sd[f'{prefix}.1.running_mean'], sd[f'{prefix}.1.running_var'], sd[f'{prefix}.1.weight'],
+                            sd[f'{prefix}.1.bias'], training=False, eps=1e-5)
+    psi = F.relu(cb(f'{name}.W_gate', gate) + cb(f'{name}.W_x', skip))
+    psi = torch.sigmoid(cb(f'{name}.psi', psi))
+    return skip * psi
+
+
+def attention_unet_forward(sd, x, collect=None):
+    """AttentionUnet.forward, unet/attention_unet.py:69-108: Unet encoder; in the decoder the skip tensor is gated
+    by the up-sampled tensor and concatenated FIRST: cat((attention(u, e), u))."""
+    e1 = _block(sd, 'encode1', x); e2 = _block(sd, 'encode2', e1); m1 = F.max_pool2d(e2, 2, 2)
+    e3 = _block(sd, 'encode3', m1); e4 = _block(sd, 'encode4', e3); m2 = F.max_pool2d(e4, 2, 2)
+    e5 = _block(sd, 'encode5', m2); e6 = _block(sd, 'encode6', e5); m3 = F.max_pool2d(e6, 2, 2)
+    e7 = _block(sd, 'encode7', m3); e8 = _block(sd, 'encode8', e7); m4 = F.max_pool2d(e8, 2, 2)
+    x = _block(sd, 'middle_conv2', _block(sd, 'middle_conv1', m4))
+    for k, e in enumerate((e8, e6, e4, e2)):
+        u = _up(sd, f'up{k + 1}', x)
+        a = _attention(sd, f'attention{k + 1}', u, e)
+        if collect is not None:
+            collect[f'a{k + 1}'] = a
+        x = _block(sd, f'decode{2 * k + 2}', _block(sd, f'decode{2 * k + 1}', torch.cat((a, u), 1)))
+    logits = F.conv2d(x, sd['final.0.weight'], sd['final.0.bias'])
+    return torch.sigmoid(logits), logits
+
+
+FORWARD_2D = {'Unet': unet_forward, 'Unet_v0': unet_v0_forward, 'AttentionUnet': attention_unet_forward}
+
+
 def _siam_encoder(sd, x):
     """One pass of the shared-weight encoder, siam_unet/siam_unet.py:87-98 (== :101-112)."""
     e1 = _block(sd, 'encode1', x); e2 = _block(sd, 'encode2', e1); m1 = F.max_pool2d(e2, 2, 2)

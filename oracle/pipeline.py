@@ -160,21 +160,23 @@ def _to_sd(state_dict):
     return {k: (v if torch.is_tensor(v) else torch.from_numpy(np.asarray(v))) for k, v in state_dict.items()}
 
 
-def predict_tiles_unet(sd, patches):
-    """unet.Predict.__predict (unet/predict.py:184-202): batch 1, float32(u8)/255, (sigmoid*255).astype(uint8)."""
+def predict_tiles_unet(sd, patches, network='Unet'):
+    """unet.Predict.__predict (unet/predict.py:184-202): batch 1, float32(u8)/255, (sigmoid*255).astype(uint8).
+    `network`: 'Unet' | 'AttentionUnet' | 'Unet_v0' (unet/predict.py:89-97)."""
     sd = _to_sd(sd)
+    forward = models.FORWARD_2D[network]
     out_ch = sd['final.0.weight'].shape[0]
     res = np.zeros((patches.shape[0], out_ch, *patches.shape[2:]), dtype='uint8')
     with torch.no_grad():
         for i, p in enumerate(patches):
             x = torch.from_numpy(p.astype('float32') / 255).view(1, p.shape[0], *p.shape[1:])
-            r = models.unet_forward(sd, x)[0].view(out_ch, *p.shape[1:]).numpy()
+            r = forward(sd, x)[0].view(out_ch, *p.shape[1:]).numpy()
             res[i] = (r * 255).astype('uint8')
     return res
 
 
 def unet_predict(imgs, sd, resize_dim=(512, 512), invert=False, normalization_mode='single',
-                 clip_threshold=(0., 99.8), add_tile=0, stages=None):
+                 clip_threshold=(0., 99.8), add_tile=0, stages=None, network='Unet'):
     """unet.Predict end to end (unet/predict.py:54-113) minus file I/O. Returns the stitched uint8 result (the
     reference then stores it as float16, utils/utils.py:21). `stages` (dict) receives intermediates."""
     if imgs.ndim == 2:
@@ -182,7 +184,7 @@ def unet_predict(imgs, sd, resize_dim=(512, 512), invert=False, normalization_mo
     shape = imgs.shape
     imgs = preprocess_stack(imgs, normalization_mode, clip_threshold, invert)
     patches, grid = split_2d(imgs, resize_dim, add_tile)
-    res = predict_tiles_unet(sd, patches)
+    res = predict_tiles_unet(sd, patches, network)
     out = stitch_mean_2d(res, shape[0], shape[1:], resize_dim, grid)
     if stages is not None:
         stages.update(patches=patches, result_patches=res, grid=grid)

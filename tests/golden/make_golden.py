@@ -21,6 +21,8 @@ from oracle import ref_import  # noqa: E402
 ref = ref_import.import_reference()
 from bio_image_unet.unet.predict import Predict as UnetPredict  # noqa: E402
 from bio_image_unet.unet.unet import Unet  # noqa: E402
+from bio_image_unet.unet.attention_unet import AttentionUnet  # noqa: E402
+from bio_image_unet.unet.unet_v0 import Unet_v0  # noqa: E402
 from bio_image_unet.siam_unet.predict import Predict as SiamPredict  # noqa: E402
 from bio_image_unet.siam_unet.siam_unet import Siam_UNet  # noqa: E402
 from bio_image_unet.unet3d.predict import Predict as Unet3dPredict  # noqa: E402
@@ -101,20 +103,23 @@ def save(name, **arrays):
     print(f'{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB')
 
 
-def gen_unet(name, shape, resize_dim, add_tile, mode, invert, seed, dtype='uint16', nf=4):
+def gen_unet(name, shape, resize_dim, add_tile, mode, invert, seed, dtype='uint16', nf=4, network='Unet'):
     torch.manual_seed(seed)
-    model = stress_init(Unet(n_filter=nf), seed)
+    model = stress_init({'Unet': Unet, 'AttentionUnet': AttentionUnet, 'Unet_v0': Unet_v0}[network](n_filter=nf), seed)
     ckpt = f'/tmp/golden_{name}.pt'
-    torch.save({'state_dict': model.state_dict(), 'n_filter': nf, 'in_channels': 1, 'out_channels': 1}, ckpt)
+    params = {'state_dict': model.state_dict(), 'n_filter': nf, 'in_channels': 1, 'out_channels': 1}
+    if network == 'Unet_v0':          # old checkpoints carry no channel counts (unet/predict.py:94-97)
+        del params['in_channels'], params['out_channels']
+    torch.save(params, ckpt)
     imgs = blobs(shape, seed, dtype)
     original = imgs.copy()
     with Capture(UnetPredict, ['split', 'predict', 'stitch']) as cap:
-        p = UnetPredict(imgs, 'res_' + name, ckpt, network='Unet', resize_dim=resize_dim, invert=invert,
+        p = UnetPredict(imgs, 'res_' + name, ckpt, network=network, resize_dim=resize_dim, invert=invert,
                         normalization_mode=mode, clip_threshold=(0., 99.8), add_tile=add_tile, show_progress=False,
                         device='cpu')
     result_file = ref_import.TIFF_STORE['res_' + name]
     save(name, imgs=original, imgs_after=imgs, resize_dim=np.array(resize_dim), add_tile=add_tile,
-         invert=int(invert), mode=mode, clip=np.array([0., 99.8]), n_filter=nf,
+         invert=int(invert), mode=mode, clip=np.array([0., 99.8]), n_filter=nf, network=network,
          N_x=p.N_x, N_y=p.N_y, X_start=p.X_start, Y_start=p.Y_start, patches=cap.out['split'][0],
          result_patches=cap.out['predict'][0], result=cap.out['stitch'][0], result_file=result_file,
          **sd_arrays(model))
@@ -177,6 +182,17 @@ def gen_mo3d(name, shape, max_patch, overlap, norm_mode, interp, seed, nf=4, bat
 
 if __name__ == '__main__':
     torch.set_num_threads(4)
+    only = sys.argv[1:]            # optional: names of the fixtures to (re)generate
+    if only:
+        _save = save
+
+        def save(name, **arrays):  # noqa: F811
+            if name in only:
+                _save(name, **arrays)
+    gen_unet('attunet_single', (2, 70, 90), (32, 48), 1, 'single', False, seed=15, network='AttentionUnet', nf=8)
+    gen_unet('unetv0_all', (2, 64, 80), (32, 32), 1, 'all', False, seed=16, network='Unet_v0')
+    if only:
+        sys.exit(0)
     gen_unet('unet_single', (2, 70, 90), (32, 48), 1, 'single', False, seed=11)
     gen_unet('unet_all_invert', (3, 64, 64), (32, 32), 1, 'all', True, seed=12)
     gen_unet('unet_first_u8', (2, 48, 80), (32, 32), 0, 'first', False, seed=13, dtype='uint8')

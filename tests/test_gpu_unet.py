@@ -238,3 +238,113 @@ def test_fused_maxpool_is_bit_identical(precision, tile):
         assert np.array_equal(a_fused[n], a_plain[n]), n
     assert torch.equal(v_fused, v_plain) and torch.equal(u_fused, u_plain)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AttentionUnet / Unet_v0 (unet.Predict(network=...), unet/predict.py:89-97)
+# ---------------------------------------------------------------------------------------------------------------
+def _variant_state_dict(network, n_filter, seed, stress):
+    """State dict of the product's own module class; 'stress' = Kaiming weights + randomised BN statistics."""
+    from bio_image_unet_b200.unet import AttentionUnet, Unet_v0
+    torch.manual_seed(seed)
+    m = (AttentionUnet if network == 'AttentionUnet' else Unet_v0)(n_filter=n_filter)
+    sd = m.state_dict()
+    if not stress:
+        return sd
+    g = torch.Generator().manual_seed(seed)
+    for k, v in sd.items():
+        if k.endswith('num_batches_tracked'):
+            continue
+        if k.endswith('.0.weight') or (k.startswith('up') and k.endswith('weight')):
+            fan_in = v[0].numel() if not k.startswith('up') else v.shape[0]
+            sd[k] = torch.randn(v.shape, generator=g) * (2.0 / fan_in) ** 0.5
+        elif k.endswith('.0.bias') or (k.startswith('up') and k.endswith('bias')):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.05
+        elif k.endswith('running_var') or k.endswith('.1.weight'):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        else:
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+    return sd
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('regime', ['default', 'stress'])
+@pytest.mark.parametrize('network,n_filter,tile,batch', [('AttentionUnet', 32, (64, 64), 2), ('AttentionUnet', 8, (32, 48), 3),
+                                                         ('AttentionUnet', 16, (256, 128), 1),
+                                                         ('Unet_v0', 32, (64, 64), 2), ('Unet_v0', 4, (48, 32), 3),
+                                                         ('Unet_v0', 16, (256, 128), 1)])
+def test_variant_forward_matches_oracle(precision, regime, network, n_filter, tile, batch):
+    from bio_image_unet_b200.engine import Engine
+    g = torch.Generator().manual_seed(17)
+    tiles = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
+    sd = _variant_state_dict(network, n_filter, 200 + n_filter, regime == 'stress')
+    forward = omodels.FORWARD_2D[network]
+    with torch.no_grad():
+        ref, logits = forward(sd, tiles.float() / 255)
+        if regime == 'stress':          # rescale the head so that the logits have unit variance (steep sigmoid)
+            sd['final.0.weight'] = sd['final.0.weight'] / logits.std()
+            sd['final.0.bias'] = (sd['final.0.bias'] - logits.mean()) / logits.std()
+            ref, logits = forward(sd, tiles.float() / 255)
+    tol = TOL[precision] if regime == 'default' else TOL_STRESS[precision]
+    kind = 'attunet2d' if network == 'AttentionUnet' else 'unet2d_v0'
+    eng = Engine(kind, sd, n_filter, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
+    eng.plan(batch, tile)
+    val, u8 = eng.forward(tiles.cuda(), want_val=True, want_u8=True)
+    torch.cuda.synchronize()
+    err = (val.cpu() - ref).abs().max().item()
+    assert err < tol, (network, precision, regime, err)
+    ref_u8 = (ref.numpy() * 255).astype('uint8')
+    d = np.abs(u8.cpu().numpy().astype(np.int16) - ref_u8.astype(np.int16))
+    assert d.max() <= 1 + int(np.ceil(tol * 255)), d.max()
+    eng.close()
+
+
+def test_attention_gate_matches_oracle_activations():
+    """The gated skip tensors a1..a4 (skip * psi) against the oracle, exact-fp32 mode and tf32 tensor-core mode."""
+    from bio_image_unet_b200.engine import Engine
+    sd = _variant_state_dict('AttentionUnet', 32, 5, True)
+    tiles = torch.randint(0, 256, (2, 1, 128, 128), dtype=torch.uint8, generator=torch.Generator().manual_seed(2))
+    acts = {}
+    with torch.no_grad():
+        omodels.attention_unet_forward(sd, tiles.float() / 255, collect=acts)
+    for precision, tol in (('fp32', 2e-4), ('tf32', 3e-2)):
+        eng = Engine('attunet2d', sd, 32, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
+        eng.plan(2, (128, 128))
+        eng.forward(tiles.cuda(), want_val=True)
+        for k, (c, level) in enumerate([(256, 3), (128, 2), (64, 1), (32, 0)]):
+            cat = eng.debug_activation(f'cat{k + 1}', 2 * c, level)          # [up | gated skip], NHWC
+            got = torch.from_numpy(cat[:, 0, :, :, c:].copy()).permute(0, 3, 1, 2)
+            ref = acts[f'a{k + 1}']
+            scale = ref.abs().max().item()
+            assert (got - ref).abs().max().item() <= tol * max(scale, 1.0), (precision, k)
+        eng.close()
+
+
+@pytest.mark.parametrize('name', ['attunet_single', 'unetv0_all'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('as_class', [False, True])
+def test_variant_predict_matches_reference_golden(name, precision, as_class, tmp_path):
+    from bio_image_unet_b200 import tiff, unet
+    g = _golden.load(name)
+    network = str(g['network'])
+    params = {'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1, 'out_channels': 1}
+    if network == 'Unet_v0':            # old checkpoints carry no channel counts (unet/predict.py:94-97)
+        del params['in_channels'], params['out_channels']
+    ckpt = str(tmp_path / 'model.pt')
+    torch.save(params, ckpt)
+    imgs = g['imgs'].copy()
+    res_file = str(tmp_path / 'res.tif')
+    net_arg = getattr(unet, network) if as_class else network
+    p = unet.Predict(imgs, res_file, ckpt, network=net_arg, resize_dim=tuple(int(v) for v in g['resize_dim']),
+                     invert=bool(g['invert']), normalization_mode=str(g['mode']), clip_threshold=tuple(g['clip']),
+                     add_tile=int(g['add_tile']), show_progress=False, device='cuda:0', precision=precision,
+                     keep_intermediates=True)
+    assert (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
+    assert np.array_equal(p.X_start, g['X_start']) and np.array_equal(p.Y_start, g['Y_start'])
+    assert np.array_equal(p.patches, g['patches'])
+    lsb = LSB_GOLDEN[precision]
+    d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
+    assert d.max() <= lsb, d.max()
+    out = tiff.imread(res_file)
+    assert out.dtype == np.float16 and out.shape == g['result_file'].shape
+    assert np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= lsb

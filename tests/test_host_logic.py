@@ -138,6 +138,11 @@ def test_training_mode_forward_matches_oracle_cpu():
     with torch.no_grad():
         u = bn_eval(Unet(n_filter=4))
         assert torch.allclose(u(x2)[1], om.unet_forward(u.state_dict(), x2)[1], atol=1e-5)
+        from bio_image_unet_b200.unet import AttentionUnet, Unet_v0
+        a = bn_eval(AttentionUnet(n_filter=4))
+        assert torch.allclose(a(x2)[1], om.attention_unet_forward(a.state_dict(), x2)[1], atol=1e-5)
+        v0 = bn_eval(Unet_v0(n_filter=4, in_channels=1, out_channels=1))
+        assert torch.allclose(v0(x2)[1], om.unet_v0_forward(v0.state_dict(), x2)[1], atol=1e-5)
         for mode in ('concat', 'max', 'control', 'corr'):
             s = bn_eval(Siam_UNet(4, mode))
             assert torch.allclose(s(x2, x2.flip(2))[1], om.siam_forward(s.state_dict(), x2, x2.flip(2), mode)[1], atol=1e-5)
@@ -152,9 +157,10 @@ def test_training_mode_forward_matches_oracle_cpu():
 def test_state_dict_layouts_match_reference():
     from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
     from bio_image_unet_b200.siam_unet import Siam_UNet
-    from bio_image_unet_b200.unet import Unet
+    from bio_image_unet_b200.unet import AttentionUnet, Unet, Unet_v0
     from bio_image_unet_b200.unet3d import UNet3D
     cases = [('unet_single', Unet(n_filter=4), 136), ('siam_concat', Siam_UNet(4, 'concat'), 143),
+             ('attunet_single', AttentionUnet(n_filter=8), 220), ('unetv0_all', Unet_v0(n_filter=4), 143),
              ('siam_max', Siam_UNet(4, 'max'), 136), ('unet3d_overlap', UNet3D(n_filter=4), 106),
              ('mo3d_interp', MultiOutputUnet3D(1, _golden.MO3D_HEADS, 4, True), 125)]
     for name, model, count in cases:
