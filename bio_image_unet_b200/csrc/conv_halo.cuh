@@ -254,19 +254,18 @@ __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const ui
     if (MODE == EPI_HEAD) {
 #pragma unroll
       for (int h = 0; h < kMaxHead; ++h) {
-        if (h < p.head_n) {
-          const float4* hw4 = reinterpret_cast<const float4*>(s_hw + h * p.n_blk + q * 16);
-          float sacc = hacc[h];
+        if (h >= p.head_n) break;                     // uniform exit: no predicated-off work for absent heads
+        const float4* hw4 = reinterpret_cast<const float4*>(s_hw + h * p.n_blk + q * 16);
+        float sacc = hacc[h];
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 w = hw4[i4];
-            sacc = fmaf(v[4 * i4 + 0], w.x, sacc);
-            sacc = fmaf(v[4 * i4 + 1], w.y, sacc);
-            sacc = fmaf(v[4 * i4 + 2], w.z, sacc);
-            sacc = fmaf(v[4 * i4 + 3], w.w, sacc);
-          }
-          hacc[h] = sacc;
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 w = hw4[i4];
+          sacc = fmaf(v[4 * i4 + 0], w.x, sacc);
+          sacc = fmaf(v[4 * i4 + 1], w.y, sacc);
+          sacc = fmaf(v[4 * i4 + 2], w.z, sacc);
+          sacc = fmaf(v[4 * i4 + 3], w.w, sacc);
         }
+        hacc[h] = sacc;
       }
       if (p.out == nullptr) continue;
     }
@@ -380,12 +379,11 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
           const long long sp = ((long long)tl.z0 * p.H + py) * p.W + px0 + 8 * j;
 #pragma unroll
           for (int h = 0; h < kMaxHead; ++h) {
-            if (h < p.head_n) {
-              const float val = apply_head_act(hacc[h] + __ldg(p.head_b + h), p.head_act[h]);
-              const long long o2 = ((long long)tl.b0 * p.head_n + h) * plane + sp;
-              if (p.out_val) p.out_val[o2] = val;
-              if (p.out_u8) p.out_u8[o2] = (uint8_t)(val * 255.0f);     // unet/predict.py:200 truncating cast
-            }
+            if (h >= p.head_n) break;
+            const float val = apply_head_act(hacc[h] + __ldg(p.head_b + h), p.head_act[h]);
+            const long long o2 = ((long long)tl.b0 * p.head_n + h) * plane + sp;
+            if (p.out_val) p.out_val[o2] = val;
+            if (p.out_u8) p.out_u8[o2] = (uint8_t)(val * 255.0f);     // unet/predict.py:200 truncating cast
           }
         }
 #pragma unroll

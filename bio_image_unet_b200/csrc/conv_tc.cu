@@ -148,18 +148,18 @@ static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
   if (g_halo_force_mt > 0 && mt_max > g_halo_force_mt) mt_max = g_halo_force_mt;
 #endif
   while (mt_max & (mt_max - 1)) --mt_max;                  // the kernel is instantiated for mt = 1, 2, 4, 8
-  // Preference: two A buffers (load of tile i+1 overlaps the MMAs of tile i) before wide chunks / wide tiles.
+  // Preference: two A buffers (load of tile i+1 overlaps the MMAs of tile i), then wide tiles (more MMAs share a
+  // weight tile and the halo overhead shrinks), then wide channel chunks.
   for (int abufs = 2; abufs >= 1; --abufs)
-    for (int ck = ck0; ck >= 32 / a.esz; ck >>= 1) {
-      if (a.cin % ck) continue;
+    for (int mt = mt_max; mt >= 1; mt >>= 1) {
+      if (abufs == 2 && 2 * mt < mt_max) break;            // do not shrink tiles below half for the 2nd buffer
+      for (int ck = ck0; ck >= 32 / a.esz; ck >>= 1) {
+        if (a.cin % ck) continue;
 #ifdef BIU_DBG_KNOBS
-      if (g_halo_force_ck > 0 && ck != g_halo_force_ck) continue;
+        if (g_halo_force_ck > 0 && ck != g_halo_force_ck) continue;
 #endif
-      const int rb = ck * a.esz;
-      const int chunks = a.cin / ck;
-      for (int mt = mt_max; mt >= 1; --mt) {
-        if (mt != mt_max && (mt & (mt - 1))) continue;     // after the first try only powers of two
-        if (abufs == 2 && mt < mt_max && 2 * mt < mt_max) break;   // do not shrink tiles below half for the 2nd buffer
+        const int rb = ck * a.esz;
+        const int chunks = a.cin / ck;
         const uint32_t tile = ((uint32_t)(a.kd * rows * (8 * mt + 2 * halo) * rb) + 1023u) & ~1023u;
         const uint32_t bst = ((uint32_t)(n_blk * rb) + 1023u) & ~1023u;
         int stages = (budget - (int)(abufs * tile) - 2048) / (int)bst;

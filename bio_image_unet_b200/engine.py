@@ -145,8 +145,20 @@ class Engine:
 # ----------------------------------------------------------------------------------------------------------------
 # HBM pipeline wrappers (all stream-ordered on torch's current stream)
 # ----------------------------------------------------------------------------------------------------------------
+_I32_CACHE = {}
+
+
 def _dev_i32(values, device):
-    return torch.tensor([int(v) for v in values], dtype=torch.int32, device=device)
+    """Device int32 array of tile starts. Cached: building it is a synchronous pageable H2D copy, which would stall
+    the launching thread behind all queued work once per call (the starts repeat for every chunk of a movie)."""
+    key = (tuple(int(v) for v in values), str(device))
+    t = _I32_CACHE.get(key)
+    if t is None:
+        if len(_I32_CACHE) > 256:
+            _I32_CACHE.clear()
+        t = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
+        _I32_CACHE[key] = t
+    return t
 
 
 def histogram(frames):
