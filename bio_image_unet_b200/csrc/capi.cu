@@ -83,6 +83,11 @@ int biu_net_set_force_direct(biu_net* net, int on) {
   return 0;
 }
 
+int biu_set_rows_kernel(int on) {
+  conv_rows_set_enabled(on);
+  return 0;
+}
+
 int biu_net_set_fuse_pool(biu_net* net, int on) {
   BIU_REQUIRE(net && net->n, "null handle");
   net->n->no_fuse = on ? 0 : 1;

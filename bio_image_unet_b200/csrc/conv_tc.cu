@@ -2,6 +2,7 @@
 // activation tensor and the packed weights, picks the pixel box / pipeline depth, launches.
 #include "conv_tc.cuh"
 #include "conv_halo.cuh"
+#include "conv_rows.cuh"
 #include "launch.h"
 #include <cstdlib>
 
@@ -118,6 +119,17 @@ int g_halo_force_mt = 0;
 int g_halo_force_ck = 0;
 #endif
 
+static int sm_count_cached() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
 
 // can the halo kernel take this layer? (3x3(x3) blocks, and transposed convolutions as a 1-tap GEMM)
@@ -231,6 +243,84 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row-streaming folded-tap kernel (conv_rows.cuh): eligibility, plan and launch
+// ---------------------------------------------------------------------------------------------------------------
+static int g_rows_enabled = -1;     // -1: from the environment (BIU_CONV_NOROWS=1 disables), else 0 / 1
+void conv_rows_set_enabled(int on) { g_rows_enabled = on ? 1 : 0; }
+static bool rows_disabled() {
+  if (g_rows_enabled < 0) { const char* e = getenv("BIU_CONV_NOROWS"); g_rows_enabled = (e && e[0] == '1') ? 0 : 1; }
+  return g_rows_enabled == 0;
+}
+
+struct RowsPlan { int ck, a_slots, t_slots, RB, smem; uint32_t a_slot_bytes, a_chunk_bytes, w_tile_bytes; bool ok; };
+
+static RowsPlan plan_rows(const ConvTcArgs& a) {
+  RowsPlan pl{};
+  pl.ok = false;
+  if (rows_disabled() || halo_disabled() || a.wgt_fold == nullptr) return pl;
+  if (a.mode != EPI_CONV && a.mode != EPI_HEAD) return pl;
+  if (a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return pl;
+  if (a.n_total != 16 && a.n_total != 32) return pl;        // N of the folded MMA = 3 * Cout: 48 or 96 TMEM columns per row
+  if (a.W < 128) return pl;                                  // one MMA tile = 128 consecutive pixels of a row
+  if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
+  if (a.pool_out != nullptr && (a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1))) return pl;
+  const int ck = pick_ck(a.cin, a.esz);
+  if (ck == 0) return pl;
+  const int rb = ck * a.esz, chunks = a.cin / ck, nfold = 3 * a.n_total;
+  pl.ck = ck;
+  pl.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
+  pl.a_chunk_bytes = ((uint32_t)(kRowsPx * rb) + 1023u) & ~1023u;
+  pl.a_slot_bytes = (uint32_t)chunks * pl.a_chunk_bytes;
+  const int tail = (2 * a.n_total + kMaxHead * a.n_total + 2 * 128 * kMaxHead) * 4 + 64;
+  const int budget = 225 * 1024 - tail - 1024 - (int)(a.kd * 3 * chunks * pl.w_tile_bytes);
+  int slots = budget / (int)pl.a_slot_bytes;
+  if (slots > kRowsMaxASlots) slots = kRowsMaxASlots;
+  if (slots < 2 * a.kd + 1) return pl;                       // weights + a few rows in flight must fit
+  pl.a_slots = slots;
+  pl.t_slots = 512 / nfold;
+  if (pl.t_slots > kRowsMaxTSlots) pl.t_slots = kRowsMaxTSlots;
+  pl.smem = (int)(a.kd * 3 * chunks * pl.w_tile_bytes + slots * pl.a_slot_bytes) + tail + 1024;
+  // rows per work item: as tall as possible (2 halo rows per block) while every SM still gets several items
+  const long long per_rb1 = (long long)((a.W + 127) / 128) * a.D * a.B;
+  pl.RB = 16;
+  for (int rbk : {64, 32}) {
+    if (per_rb1 * ((a.H + rbk - 1) / rbk) >= 4LL * sm_count_cached()) { pl.RB = rbk; break; }
+  }
+  pl.ok = true;
+  return pl;
+}
+
+static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_t stream) {
+  ConvRowsParams p;
+  memset(&p, 0, sizeof(p));
+  p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
+  p.strips = (a.W + 127) / 128; p.RB = pl.RB; p.rblocks = (a.H + pl.RB - 1) / pl.RB;
+  p.total_items = p.strips * p.rblocks * a.D * a.B;
+  p.kd = a.kd;
+  p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
+  p.cp = a.n_total;
+  p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.a_chunk_bytes = pl.a_chunk_bytes;
+  p.w_tile_bytes = pl.w_tile_bytes; p.t_slots = pl.t_slots;
+  p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out; p.out_ctot = a.out_ctot; p.out_coff = a.out_coff;
+  p.pool_out = a.pool_out; p.pool_ctot = a.pool_ctot; p.pool_coff = a.pool_coff;
+  p.head_n = a.head_n; p.head_w = a.head_w; p.head_b = a.head_b;
+  for (int i = 0; i < kMaxHead; ++i) p.head_act[i] = a.head_act[i];
+  p.out_val = a.out_val; p.out_u8 = a.out_u8;
+  CUtensorMap tmA, tmW;
+  const char* in_base = reinterpret_cast<const char*>(a.in) + (size_t)a.in_coff * a.esz;
+  if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, kRowsPx, 1, 1, 1)) return rc;
+  if (int rc = encode_wgt_map(&tmW, a.wgt_fold, a.esz, a.cin, 3 * a.n_total, a.kd * 3, pl.ck, 3 * a.n_total)) return rc;
+  const int grid = p.total_items < sm_count_cached() ? p.total_items : sm_count_cached();
+  if (int rc = a.esz == 2 ? rows_dispatch_bf16(tmA, tmW, p, grid, pl.smem, stream)
+                          : rows_dispatch_tf32(tmA, tmW, p, grid, pl.smem, stream))
+    return rc;
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 static int choose_n_blk(const ConvTcArgs& a) {
   // N per CTA: whole N when it fits one accumulator, otherwise the largest divisor <= 256
   int n_blk = a.n_total;
@@ -244,7 +334,7 @@ static int choose_n_blk(const ConvTcArgs& a) {
 
 bool conv_tc_can_fuse_pool(const ConvTcArgs& a) {
   if (!conv_tc_supported(a) || a.mode != EPI_CONV || a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1)) return false;
-  return plan_halo(a, choose_n_blk(a)).ok;
+  return plan_rows(a).ok || plan_halo(a, choose_n_blk(a)).ok;
 }
 
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
@@ -262,6 +352,10 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
   p.ck = pick_ck(a.cin, a.esz);
   p.cin_chunks = a.cin / p.ck;
   p.row_bytes = p.ck * a.esz;
+  {
+    const RowsPlan rp = plan_rows(a);
+    if (rp.ok) return launch_conv_rows(a, rp, stream);
+  }
   const int n_blk = choose_n_blk(a);
   {
     const HaloPlan pl = plan_halo(a, n_blk);

@@ -33,11 +33,13 @@ struct ConvTcArgs {
   float* out_val;
   uint8_t* out_u8;
   int smem_budget;              // 0 = default
-  void* pool_out;               // optional fused MaxPool2d(2) output (EPI_CONV, 2D, halo-tile kernel only)
+  const void* wgt_fold;         // optional: weights packed [kd*3 (dz,dx)][3*cout (dy,co)][cin] for the row-streaming kernel
+  void* pool_out;               // optional fused MaxPool2d(2) output (EPI_CONV, 2D, halo-tile / row kernels only)
   int pool_ctot, pool_coff;
 };
 bool conv_tc_supported(const ConvTcArgs& a);
 bool conv_tc_can_fuse_pool(const ConvTcArgs& a);
+void conv_rows_set_enabled(int on);   // test hook: route narrow 3x3 blocks through the row-streaming kernel (default on)
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 int read_device_fault(unsigned int* out);
 int pick_ck(int cin, int esz);

@@ -348,3 +348,91 @@ def test_variant_predict_matches_reference_golden(name, precision, as_class, tmp
     out = tiff.imread(res_file)
     assert out.dtype == np.float16 and out.shape == g['result_file'].shape
     assert np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= lsb
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row-streaming folded-tap kernel (conv_rows.cuh): narrow 3x3 blocks on planes at least 128 pixels wide
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def rows_kernel_toggle():
+    from bio_image_unet_b200 import _lib
+    lib = _lib.load()
+    yield lambda on: lib.biu_set_rows_kernel(int(on))
+    lib.biu_set_rows_kernel(1)
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+@pytest.mark.parametrize('n_filter,tile,batch', [(32, (64, 256), 2), (32, (48, 144), 3), (16, (80, 128), 2), (32, (16, 640), 1)])
+def test_rows_kernel_matches_halo_kernel_2d(precision, n_filter, tile, batch, rows_kernel_toggle):
+    """Same network, narrow blocks (encode2 + fused pool, decode7, decode8 + head) through conv_rows vs conv_halo:
+    identical up to the fp32 summation order of the three partial rows (one ulp of the stored format), and both
+    within tolerance of the oracle. W = 144 / 640 exercise a partial last strip, H = 48 / 80 / 16 partial row blocks."""
+    from bio_image_unet_b200.engine import Engine
+    sd = stress_state_dict(n_filter, seed=21)
+    tiles = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
+    sd = unit_logit_state_dict(n_filter, 21, tiles)
+    with torch.no_grad():
+        ref, _ = omodels.unet_forward(sd, tiles.float() / 255)
+    names = [('cat4', 2 * n_filter, 0), ('m1', n_filter, 1), ('d7', n_filter, 0)]
+    got = {}
+    for on in (1, 0):
+        rows_kernel_toggle(on)
+        eng = Engine('unet2d', sd, n_filter, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
+        eng.plan(batch, tile)
+        val, u8 = eng.forward(tiles.cuda(), want_val=True, want_u8=True)
+        got[on] = (val.cpu(), u8.cpu(), {n: eng.debug_activation(n, c, l).copy() for n, c, l in names})
+        eng.close()
+    rel = 2 ** -7 if precision == 'bf16' else 2 ** -9       # one ulp of the stored format
+    for n, _, _ in names:
+        a, b = got[1][2][n], got[0][2][n]
+        if n == 'cat4':                   # [up4 | encode2]: only the skip half comes straight out of a narrow block
+            a, b = a[..., n_filter:], b[..., n_filter:]
+        # encode2 / m1 come straight out of the first narrow block; d7 has the whole network in between
+        assert np.abs(a - b).max() <= (8 if n == 'd7' else 1) * rel * max(np.abs(b).max(), 1.0), \
+            (n, np.abs(a - b).max(), np.abs(b).max())
+    assert (got[1][0] - got[0][0]).abs().max().item() < 0.5 * TOL_STRESS[precision]
+    assert (got[1][0] - ref).abs().max().item() < TOL_STRESS[precision]
+    assert np.abs(got[1][1].numpy().astype(np.int16) - got[0][1].numpy().astype(np.int16)).max() <= \
+        1 + int(np.ceil(0.5 * TOL_STRESS[precision] * 255))
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+@pytest.mark.parametrize('kind,n_filter,tile,batch', [('unet3d', 16, (8, 16, 128), 2), ('unet3d', 32, (16, 24, 128), 1),
+                                                      ('mo3d', 16, (8, 32, 256), 1)])
+def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, batch, rows_kernel_toggle):
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
+    from bio_image_unet_b200.unet3d import UNet3D
+    torch.manual_seed(31)
+    if kind == 'unet3d':
+        module, heads = UNet3D(n_filter=n_filter), [('', 1, 'sigmoid')]
+        spec = dict(n_filter=n_filter, in_channels=1, heads=heads)
+    else:
+        cfg = {'seg': {'channels': 1, 'activation': 'sigmoid'}, 'flow': {'channels': 2, 'activation': None}}
+        module = MultiOutputUnet3D(1, cfg, n_filter, True)
+        spec = dict(n_filter=n_filter, in_channels=1, heads=[('seg', 1, 'sigmoid'), ('flow', 2, None)], use_interpolation=True)
+    sd = module.state_dict()
+    g = torch.Generator().manual_seed(8)
+    for k, v in sd.items():                       # randomised BN statistics so that the folding is exercised
+        if k.endswith('running_var') or k.endswith('.1.weight'):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith('running_mean') or k.endswith('.1.bias'):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+    x = torch.rand((batch, 1, *tile), generator=g)
+    with torch.no_grad():
+        if kind == 'unet3d':
+            ref = omodels.unet3d_forward(sd, x)[0]
+        else:
+            o = omodels.mo3d_forward(sd, x, cfg, True)
+            ref = torch.cat([o['seg'], o['flow']], 1)
+    got = {}
+    for on in (1, 0):
+        rows_kernel_toggle(on)
+        eng = Engine(kind, sd, precision=precision, device='cuda:0', **spec)
+        eng.plan(batch, tile)
+        val, _ = eng.forward(x.cuda(), want_val=True, want_u8=False)
+        got[on] = val.cpu()
+        eng.close()
+    tol = 2e-3 if precision == 'tf32' else 2e-2
+    assert (got[1] - got[0]).abs().max().item() < 0.5 * tol
+    assert (got[1] - ref).abs().max().item() < tol, (got[1] - ref).abs().max().item()
