@@ -92,12 +92,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
-      : "memory");
+      : "r"(smem_u32(bar)), "r"(parity)      // no suspend-time hint: it compiles to NANOSLEEP.SYNCS whose wake-up
+      : "memory");                           // latency sits on every producer/consumer hand-off
   return ok != 0;
 }
 // Bounded wait: a pipeline bug must never hang the GPU box. ~4e9 cycles (≈2 s) then fault+trap.

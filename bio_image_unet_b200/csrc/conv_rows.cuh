@@ -9,22 +9,28 @@
 // i.e. 3 (x kd) MMAs of N = 96 per 16 input channels instead of 9 (x kd) of N = 32: ~2.1x fewer operand bytes per
 // useful MAC. The epilogue adds the three partial rows while it drains TMEM.
 //
+// The three partial rows are summed by the tensor core itself: every OUTPUT row owns a TMEM slot of Cout fp32
+// columns (ring of 512 / Cout = 16 or 32 slots, zeroed by the epilogue before reuse) and the MMA of input row r
+// accumulates its N = 3*Cout result over the three consecutive slots of output rows r-1, r, r+1 (weights packed in
+// the order dy = 2, 1, 0). Where the three slots wrap around the ring the MMA is split in two (N = Cout + 2*Cout).
+// The deep ring lets the MMA warp run a dozen rows ahead of the epilogue: the kernel is no longer bound by the
+// barrier round trips between the two (tools/conv_bench.cu: 600 cycles per row with a 5-slot ring of 3*Cout slots).
+//
 // Work item = a strip of 128 pixels (one MMA M tile = 128 consecutive x of one image row) x RB output rows of one
 // plane. Input rows y0-1 .. y0+RB stream through a shared-memory ring (one TMA box of 130 pixels per row, plane and
-// channel chunk; out-of-image rows / columns / planes are zero-filled = the convolution's padding). Every input
-// row owns a TMEM slot of 3*Cout fp32 columns (ring of 512 / (3*Cout) slots); output row y is ready once input row
-// y+1 has been accumulated. The folded weights of the layer stay resident in shared memory.
+// channel chunk; out-of-image rows / columns / planes are zero-filled = the convolution's padding). Per item the
+// ring sees RB+4 "virtual" output rows: two dummies on either side collect the unused partial rows of the halo
+// input rows and are only zeroed again. The folded weights of the layer stay resident in shared memory.
 // Warp roles: 0 = row (A) producer, 1 = TMEM alloc + MMA issuer (warp-uniform, see conv_halo.cuh), 2 = weight
-// loader, 4..11 = epilogue: warp w drains TMEM lane quarter w % 4 (32 pixels) and channel half (w - 4) / 4, all
-// eight warps work on the same output row, so a slot is simply released by eight arrivals after the row that last
-// read it.
+// loader, 4..11 = epilogue: warp w drains TMEM lane quarter w % 4 (32 pixels) and channel half (w - 4) / 4; all
+// eight warps work on the same output row, a slot is released by their eight arrivals.
 #pragma once
 #include "conv_halo.cuh"
 
 namespace biu {
 
 constexpr int kRowsMaxASlots = 24;
-constexpr int kRowsMaxTSlots = 10;
+constexpr int kRowsMaxTSlots = 32;
 constexpr int kRowsThreads = 384;
 constexpr int kRowsPx = 130;                 // 128 pixels + 1 halo column on each side
 
@@ -38,7 +44,7 @@ struct ConvRowsParams {
   int a_slots;                   // shared-memory ring: one slot = one input row of one plane, all channel chunks
   uint32_t a_slot_bytes, a_chunk_bytes;
   uint32_t w_tile_bytes;         // one folded weight tile [(dy, co)][ck]; kd * 3 * cin_chunks of them
-  int t_slots;                   // TMEM ring: slots of 3 * cp columns
+  int t_slots;                   // TMEM ring: 512 / cp slots of cp columns (one per output row)
   int mode;                      // EPI_CONV or EPI_HEAD
   float slope;
   const float* scale;
@@ -94,9 +100,43 @@ __device__ __forceinline__ void tmem_wait3(uint32_t (&a)[16], uint32_t (&b)[16],
   }
 }
 
+template <int HC>
+__device__ __forceinline__ void tmem_wait1(uint32_t (&a)[16]) {
+  if (HC == 16) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+                 :
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])
+                 :
+                 : "memory");
+  }
+}
+// zero HC consecutive fp32 columns of this warp's 32 TMEM lanes
+template <int HC>
+__device__ __forceinline__ void tmem_zero_hc(uint32_t taddr) {
+  const uint32_t z = 0;
+  if (HC == 16) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(z) : "memory");
+  } else {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+#ifdef BIU_DBG_KNOBS
+static __device__ int g_rows_dbg = 0;
+#endif
 
 struct RowsItem { int x0, y0, rows, z, b; };
 
@@ -121,19 +161,27 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
   const int hsel = (warp - 4) >> 2;              // channel half
   const int c0 = hsel * HC;                      // first channel of this warp
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  const int nfold = 3 * p.cp;
-  int ts = 0;                                    // ring position (slot) and use parity of the item's first input row
+  int ts = 0;                                    // ring slot / use parity of the item's first virtual output row
   uint32_t tph = 0;
-  float sc[HC], sh[HC];
-#pragma unroll
-  for (int i = 0; i < HC; ++i) { sc[i] = s_scale[c0 + i]; sh[i] = s_shift[c0 + i]; }
   uint32_t carry[HC / 2 * (ESZ == 2 ? 1 : 2)];   // POOL: previous (even) row, already max-ed over the x pair
   (void)carry;
+
+  // Before anything accumulates: zero this warp's part of every slot and mark all slots empty (phase 0).
+  for (int sl = 0; sl < p.t_slots; ++sl) tmem_zero_hc<HC>(tmem_base + lane_addr + (uint32_t)(sl * p.cp + c0));
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0)
+    for (int sl = 0; sl < p.t_slots; ++sl) mbar_arrive(&t_empty[sl]);
 
   for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
     const RowsItem it = rows_decode(p, t);
     const int px = it.x0 + q * 32 + lane;
+#ifdef BIU_DBG_KNOBS
+    const bool col_ok = px < p.W && !(g_rows_dbg & 8);
+#else
     const bool col_ok = px < p.W;
+#endif
     const long long plane_row0 = ((long long)it.b * p.D + it.z) * p.H + it.y0;
     char* out_px = nullptr;
     if (MODE == EPI_CONV)
@@ -146,32 +194,24 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
       pool_px = reinterpret_cast<char*>(p.pool_out) + ((prow0 * (p.W >> 1) + (px >> 1)) * p.pool_ctot + p.pool_coff + c0) * ESZ;
       pool_row_bytes = (long long)(p.W >> 1) * p.pool_ctot * ESZ;
     }
-    // slots / parities of input rows o, o+1, o+2 (relative to the item's first input row y0-1)
-    int s0 = ts; uint32_t ph0 = tph;
-    int s1 = s0 + 1; uint32_t ph1 = ph0; if (s1 == p.t_slots) { s1 = 0; ph1 ^= 1; }
-    int s2 = s1 + 1; uint32_t ph2 = ph1; if (s2 == p.t_slots) { s2 = 0; ph2 ^= 1; }
-    for (int o = 0; o < it.rows; ++o) {
-      mbar_wait(&t_full[s2], ph2, 0xA00 + s2);   // rows complete in order: o and o+1 are done as well
-      tc_fence_after();
-      uint32_t e0[16], e1[16], e2[16];
-      tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(s0 * nfold + c0), e0);
-      tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(s1 * nfold + p.cp + c0), e1);
-      tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(s2 * nfold + 2 * p.cp + c0), e2);
-      tmem_wait3<HC>(e0, e1, e2);
+    const int vrows = it.rows + 4;               // virtual output rows: 2 dummies, rows real ones, 2 dummies
+    // math + stores of real output row o from its accumulator
+    auto process = [&](const uint32_t (&e)[16], int o) {
       float v[HC];
 #pragma unroll
-      for (int i = 0; i < HC; ++i) {
-        float a = (__uint_as_float(e0[i]) + __uint_as_float(e1[i])) + __uint_as_float(e2[i]);
-        a = fmaf(a, sc[i], sh[i]);
-        a = fmaxf(a, a * p.slope);               // LeakyReLU for 0 <= slope <= 1
-        if (ESZ == 4) a = round_tf32(a);
-        v[i] = a;
+      for (int i4 = 0; i4 < HC / 4; ++i4) {
+        const float4 sc = reinterpret_cast<const float4*>(s_scale + c0)[i4];
+        const float4 sh = reinterpret_cast<const float4*>(s_shift + c0)[i4];
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = 4 * i4 + k;
+          float a = fmaf(__uint_as_float(e[i]), scv[k], shv[k]);
+          a = fmaxf(a, a * p.slope);               // LeakyReLU for 0 <= slope <= 1
+          if (ESZ == 4) a = round_tf32(a);
+          v[i] = a;
+        }
       }
-      // slot of input row o is not needed any more (rows o+1, o+2 are still read by the next output rows)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[s0]);
-
       if (MODE == EPI_HEAD) {
         float part[kMaxHead];
 #pragma unroll
@@ -253,13 +293,61 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
           }
         }
       }
-      s0 = s1; ph0 = ph1; s1 = s2; ph1 = ph2;
-      if (++s2 == p.t_slots) { s2 = 0; ph2 ^= 1; }
+    };
+    // Virtual rows are handled in PAIRS (one barrier wait, one TMEM drain wait, one zero-store wait per two rows):
+    // wait until the later row has all its partial rows, drain both (real rows), zero both slots for their next
+    // users and release them; the drain of the next pair is issued before this pair is processed.
+    int sl = ts; uint32_t ph = tph;
+    auto is_real = [&](int v) { return v >= 2 && v < it.rows + 2; };
+    auto fetch2 = [&](uint32_t (&e0)[16], uint32_t (&e1)[16], int v) {      // rows v, v+1 (v+1 may not exist)
+      const bool two = v + 1 < vrows;
+      int s1 = sl + 1; uint32_t p1 = ph;
+      if (s1 == p.t_slots) { s1 = 0; p1 ^= 1; }
+      if (two) mbar_wait(&t_full[s1], p1, 0xA00 + s1);                       // rows complete in order
+      else mbar_wait(&t_full[sl], ph, 0xA00 + sl);
+      tc_fence_after();
+#ifdef BIU_DBG_KNOBS
+      if (g_rows_dbg & 2) return;
+#endif
+      if (is_real(v)) tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(sl * p.cp + c0), e0);
+      if (two && is_real(v + 1)) tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(s1 * p.cp + c0), e1);
+    };
+    auto release2 = [&](uint32_t (&e0)[16], uint32_t (&e1)[16], int v) {     // data in registers, slots zeroed + freed
+      const bool two = v + 1 < vrows;
+      int s1 = sl + 1; uint32_t p1 = ph;
+      if (s1 == p.t_slots) { s1 = 0; p1 ^= 1; }
+      if (is_real(v) || (two && is_real(v + 1))) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(e0[0]), "+r"(e0[1]), "+r"(e0[2]), "+r"(e0[3]), "+r"(e0[4]), "+r"(e0[5]), "+r"(e0[6]), "+r"(e0[7]),
+                       "+r"(e0[8]), "+r"(e0[9]), "+r"(e0[10]), "+r"(e0[11]), "+r"(e0[12]), "+r"(e0[13]), "+r"(e0[14]), "+r"(e0[15]),
+                       "+r"(e1[0]), "+r"(e1[1]), "+r"(e1[2]), "+r"(e1[3]), "+r"(e1[4]), "+r"(e1[5]), "+r"(e1[6]), "+r"(e1[7]),
+                       "+r"(e1[8]), "+r"(e1[9]), "+r"(e1[10]), "+r"(e1[11]), "+r"(e1[12]), "+r"(e1[13]), "+r"(e1[14]), "+r"(e1[15])
+                     :
+                     : "memory");
+      }
+      tmem_zero_hc<HC>(tmem_base + lane_addr + (uint32_t)(sl * p.cp + c0));
+      if (two) tmem_zero_hc<HC>(tmem_base + lane_addr + (uint32_t)(s1 * p.cp + c0));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&t_empty[sl]); if (two) mbar_arrive(&t_empty[s1]); }
+      if (two) { sl = s1; ph = p1; }
+      if (++sl == p.t_slots) { sl = 0; ph ^= 1; }
+    };
+    uint32_t ea[16], eb[16], ec[16], ed[16];
+    fetch2(ea, eb, 0);
+    for (int v = 0; v < vrows; v += 4) {
+      release2(ea, eb, v);
+      if (v + 2 < vrows) fetch2(ec, ed, v + 2);
+      if (is_real(v)) process(ea, v - 2);
+      if (v + 1 < vrows && is_real(v + 1)) process(eb, v - 1);
+      if (v + 2 >= vrows) break;
+      release2(ec, ed, v + 2);
+      if (v + 4 < vrows) fetch2(ea, eb, v + 4);
+      if (is_real(v + 2)) process(ec, v);
+      if (v + 3 < vrows && is_real(v + 3)) process(ed, v + 1);
     }
-    // the last two input rows of the item were only read, never released: hand them back too
-    __syncwarp();
-    if (lane == 0) { mbar_arrive(&t_empty[s0]); mbar_arrive(&t_empty[s1]); }
-    ts = s2; tph = ph2;                          // next item starts at the slot after its rows+2 input rows
+    ts = sl; tph = ph;
   }
 }
 
@@ -332,6 +420,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
         for (int i = 0; i < it.rows + 2; ++i)
           for (int dz = 0; dz < p.kd; ++dz) {
             mbar_wait(&a_empty[as], aph ^ 1, 0xB00 + as);
+#ifdef BIU_DBG_KNOBS
+            if (g_rows_dbg & 16) { mbar_arrive(&a_full[as]); if (++as == p.a_slots) { as = 0; aph ^= 1; } continue; }
+#endif
             mbar_arrive_expect_tx(&a_full[as], row_tx);
             for (int ch = 0; ch < p.cin_chunks; ++ch)
               asm volatile(
@@ -347,54 +438,80 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     const uint32_t layout = rb == 128 ? 2u : (rb == 64 ? 4u : 6u);
-    const uint32_t idesc = make_idesc(ESZ == 2 ? 1u : 2u, (uint32_t)nfold);
+    const uint32_t fmt = ESZ == 2 ? 1u : 2u;
+    const uint32_t idesc3 = make_idesc(fmt, (uint32_t)(3 * p.cp));      // whole folded tile
+    const uint32_t idesc2 = make_idesc(fmt, (uint32_t)(2 * p.cp));      // split MMAs where the three slots wrap
+    const uint32_t idesc1 = make_idesc(fmt, (uint32_t)p.cp);
     const uint64_t a_desc0 = make_smem_desc(a_base, 8u * rb, layout);
     const uint64_t w_desc0 = make_smem_desc(smem_base, 8u * rb, layout);
     constexpr uint32_t px_step = 2u * KS;              // one pixel = row_bytes / 16
     const uint32_t aslot_step = p.a_slot_bytes >> 4, achunk_step = p.a_chunk_bytes >> 4, wtile_step = p.w_tile_bytes >> 4;
+    const uint32_t wrow_step = ((uint32_t)p.cp * rb) >> 4;             // cp weight rows (one dy block) further
+    const uint32_t wdx_step = p.cin_chunks * wtile_step;               // next dx tap
     mbar_wait(&w_full, 0, 0xC00);
     tc_fence_after();
-    int as = 0, ts = 0;
-    uint32_t aph = 0, tph = 0;
+#ifdef BIU_DBG_KNOBS
+    const bool dbg_nomma = (g_rows_dbg & 4) != 0;
+#else
+    const bool dbg_nomma = false;
+#endif
+    int as = 0;
+    uint32_t aph = 0;
+    int es = 0; uint32_t eph = 0;                      // next virtual row whose slot has to be empty (zeroed)
+    int fs = 0;                                        // next virtual row to be completed (slot of input row i)
+    auto wait_empty = [&]() {
+      mbar_wait(&t_empty[es], eph, 0xD00 + es);
+      if (++es == p.t_slots) { es = 0; eph ^= 1; }
+    };
     for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
       const RowsItem it = rows_decode(p, t);
+      wait_empty();                                    // dummy rows v = 0, 1 of this item
+      wait_empty();
       for (int i = 0; i < it.rows + 2; ++i) {
-        mbar_wait(&t_empty[ts], tph ^ 1, 0xD00 + ts);              // epilogue released this TMEM slot
+        wait_empty();                                  // virtual row i + 2 receives its first partial row now
         tc_fence_after();
-        const uint32_t tcol = tmem_base + (uint32_t)(ts * nfold);
-        bool first = true;
+        // input row i accumulates into the slots of virtual rows i, i+1, i+2 (weights ordered dy = 2, 1, 0)
+        const int s0 = fs;
+        const int wrap = s0 + 3 - p.t_slots;           // > 0: that many slots continue at slot 0
+        const uint32_t tcol = tmem_base + (uint32_t)(s0 * p.cp);
         for (int dz = 0; dz < p.kd; ++dz) {
           mbar_wait(&a_full[as], aph, 0xE00 + as);
           tc_fence_after();
           for (int ch = 0; ch < p.cin_chunks; ++ch) {
             const uint64_t ad0 = a_desc0 + (uint64_t)(as * aslot_step + ch * achunk_step);
             const uint64_t wd0 = w_desc0 + (uint64_t)((dz * 3 * p.cin_chunks + ch) * wtile_step);
-            const uint32_t wdx_step = p.cin_chunks * wtile_step;   // next dx tap
-            if (elect_one()) {
-              if (first) {
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                  for (int k = 0; k < KS; ++k) {
-                    if (dx == 0 && k == 0) tc_mma_imm<ESZ, 0>(tcol, ad0 + (dx * px_step + 2 * k), wd0 + (dx * wdx_step + 2 * k), idesc);
-                    else tc_mma_imm<ESZ, 1>(tcol, ad0 + (dx * px_step + 2 * k), wd0 + (dx * wdx_step + 2 * k), idesc);
-                  }
-              } else {
+            if (!dbg_nomma && elect_one()) {
+              if (wrap <= 0) {
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
                   for (int k = 0; k < KS; ++k)
-                    tc_mma_imm<ESZ, 1>(tcol, ad0 + (dx * px_step + 2 * k), wd0 + (dx * wdx_step + 2 * k), idesc);
+                    tc_mma_imm<ESZ, 1>(tcol, ad0 + (dx * px_step + 2 * k), wd0 + (dx * wdx_step + 2 * k), idesc3);
+              } else {
+                const uint32_t n_lo = wrap == 1 ? idesc2 : idesc1;        // slots before the wrap
+                const uint32_t n_hi = wrap == 1 ? idesc1 : idesc2;        // slots continuing at slot 0
+                const uint32_t w_hi = (uint32_t)(3 - wrap) * wrow_step;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                  for (int k = 0; k < KS; ++k) {
+                    tc_mma_imm<ESZ, 1>(tcol, ad0 + (dx * px_step + 2 * k), wd0 + (dx * wdx_step + 2 * k), n_lo);
+                    tc_mma_imm<ESZ, 1>(tmem_base, ad0 + (dx * px_step + 2 * k), wd0 + (w_hi + dx * wdx_step + 2 * k), n_hi);
+                  }
               }
             }
-            first = false;
           }
           if (elect_one()) tc_commit(&a_empty[as]);
           if (++as == p.a_slots) { as = 0; aph ^= 1; }
         }
-        if (elect_one()) tc_commit(&t_full[ts]);
-        if (++ts == p.t_slots) { ts = 0; tph ^= 1; }
+        if (elect_one()) tc_commit(&t_full[fs]);       // virtual row i has all its partial rows
+        if (++fs == p.t_slots) fs = 0;
       }
+      // the two trailing dummy rows are complete as well
+      if (elect_one()) tc_commit(&t_full[fs]);
+      if (++fs == p.t_slots) fs = 0;
+      if (elect_one()) tc_commit(&t_full[fs]);
+      if (++fs == p.t_slots) fs = 0;
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================

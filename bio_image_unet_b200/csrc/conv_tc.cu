@@ -261,9 +261,10 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   if (rows_disabled() || halo_disabled() || a.wgt_fold == nullptr) return pl;
   if (a.mode != EPI_CONV && a.mode != EPI_HEAD) return pl;
   if (a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return pl;
-  if (a.n_total != 16 && a.n_total != 32) return pl;        // N of the folded MMA = 3 * Cout: 48 or 96 TMEM columns per row
+  if (a.n_total != 16 && a.n_total != 32) return pl;        // N of the folded MMA = 3 * Cout = 48 or 96
   if (a.W < 128) return pl;                                  // one MMA tile = 128 consecutive pixels of a row
   if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
+  if (a.mode == EPI_HEAD && a.kd == 1) return pl;            // measured: the 2D head block is faster on the halo-tile kernel
   if (a.pool_out != nullptr && (a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1))) return pl;
   const int ck = pick_ck(a.cin, a.esz);
   if (ck == 0) return pl;
@@ -278,8 +279,7 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   if (slots > kRowsMaxASlots) slots = kRowsMaxASlots;
   if (slots < 2 * a.kd + 1) return pl;                       // weights + a few rows in flight must fit
   pl.a_slots = slots;
-  pl.t_slots = 512 / nfold;
-  if (pl.t_slots > kRowsMaxTSlots) pl.t_slots = kRowsMaxTSlots;
+  pl.t_slots = 512 / a.n_total;                             // one TMEM slot of Cout columns per output row
   pl.smem = (int)(a.kd * 3 * chunks * pl.w_tile_bytes + slots * pl.a_slot_bytes) + tail + 1024;
   // rows per work item: as tall as possible (2 halo rows per block) while every SM still gets several items
   const long long per_rb1 = (long long)((a.W + 127) / 128) * a.D * a.B;

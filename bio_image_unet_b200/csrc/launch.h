@@ -33,7 +33,7 @@ struct ConvTcArgs {
   float* out_val;
   uint8_t* out_u8;
   int smem_budget;              // 0 = default
-  const void* wgt_fold;         // optional: weights packed [kd*3 (dz,dx)][3*cout (dy,co)][cin] for the row-streaming kernel
+  const void* wgt_fold;         // optional: weights packed [kd*3 (dz,dx)][3*cout ((2-dy),co)][cin] for the row-streaming kernel
   void* pool_out;               // optional fused MaxPool2d(2) output (EPI_CONV, 2D, halo-tile / row kernels only)
   int pool_ctot, pool_coff;
 };

@@ -414,7 +414,8 @@ int net_finalize(Net* n) {
           if (upload(n, wp, &d)) return -1;
           L.w_tc = d;
         }
-        // narrow blocks (Cout <= 32): second packing with the dy taps folded into the GEMM's N (conv_rows.cuh)
+        // narrow blocks (Cout <= 32): second packing with the dy taps folded into the GEMM's N, in the order
+        // dy = 2, 1, 0 = output rows r-1, r, r+1 of input row r (conv_rows.cuh)
         if (L.kw == 3 && L.cout_pad <= 32) {
           const int tz = L.kd * 3, nfold = 3 * L.cout_pad;
           std::vector<float> wf((size_t)tz * nfold * L.cin_phys, 0.f);
@@ -424,7 +425,7 @@ int net_finalize(Net* n) {
                 const int t = (dz * 3 + dy) * 3 + dx;
                 for (int co = 0; co < L.cout; ++co)
                   for (int ci = 0; ci < L.cin_log; ++ci)
-                    wf[((size_t)(dz * 3 + dx) * nfold + dy * L.cout_pad + co) * L.cin_phys + phys[ci]] =
+                    wf[((size_t)(dz * 3 + dx) * nfold + (2 - dy) * L.cout_pad + co) * L.cin_phys + phys[ci]] =
                         w->data[((size_t)co * L.cin_log + ci) * taps + t];
               }
           if (n->esz == 2) {

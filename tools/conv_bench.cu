@@ -4,6 +4,8 @@
 #include "../bio_image_unet_b200/csrc/conv_tc.cu"
 #include "../bio_image_unet_b200/csrc/conv_halo_bf16.cu"
 #include "../bio_image_unet_b200/csrc/conv_halo_tf32.cu"
+#include "../bio_image_unet_b200/csrc/conv_rows_bf16.cu"
+#include "../bio_image_unet_b200/csrc/conv_rows_tf32.cu"
 #include <vector>
 #include <cstdarg>
 namespace biu {
@@ -14,6 +16,7 @@ unsigned long long g_launch_count = 0;
 }
 using namespace biu;
 
+static int g_use_rows = 0;
 struct LayerCfg { const char* name; int cin, cout, level; int up; };
 
 static float time_layer(const LayerCfg& L, int tiles, void* in, void* wgt, float* scale, float* shift, void* out, int reps) {
@@ -28,7 +31,7 @@ static float time_layer(const LayerCfg& L, int tiles, void* in, void* wgt, float
     a.kw = a.kh = a.kd = 1; a.n_total = 4 * L.cout; a.mode = EPI_UP; a.slope = 1.f; a.up_cout = L.cout; a.up_dims = 2;
     a.out_ctot = 2 * L.cout;
   }
-  a.wgt = wgt; a.scale = scale; a.shift = shift; a.out = out; a.out_coff = 0;
+  a.wgt = wgt; a.wgt_fold = (g_use_rows && !L.up) ? wgt : nullptr; a.scale = scale; a.shift = shift; a.out = out; a.out_coff = 0;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   if (launch_conv_tc(a, 0)) { printf("launch failed: %s\n", get_error()); return -1; }
@@ -104,6 +107,19 @@ int main(int argc, char** argv) {
         printf("ck=%d %-24s %8.3f ms\n", ck, layers[li].name, time_layer(layers[li], tiles, in, wgt, scale, shift, out, reps));
     }
     g_halo_force_ck = 0;
+  }
+  {  // row-streaming kernel on the narrow layers: full / one TMEM load per row / no TMEM loads / no MMA
+    g_halo_dbg = 0; g_use_rows = 1;
+    for (int li : {0, 1}) {
+      printf("rows kernel %-24s", layers[li].name);
+      for (int k : {0, 8, 16, 4, 4 | 8, 4 | 16, 4 | 8 | 16 | 2}) {
+        cudaMemcpyToSymbol(g_rows_dbg, &k, sizeof(int));
+        printf("  dbg%d %.3f ms", k, time_layer(layers[li], tiles, in, wgt, scale, shift, out, reps));
+      }
+      printf("\n");
+    }
+    int z = 0; cudaMemcpyToSymbol(g_rows_dbg, &z, sizeof(int));
+    g_use_rows = 0;
   }
   {  // cycle accounting of CTA 0
     const char* slot_names[12] = {"A: wait a_empty", "A: issue TMA", "B: wait b_empty", "MMA: wait acc_empty", "MMA: wait a_full",
