@@ -40,6 +40,8 @@ SIGNATURES = {
                                    _P]),
     'biu_stitch_ramp_f32': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, _P, _P]),
+    'biu_stitch_margin_f32': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
+                                      _P, _P]),
     'biu_conv_tc': (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int,
                             _P, _P, c_float, _P, c_int, c_int, _P]),
     'biu_up_tc': (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int,

@@ -33,7 +33,7 @@ int biu_version(void) { return 100; }
 biu_net* biu_net_create(int kind, int n_filter, int in_channels, int n_heads, const int* head_channels,
                         const int* head_acts, const char* const* head_names, int siam_mode, int use_interpolation,
                         int precision) {
-  if (kind < 0 || kind > 5) { set_error("unknown network kind %d", kind); return nullptr; }
+  if (kind < 0 || kind > 6) { set_error("unknown network kind %d", kind); return nullptr; }
   if (precision < 0 || precision > 2) { set_error("unknown precision %d", precision); return nullptr; }
   if (n_heads < 1 || !head_channels || !head_acts) { set_error("at least one output head is required"); return nullptr; }
   Net* n = new Net();
@@ -192,6 +192,16 @@ int biu_pool2(int esz, const void* in, int in_ctot, int in_coff, int c, int B, i
   return launch_pool2(a, (cudaStream_t)stream);
 }
 int biu_device_fault(unsigned int* code_host) { return read_device_fault(code_host); }
+int biu_stitch_margin_f32(const float* tiles, const int* src_index, int T, int C, int H, int W, const int* ys,
+                          const int* xs, int ny, int nx, int ph, int pw, int margin, const float* fill, float* out,
+                          void* stream) {
+  StitchMarginArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tiles = tiles; a.src_index = src_index; a.T = T; a.C = C; a.H = H; a.W = W; a.ys = ys; a.xs = xs;
+  a.ny = ny; a.nx = nx; a.ph = ph; a.pw = pw; a.margin = margin; a.fill = fill; a.out = out;
+  return launch_stitch_margin(a, (cudaStream_t)stream);
+}
+
 unsigned long long biu_launch_count(void) { return g_launch_count; }
 int biu_net_set_profile(biu_net* net, int on) {
   BIU_REQUIRE(net && net->n, "null handle");

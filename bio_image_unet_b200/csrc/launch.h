@@ -177,6 +177,16 @@ struct StitchRampArgs {         // multi_output_unet3d/predict.py:203-307
   float* out;                   // [V][C][Z][H][W]
 };
 int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream);
+struct StitchMarginArgs {       // multi_output_unet/predict.py:230-285 (ys/ny index image rows, xs/nx columns)
+  const float* tiles;           // [P][C][ph][pw] float32 (rounded to float16 on read, as the reference stores them)
+  const int* src_index;         // [T][ny][nx] flat patch index of tile (image, j, k)
+  int T, C, H, W;
+  const int* ys; const int* xs;
+  int ny, nx, ph, pw, margin;
+  const float* fill;            // device scalar: value of pixels without any weight
+  float* out;                   // [T][C][H][W]
+};
+int launch_stitch_margin(const StitchMarginArgs& a, cudaStream_t stream);
 int launch_norm_lut_f32(const unsigned int* hist_bounds, const unsigned int* hist_range, long long bounds_stride,
                         long long range_stride, int frames, double q_lo, double q_hi, int mode, float* lut,
                         double* params, cudaStream_t stream);

@@ -109,7 +109,8 @@ int net_build(Net* n) {
               kMaxHead, n->head_total);
   BIU_REQUIRE(nf >= 2 && nf % 2 == 0, "n_filter must be even (got %d)", nf);
 
-  if (n->kind == NET_UNET2D || n->kind == NET_SIAM2D || n->kind == NET_UNET2D_V0 || n->kind == NET_ATTUNET2D) {
+  if (n->kind == NET_UNET2D || n->kind == NET_SIAM2D || n->kind == NET_UNET2D_V0 || n->kind == NET_ATTUNET2D ||
+      n->kind == NET_MO2D) {      // NET_MO2D: Unet body, heads 'output_layers.<name>' (multi_output_unet.py:62-65)
     n->dims = 2;
     n->levels = 4;
     const bool siam = n->kind == NET_SIAM2D;
@@ -494,7 +495,7 @@ int net_finalize(Net* n) {
     int row = 0;
     for (size_t hi = 0; hi < n->head_channels.size(); ++hi) {
       std::string base;
-      if (n->kind == NET_MO3D) base = "output_layers." + n->head_names[hi];
+      if (n->kind == NET_MO3D || n->kind == NET_MO2D) base = "output_layers." + n->head_names[hi];
       else if (n->kind == NET_UNET3D) base = "final";
       else base = "final.0";
       const HostTensor* w = find_param(n, base + ".weight");

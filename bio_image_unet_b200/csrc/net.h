@@ -10,7 +10,7 @@
 
 namespace biu {
 
-enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3, NET_UNET2D_V0 = 4, NET_ATTUNET2D = 5 };
+enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3, NET_UNET2D_V0 = 4, NET_ATTUNET2D = 5, NET_MO2D = 6 };
 enum Precision { PREC_BF16 = 0, PREC_TF32 = 1, PREC_FP32 = 2 };
 enum SiamMode { SIAM_CONCAT = 0, SIAM_MAX = 1, SIAM_CONTROL = 2, SIAM_CORR = 3 };
 

@@ -511,6 +511,8 @@ __device__ float percentile_from_hist_f32(const unsigned long long* cum_sh, cons
 // lut[f][v] = float32 of the float64 expression the reference evaluates for a voxel of value v:
 //   mode 0 ('single'):      (clip(v, lo, hi) - min) / (ptp + 1e-8)         :108-112
 //   mode 1 ('first'/'all'): (clip(v, lo, hi) - lo) / (hi - lo + 1e-8)      :114-120
+//   mode 2 (multi_output_unet/predict.py:128-151, all three modes): x = clip(v, lo, hi); x = x - min(x); x / max(x),
+//           entirely in float32 (float32 percentiles, float32 stack)
 // np.clip of the float32 stack with np.float64 bounds promotes to float64 (NEP 50), the store back into the
 // float32 stack rounds once.
 __global__ void __launch_bounds__(256) norm_lut_f32_kernel(const unsigned int* __restrict__ hist_bounds,
@@ -545,7 +547,7 @@ __global__ void __launch_bounds__(256) norm_lut_f32_kernel(const unsigned int* _
   if (threadIdx.x == 0) {
     const long long n = (long long)cum[255];
     double lo, hi, sub, den;
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
       // 'single' (:108-112): np.percentile(float32 array, python float) runs entirely in float32 (the quantile is
       // divided by np.float32(100)), and so do the clip, min, ptp and the division.
       const float lo_f = percentile_from_hist_f32(cum, hb, n, (float)q_lo);
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(256) norm_lut_f32_kernel(const unsigned int* _
       const float cmin = fminf(fmaxf((float)s_vmin, lo_f), hi_f);
       const float cmax = fminf(fmaxf((float)s_vmax, lo_f), hi_f);
       lo = lo_f; hi = hi_f; sub = cmin;
-      den = __fadd_rn(__fsub_rn(cmax, cmin), 1e-8f);
+      den = mode == 0 ? __fadd_rn(__fsub_rn(cmax, cmin), 1e-8f) : __fsub_rn(cmax, cmin);
     } else {
       lo = percentile_from_hist(cum, hb, n, q_lo);
       hi = percentile_from_hist(cum, hb, n, q_hi);
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(256) norm_lut_f32_kernel(const unsigned int* _
   const double lo = sp[0], hi = sp[1], sub = sp[2], den = sp[3];
   float* out = lut + (long long)f * kHistBins;
   for (int v = threadIdx.x; v < kHistBins; v += blockDim.x) {
-    if (mode == 0) {
+    if (mode == 0 || mode == 2) {
       const float x = fminf(fmaxf((float)v, (float)lo), (float)hi);
       out[v] = __fdiv_rn(__fsub_rn(x, (float)sub), (float)den);
     } else {
@@ -638,7 +640,10 @@ __global__ void __launch_bounds__(256) gather_tiles_f32_kernel(const float* __re
     const int iy = (int)(r % ny); r /= ny;
     const int iz = (int)(r % nz); r /= nz;
     const int f = (int)r;
-    dst[idx] = __ldg(src + (((long long)f * Z + zs[iz] + z) * H + ys[iy] + y) * W + xs[ix] + x);
+    int yy = ys[iy] + y, xx = xs[ix] + x;
+    if (yy >= H) yy = 2 * (H - 1) - yy;          // np.pad(..., 'reflect') at the far end (multi_output_unet/predict.py:172)
+    if (xx >= W) xx = 2 * (W - 1) - xx;
+    dst[idx] = __ldg(src + (((long long)f * Z + zs[iz] + z) * H + yy) * W + xx);
   }
 }
 int launch_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int* zs, const int* ys, const int* xs,
@@ -648,6 +653,53 @@ int launch_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const 
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (blocks < 1) blocks = 1;
   gather_tiles_f32_kernel<<<(int)blocks, 256, 0, stream>>>(src, F, Z, H, W, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi_output_unet/predict.py:230-285: margin-weighted mean of the float16 result patches. A patch has weight 1
+// except on its first / last `margin` rows and columns where a neighbouring patch exists (weight 0); pixels no
+// patch covers with weight > 0 get `*fill` (the global mean of the result patches). Patches are taken through the
+// table src_index[(image, j, k)] because the reference indexes its flat patch list as image*N_per_img + j*N_y + k
+// whatever the sliding-window count was. Accumulation in (j, k) order, float32, as numpy does.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_margin_kernel(StitchMarginArgs a) {
+  const long long total = (long long)a.T * a.C * a.H * a.W;
+  const float fill = __ldg(a.fill);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H); r /= a.H;
+    const int c = (int)(r % a.C); r /= a.C;
+    const int i = (int)r;
+    float acc = 0.f, wsum = 0.f;
+    for (int j = 0; j < a.ny; ++j) {
+      const int dy = y - a.ys[j];
+      if (dy < 0 || dy >= a.ph) continue;
+      const bool wy = !((j > 0 && dy < a.margin) || (j < a.ny - 1 && dy >= a.ph - a.margin));
+      for (int k = 0; k < a.nx; ++k) {
+        const int dx = x - a.xs[k];
+        if (dx < 0 || dx >= a.pw) continue;
+        const bool wx = !((k > 0 && dx < a.margin) || (k < a.nx - 1 && dx >= a.pw - a.margin));
+        const float w = (wy && wx) ? 1.f : 0.f;
+        const long long p = a.src_index[((long long)i * a.ny + j) * a.nx + k];
+        const float v = __half2float(__float2half_rn(__ldg(a.tiles + ((p * a.C + c) * a.ph + dy) * a.pw + dx)));
+        acc = __fadd_rn(acc, __fmul_rn(v, w));
+        wsum += w;
+      }
+    }
+    a.out[idx] = wsum > 0.f ? __fdiv_rn(acc, wsum) : fill;
+  }
+}
+int launch_stitch_margin(const StitchMarginArgs& a, cudaStream_t stream) {
+  const long long total = (long long)a.T * a.C * a.H * a.W;
+  long long blocks = ceil_div_ll(total, 256);
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  stitch_margin_kernel<<<(int)blocks, 256, 0, stream>>>(a);
   BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -10,8 +10,8 @@ import torch
 
 from . import _lib
 
-KIND = {'unet2d': 0, 'siam2d': 1, 'unet3d': 2, 'mo3d': 3, 'unet2d_v0': 4, 'attunet2d': 5}
-KIND_2D = ('unet2d', 'siam2d', 'unet2d_v0', 'attunet2d')
+KIND = {'unet2d': 0, 'siam2d': 1, 'unet3d': 2, 'mo3d': 3, 'unet2d_v0': 4, 'attunet2d': 5, 'mo2d': 6}
+KIND_2D = ('unet2d', 'siam2d', 'unet2d_v0', 'attunet2d', 'mo2d')
 PRECISION = {'bf16': 0, 'tf32': 1, 'fp32': 2}
 SIAM_MODE = {'concat': 0, 'max': 1, 'control': 2, 'corr': 3}
 ACT = {None: 0, 'none': 0, 'sigmoid': 1, 'tanh': 2, 'relu': 3}
@@ -299,4 +299,19 @@ def gather_tiles_f32(src, zs, ys, xs, tile):
         _lib.check(lib.biu_gather_tiles_f32(_lib.ptr(src), f, z, h, w, _lib.ptr(dzs), _lib.ptr(dys), _lib.ptr(dxs),
                                             len(zs), len(ys), len(xs), pd, ph, pw, _lib.ptr(out), _lib.stream_ptr()),
                    'biu_gather_tiles_f32')
+    return out
+
+
+def stitch_margin_f32(tiles, src_index, frames, channels, out_hw, ys, xs, tile_hw, fill, margin=20):
+    """multi_output_unet/predict.py:230-285. tiles (P, C, ph, pw) float32; src_index (frames, ny, nx) int32 device
+    tensor of flat patch indices; fill: 1-element float32 device tensor. Returns (frames, C, H, W) float32."""
+    lib = _lib.load()
+    dev = tiles.device
+    dys, dxs = _dev_i32(ys, dev), _dev_i32(xs, dev)
+    out = torch.empty((frames, channels, out_hw[0], out_hw[1]), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.biu_stitch_margin_f32(_lib.ptr(tiles), _lib.ptr(src_index), frames, channels, out_hw[0], out_hw[1],
+                                             _lib.ptr(dys), _lib.ptr(dxs), len(ys), len(xs), tile_hw[0], tile_hw[1],
+                                             int(margin), _lib.ptr(fill), _lib.ptr(out), _lib.stream_ptr()),
+                   'biu_stitch_margin_f32')
     return out

@@ -27,7 +27,8 @@ enum { BIU_NET_UNET2D = 0,   /* unet/unet.py:5 Unet */
        BIU_NET_UNET3D = 2,   /* unet3d/unet3d.py:6 UNet3D */
        BIU_NET_MO3D   = 3,   /* multi_output_unet3d/multi_output_unet3d.py:7 MultiOutputUnet3D */
        BIU_NET_UNET2D_V0 = 4, /* unet/unet_v0.py:5 Unet_v0 (ReLU blocks, early skips, decode9) */
-       BIU_NET_ATTUNET2D = 5 }; /* unet/attention_unet.py:5 AttentionUnet (gated skip connections) */
+       BIU_NET_ATTUNET2D = 5, /* unet/attention_unet.py:5 AttentionUnet (gated skip connections) */
+       BIU_NET_MO2D = 6 };   /* multi_output_unet/multi_output_unet.py:6 MultiOutputUnet (Unet body, named heads) */
 enum { BIU_PREC_BF16 = 0,    /* bf16 operands on tcgen05, fp32 accumulate */
        BIU_PREC_TF32 = 1,    /* tf32 operands on tcgen05, fp32 storage */
        BIU_PREC_FP32 = 2 };  /* fp32 CUDA-core kernels */
@@ -96,7 +97,8 @@ int biu_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int f
                   long long lut_stride, uint8_t* out, void* stream);
 
 /* multi_output_unet3d/predict.py:104-125 on an integer-valued stack: float32 LUT of the float64 expression
- * (clip(v,lo,hi) - min) / (ptp + 1e-8) [mode 0, 'single'] or (clip(v,lo,hi) - lo) / (hi - lo + 1e-8) [mode 1]. */
+ * (clip(v,lo,hi) - min) / (ptp + 1e-8) [mode 0, 'single'] or (clip(v,lo,hi) - lo) / (hi - lo + 1e-8) [mode 1];
+ * mode 2 = multi_output_unet/predict.py:128-151: (clip(v,lo,hi) - min) / max in float32. */
 int biu_norm_lut_f32(const uint32_t* hist_bounds, const uint32_t* hist_range, long long bounds_stride,
                      long long range_stride, int frames, double q_lo, double q_hi, int mode, float* lut,
                      double* params, void* stream);
@@ -124,6 +126,14 @@ int biu_stitch_mod3_u8(const uint8_t* tiles, int Z, int H, int W, const int* zs,
 int biu_stitch_ramp_f32(const float* tiles, int V, int C, int Z, int H, int W, const int* zs, const int* ys,
                         const int* xs, int nz, int ny, int nx, int pd, int ph, int pw, int margin, float* out,
                         void* stream);
+
+/* multi_output_unet/predict.py:230-285: margin-weighted mean (weight 0 on the `margin` border rows / columns that face
+ * a neighbouring patch), tiles [P][C][ph][pw] float32 read through float16 rounding like the reference's float16 patch
+ * store; src_index [T][ny][nx] = flat patch index of tile (image, j, k); ys/ny along rows, xs/nx along columns;
+ * pixels without weight get *fill (device scalar). out [T][C][H][W]. */
+int biu_stitch_margin_f32(const float* tiles, const int* src_index, int T, int C, int H, int W, const int* ys,
+                          const int* xs, int ny, int nx, int ph, int pw, int margin, const float* fill, float* out,
+                          void* stream);
 
 /* ---- single layers (used by the parity tests; same kernels the network handle launches) ------------------- */
 /* Conv(k in {1,3}, pad k/2) + per-channel scale/shift + LeakyReLU(slope) on tcgen05.

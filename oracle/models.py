@@ -102,6 +102,28 @@ def attention_unet_forward(sd, x, collect=None):
     return torch.sigmoid(logits), logits
 
 
+def mo2d_forward(sd, x, output_heads):
+    """MultiOutputUnet.forward, multi_output_unet/multi_output_unet.py:88-134: Unet body + one 1x1 conv per head."""
+    acts = {}
+    unet_body = dict(sd)
+    unet_body['final.0.weight'] = torch.zeros(1, sd['decode8.0.weight'].shape[0], 1, 1)
+    unet_body['final.0.bias'] = torch.zeros(1)
+    unet_forward(unet_body, x, collect=acts)
+    d8 = acts['d8']
+    out = {}
+    for name, cfg in output_heads.items():
+        logits = F.conv2d(d8, sd[f'output_layers.{name}.weight'], sd[f'output_layers.{name}.bias'])
+        act = cfg.get('activation')
+        if act == 'sigmoid':
+            logits = torch.sigmoid(logits)
+        elif act == 'tanh':
+            logits = torch.tanh(logits)
+        elif act == 'relu':
+            logits = torch.relu(logits)
+        out[name] = logits
+    return out
+
+
 FORWARD_2D = {'Unet': unet_forward, 'Unet_v0': unet_v0_forward, 'AttentionUnet': attention_unet_forward}
 
 

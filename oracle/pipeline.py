@@ -392,3 +392,104 @@ def mo3d_predict(imgs, sd, output_heads, use_interpolation=True, max_patch_size=
             for k in results:
                 results[k].append(preds[k].numpy())
     return {k: mo3d_stitch(np.concatenate(results[k]), shape, info) for k in results}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi_output_unet.Predict (2D, several heads): multi_output_unet/predict.py:13-285
+# ---------------------------------------------------------------------------------------------------------------
+def mo2d_preprocess(imgs, mode, clip_threshold):
+    """Predict.__preprocess (:128-151) on the float32 stack (T, H, W); numpy's own promotion rules apply."""
+    if mode == 'single':
+        for i, img in enumerate(imgs):
+            img = np.clip(img, a_min=np.nanpercentile(img, clip_threshold[0]), a_max=np.percentile(img, clip_threshold[1]))
+            img = img - np.min(img)
+            img = img / np.max(img)
+            imgs[i] = img
+    elif mode in ('first', 'all'):
+        src = imgs[0] if mode == 'first' else imgs
+        ct = (np.nanpercentile(src, clip_threshold[0]), np.percentile(src, clip_threshold[1]))
+        imgs = np.clip(imgs, ct[0], ct[1])
+        imgs = imgs - np.min(imgs)
+        imgs = imgs / np.max(imgs)
+    else:
+        raise ValueError(f'normalization_mode {mode} not valid!')
+    return imgs
+
+
+def mo2d_grid(shape, max_patch_size, add_tile):
+    """Patch size (rounded up to a multiple of 16), tile counts, linspace starts and the sliding-window starts the
+    patches are REALLY taken at (:153-184: windows every X_start[1] pixels, which can differ from the linspace)."""
+    _, h, w = shape
+    ph = ((min(h, max_patch_size[0]) + 15) // 16) * 16
+    pw = ((min(w, max_patch_size[1]) + 15) // 16) * 16
+    n_x = int(np.ceil(h / ph)) + add_tile
+    n_y = int(np.ceil(w / pw)) + add_tile
+    hp, wp = h + max(ph - h, 0), w + max(pw - w, 0)
+    xs = np.linspace(0, hp - ph, n_x).astype('uint16')
+    ys = np.linspace(0, wp - pw, n_y).astype('uint16')
+    sx = int(xs[1]) if n_x > 1 else 1
+    sy = int(ys[1]) if n_y > 1 else 1
+    wx = np.arange(0, hp - ph + 1, sx)
+    wy = np.arange(0, wp - pw + 1, sy)
+    return (ph, pw), n_x, n_y, xs, ys, wx, wy
+
+
+def mo2d_split(imgs, max_patch_size, add_tile):
+    (ph, pw), n_x, n_y, xs, ys, wx, wy = mo2d_grid(imgs.shape, max_patch_size, add_tile)
+    imgs = np.pad(imgs, ((0, 0), (0, max(ph - imgs.shape[1], 0)), (0, max(pw - imgs.shape[2], 0))), 'reflect')
+    patches = np.lib.stride_tricks.sliding_window_view(imgs, (ph, pw), axis=(1, 2))
+    patches = patches[:, ::int(xs[1]) if n_x > 1 else 1, ::int(ys[1]) if n_y > 1 else 1]
+    return patches.reshape(-1, ph, pw), ((ph, pw), n_x, n_y, xs, ys, wx, wy)
+
+
+def mo2d_stitch(result_patches, channels, shape, info, safe_margin=20):
+    """Predict.__stitch (:230-285) for one head: margin-weighted mean, holes filled with the global mean of the
+    (float16) result patches. result_patches: float16 (N, C, ph, pw)."""
+    (ph, pw), n_x, n_y, xs, ys, _, _ = info
+    t, h, w = shape
+    n_per_img = n_x * n_y
+    res = np.zeros((t, channels, max(ph, h), max(pw, w)), dtype='float32')
+    weight = np.zeros_like(res)
+    for i in range(t):
+        stack = result_patches[i * n_per_img:(i + 1) * n_per_img].reshape(n_x, n_y, *result_patches.shape[1:])
+        for j, x0 in enumerate(xs):
+            for k, y0 in enumerate(ys):
+                patch = stack[j, k]
+                pwt = np.ones_like(patch)
+                if j > 0:
+                    pwt[..., :safe_margin, :] = 0
+                if j < n_x - 1:
+                    pwt[..., -safe_margin:, :] = 0
+                if k > 0:
+                    pwt[..., :safe_margin] = 0
+                if k < n_y - 1:
+                    pwt[..., -safe_margin:] = 0
+                res[i, :, int(x0):int(x0) + ph, int(y0):int(y0) + pw] += patch * pwt
+                weight[i, :, int(x0):int(x0) + ph, int(y0):int(y0) + pw] += pwt
+    np.divide(res, weight, out=res, where=weight > 0)
+    res[weight == 0] = result_patches.mean()
+    return np.squeeze(res[:, :, :h, :w])
+
+
+def mo2d_predict(imgs, sd, output_heads, max_patch_size=(1024, 1024), batch_size=1, normalization_mode='single',
+                 clip_threshold=(0., 99.98), add_tile=0, stages=None):
+    """multi_output_unet.Predict end to end (:16-126) with network=MultiOutputUnet on the CPU (float32 model,
+    float16 result patches) minus file I/O. Returns {head: ndarray}."""
+    sd = _to_sd(sd)
+    imgs = imgs.astype('float32')
+    if imgs.ndim == 2:
+        imgs = np.expand_dims(imgs, 0)
+    shape = imgs.shape
+    imgs = mo2d_preprocess(imgs, normalization_mode, clip_threshold)
+    patches, info = mo2d_split(imgs, max_patch_size, add_tile)
+    ph, pw = info[0]
+    results = {k: np.zeros((patches.shape[0], cfg['channels'], ph, pw), dtype='float16') for k, cfg in output_heads.items()}
+    with torch.no_grad():
+        for i in range(int(np.ceil(len(patches) / batch_size))):
+            batch = torch.tensor(patches[i * batch_size:(i + 1) * batch_size], dtype=torch.float32).view(-1, 1, ph, pw)
+            preds = models.mo2d_forward(sd, batch, output_heads)
+            for k in results:
+                results[k][i * batch_size:(i + 1) * batch_size] = preds[k].numpy()
+    if stages is not None:
+        stages.update(norm=imgs, patches=patches, info=info, result_patches=results)
+    return {k: mo2d_stitch(results[k], output_heads[k]['channels'], shape, info) for k in results}

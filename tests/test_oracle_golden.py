@@ -102,3 +102,30 @@ def test_mo3d_split_and_weights():
     # survey appendix B: blend profile of a middle patch along x
     w = pipeline.mo3d_patch_weight((1, 4, 40, 40), (0, 1, 1), (1, 3, 3))
     assert w[0, 0, 20, 0] == np.float32(15 / 16) and w[0, 0, 20, 1] == np.float32(1 / 16) and w[0, 0, 20, 39] == 1
+
+
+MO2D_HEADS = {'seg': {'channels': 1, 'activation': 'sigmoid'}, 'vec': {'channels': 2, 'activation': None},
+              'dist': {'channels': 1, 'activation': 'relu'}}
+
+
+@pytest.mark.parametrize('name', ['mo2d_single_overlap', 'mo2d_all_pad', 'mo2d_first_holes'])
+def test_mo2d_pipeline_matches_reference(name):
+    """multi_output_unet.Predict(network=MultiOutputUnet): normalisation and patches bit-exact (float32), result
+    patches after the reference's own float16 storage within 1 fp16 ulp, stitch exact from the reference's patches."""
+    g = _golden.load(name)
+    stages = {}
+    out = pipeline.mo2d_predict(g['imgs'].copy(), _golden.state_dict(g), MO2D_HEADS, tuple(int(v) for v in g['max_patch']),
+                                2, str(g['norm_mode']), tuple(float(v) for v in g['clip']), int(g['add_tile']), stages)
+    (ph, pw), n_x, n_y, xs, ys, wx, wy = stages['info']
+    assert (ph, pw) == tuple(g['patch_size']) and (n_x, n_y) == (int(g['N_x']), int(g['N_y']))
+    assert np.array_equal(xs, g['X_start']) and np.array_equal(ys, g['Y_start'])
+    assert stages['norm'].dtype == g['norm'].dtype and np.array_equal(stages['norm'], g['norm'])
+    assert np.array_equal(stages['patches'], g['patches'])
+    shape = g['imgs'].shape
+    for k, cfg in MO2D_HEADS.items():
+        rp, ref_rp = stages['result_patches'][k], g[f'result_patches/{k}']
+        assert rp.dtype == np.float16 and rp.shape == ref_rp.shape
+        assert np.abs(rp.astype(np.float32) - ref_rp.astype(np.float32)).max() <= 2e-3 * max(1.0, np.abs(ref_rp).max())
+        st = pipeline.mo2d_stitch(ref_rp, cfg['channels'], shape, stages['info'])
+        assert st.dtype == np.float32 and np.array_equal(st, g[f'result/{k}'])
+        assert np.abs(out[k] - g[f'result/{k}']).max() <= 2e-3 * max(1.0, np.abs(ref_rp).max())
