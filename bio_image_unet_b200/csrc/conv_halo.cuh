@@ -41,6 +41,7 @@ struct ConvHaloParams {
   int n_blk, n_total;
   int a_bufs, b_stages;
   int b_resident;                  // all (chunk, tap) weight tiles of the single n-block fit the ring: loaded once
+  int stage_bytes;                 // shared memory reserved for the epilogue's transposed-store tiles (0 or 16 KB)
   uint32_t a_buf_bytes, b_stage_bytes;
   int mode;
   float slope;
@@ -222,9 +223,16 @@ __device__ __forceinline__ void epi_store16(char* dst, const float (&v)[16], uin
 template <int ESZ, int CW, int MODE, bool POOL>
 __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const uint32_t (&acc)[32], const float* s_sc,
                                                const float* s_sh, const float* s_hw, char* out_px, char* pool_px,
-                                               int n, float (&hacc)[kMaxHead], int up_plane_elems, int up_row_elems) {
+                                               int n, float (&hacc)[kMaxHead], int up_plane_elems, int up_row_elems,
+                                               uint32_t stage, char* tr_ptr, long long tr_row_bytes, uint32_t tr_rows,
+                                               int lane) {
   // s_sc / s_sh / s_hw already point at the first channel of this chunk; out_px at the thread's pixel (channel of
   // the chunk for CONV, channel 0 of the output pixel (2y, 2x) for UP); nullptr = masked pixel.
+  // stage != 0 (bf16, CW = 32, one destination pixel per thread): the 64 bytes of every pixel go through a
+  // per-warp shared-memory tile (16-byte chunks XOR-swizzled, conflict free both ways) and are written back
+  // transposed, lane = (pixel, chunk): one warp store covers 8 pixels x 64 contiguous bytes = full 32-byte sectors
+  // instead of 32 scattered 16-byte pieces. tr_ptr: destination of (row 0, pixel lane >> 2, chunk lane & 3) of the
+  // warp's 4 x 8 pixel group, tr_rows: bit s set when row s (and this lane's column) is inside the image.
 #pragma unroll
   for (int q = 0; q < CW / 16; ++q) {
     float v[16];
@@ -270,7 +278,18 @@ __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const ui
       if (p.out == nullptr) continue;
     }
     uint32_t w[8];
-    if (MODE == EPI_UP) {
+    if (ESZ == 2 && CW == 32 && stage != 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      const uint32_t sw = (uint32_t)(lane >> 1) & 3u, row = stage + (uint32_t)lane * 64u;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2u * q) ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
+                   "r"(w[2]), "r"(w[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2u * q + 1u) ^ sw) << 4)), "r"(w[4]),
+                   "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    } else if (MODE == EPI_UP) {
       // channel n+16q of the GEMM = (kernel position qd, output channel co); qd = (az, ay, ax) bits
       const int nn = n + q * 16;
       const int qd = nn / p.up_cout, co = nn - qd * p.up_cout;
@@ -310,12 +329,28 @@ __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const ui
       }
     }
   }
+  if (ESZ == 2 && CW == 32 && stage != 0) {
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t pp = (uint32_t)(r * 8 + (lane >> 2));
+      uint32_t d0, d1, d2, d3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3)
+                   : "r"(stage + pp * 64u + ((((uint32_t)lane & 3u) ^ ((pp >> 1) & 3u)) << 4))
+                   : "memory");
+      if (tr_ptr != nullptr && ((tr_rows >> r) & 1u))
+        *reinterpret_cast<uint4*>(tr_ptr + r * tr_row_bytes) = make_uint4(d0, d1, d2, d3);
+    }
+    __syncwarp();
+  }
 }
 
 template <int ESZ, int CW, int MODE, bool POOL>
 __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t tmem_base, uint32_t acc_cols,
                                               uint64_t* acc_full, uint64_t* acc_empty, const float* s_scale,
-                                              const float* s_shift, const float* s_headw, int warp, int lane) {
+                                              const float* s_shift, const float* s_headw, uint32_t stage_base,
+                                              int warp, int lane) {
   const int grp = warp & 3;                      // TMEM lane quarter
   const int egrp = (warp - 4) >> 2;              // epilogue group 0 / 1
   const int m = grp * 32 + lane;                 // accumulator row: pixel (m >> 3, m & 7) of each MMA tile
@@ -330,6 +365,11 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   const int jp_bytes = 4 * p.pool_ctot * ESZ;
   const int up_row_elems = 2 * p.W * p.out_ctot;                    // EPI_UP: one output row / plane, in elements
   const int up_plane_elems = 4 * p.H * p.W * p.out_ctot;
+  // staged (transposed) stores: bf16, 32-channel chunks that land in ONE destination pixel per thread
+  const bool staged = ESZ == 2 && CW == 32 && stage_base != 0 && p.out != nullptr && !dbg_nostore &&
+                      (MODE == EPI_CONV || (MODE == EPI_UP && p.up_cout % 32 == 0));
+  const uint32_t stage = staged ? stage_base + (uint32_t)(warp - 4) * 2048u : 0u;
+  const long long tr_row_bytes = (MODE == EPI_UP ? 2LL * up_row_elems : (long long)p.W * p.out_ctot) * ESZ;
   int it = 0;
   PROF_DECL(warp == 4 && lane == 0);
   for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
@@ -356,6 +396,22 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       const long long ppix = (((long long)tl.b0 * p.D + tl.z0) * (p.H >> 1) + (py >> 1)) * (p.W >> 1) + (px0 >> 1);
       pool0 = reinterpret_cast<char*>(p.pool_out) + (ppix * p.pool_ctot + p.pool_coff + tl.n0) * ESZ;
     }
+    // transposed view of the warp's 4 x 8 pixel group: this lane writes chunk (lane & 3) of pixel column lane >> 2
+    char* tr0 = nullptr;
+    uint32_t tr_rows = 0;
+    if (staged) {
+      const int ty = tl.y0 + grp * 4, tx = tl.x0 + (lane >> 2);
+      if (MODE == EPI_UP) {
+        const long long oplane = p.up_dims == 3 ? (long long)tl.b0 * (2 * p.D) + 2 * tl.z0 : (long long)tl.b0 * p.D + tl.z0;
+        const long long opix = (oplane * (2 * p.H) + 2 * ty) * (2 * p.W) + 2 * tx;
+        tr0 = reinterpret_cast<char*>(p.out) + (opix * p.out_ctot + p.out_coff) * ESZ + (lane & 3) * 16;
+      } else {
+        const long long pix = (((long long)tl.b0 * p.D + tl.z0) * p.H + ty) * p.W + tx;
+        tr0 = reinterpret_cast<char*>(p.out) + (pix * p.out_ctot + p.out_coff + tl.n0) * ESZ + (lane & 3) * 16;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tr_rows |= (ty + r < p.H ? 1u : 0u) << r;
+    }
     const bool pool_lane = (lane & 9) == 0;      // even x and even y
     const uint32_t trow = tmem_base + as * acc_cols + ((uint32_t)(grp * 32) << 16);
     const float* sc_n0 = s_scale + tl.n0;
@@ -371,8 +427,20 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       const bool ok = row_ok && (px0 + 8 * j) < p.W && !dbg_nostore;
       char* o = (ok && out0 != nullptr) ? out0 + j * j_bytes + (MODE == EPI_UP ? 0 : c * CW * ESZ) : nullptr;
       char* po = (POOL && ok && pool_lane) ? pool0 + j * jp_bytes + c * CW * ESZ : nullptr;
+      char* tr = nullptr;
+      if (staged && (tl.x0 + 8 * j + (lane >> 2)) < p.W) {
+        if (MODE == EPI_UP) {
+          const int nn = tl.n0 + c * CW;
+          const int qd = nn / p.up_cout, co = nn - qd * p.up_cout;
+          tr = tr0 + j * j_bytes +
+               (long long)((qd >> 2) * up_plane_elems + ((qd >> 1) & 1) * up_row_elems + (qd & 1) * p.out_ctot + co) * ESZ;
+        } else {
+          tr = tr0 + j * j_bytes + c * CW * ESZ;
+        }
+      }
       halo_epi_chunk<ESZ, CW, MODE, POOL>(p, acc, sc_n0 + c * CW, sh_n0 + c * CW, s_headw + c * CW, o, po,
-                                          tl.n0 + c * CW, hacc, up_plane_elems, up_row_elems);
+                                          tl.n0 + c * CW, hacc, up_plane_elems, up_row_elems, stage, tr, tr_row_bytes,
+                                          tr_rows, lane);
       if (MODE == EPI_HEAD && c == nchunks - 1) {
         if (row_ok && (px0 + 8 * j) < p.W) {
           const long long plane = (long long)p.D * p.H * p.W;
@@ -436,6 +504,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       reinterpret_cast<float*>(smem_raw + smem_off + p.a_bufs * p.a_buf_bytes + p.b_stages * p.b_stage_bytes);
   float* s_shift = s_scale + p.n_total;
   float* s_headw = s_shift + p.n_total;
+  // 8 x 2 KB staging tiles of the epilogue warps (0 when the plan reserved none)
+  const uint32_t stage_base = p.stage_bytes ? ((smem_u32(s_headw + (p.mode == EPI_HEAD ? p.head_n * p.n_blk : 0)) + 15u) & ~15u) : 0u;
   const int pw = 8 * p.mt + 2 * p.halo;                          // smem tile pitch in pixels
   const int rows = 16 + 2 * p.halo;
   const uint32_t rb = p.row_bytes;
@@ -605,7 +675,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
 #define BIU_EPI(CW, MODE, POOL) \
-    halo_epilogue<ESZ, CW, MODE, POOL>(p, tmem_base, acc_cols, acc_full, acc_empty, s_scale, s_shift, s_headw, warp, lane)
+    halo_epilogue<ESZ, CW, MODE, POOL>(p, tmem_base, acc_cols, acc_full, acc_empty, s_scale, s_shift, s_headw, stage_base, warp, lane)
     if (p.n_blk % 32 == 0) {
       if (p.mode == EPI_CONV) { if (p.pool_out != nullptr) BIU_EPI(32, EPI_CONV, true); else BIU_EPI(32, EPI_CONV, false); }
       else if (p.mode == EPI_UP) BIU_EPI(32, EPI_UP, false);

@@ -130,7 +130,7 @@ static int sm_count_cached() {
   return n;
 }
 
-struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
+struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident, stage_bytes; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
 
 // can the halo kernel take this layer? (3x3(x3) blocks, and transposed convolutions as a 1-tap GEMM)
 static bool halo_shape_ok(const ConvTcArgs& a) {
@@ -149,7 +149,10 @@ static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
   const int halo = a.kw == 3 ? 1 : 0;
   const int rows = 16 + 2 * halo;
   const int taps = halo ? 9 * a.kd : 1;
-  const int extra = (2 * a.n_total + (a.mode == EPI_HEAD ? a.head_n * n_blk : 0)) * 4 + 64;   // scale/shift/head
+  // transposed-store staging of the epilogue: bf16, 32-channel chunks, conv / transposed conv into one pixel
+  const int stage_bytes = (a.esz == 2 && n_blk % 32 == 0 && a.mode != EPI_HEAD && a.out != nullptr &&
+                           (a.mode != EPI_UP || a.up_cout % 32 == 0)) ? 8 * 2048 : 0;
+  const int extra = (2 * a.n_total + (a.mode == EPI_HEAD ? a.head_n * n_blk : 0)) * 4 + 64 + stage_bytes;   // scale/shift/head
   const int budget = 225 * 1024 - extra;
   const int ck0 = pick_ck(a.cin, a.esz);
   int mt_max = 256 / n_blk;                                // two accumulator stages of mt * n_blk TMEM columns
@@ -180,6 +183,7 @@ static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
         if (stages > taps * chunks) stages = taps * chunks;
         if (stages >= (abufs == 2 ? 3 : 2) || stages == taps * chunks) {
           pl.mt = mt; pl.a_bufs = abufs; pl.b_stages = stages; pl.ck = ck; pl.b_resident = resident ? 1 : 0;
+          pl.stage_bytes = stage_bytes;
           pl.a_buf_bytes = tile; pl.b_stage_bytes = bst;
           pl.smem = (int)(abufs * tile + stages * bst) + 1024 + extra;
           pl.ok = true;
@@ -216,6 +220,7 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   p.n_blk = n_blk; p.n_total = a.n_total;
   p.a_bufs = pl.a_bufs; p.b_stages = pl.b_stages; p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
   p.b_resident = pl.b_resident;
+  p.stage_bytes = pl.stage_bytes;
   p.up_cout = a.up_cout; p.up_dims = a.up_dims;
   p.pool_out = a.pool_out; p.pool_ctot = a.pool_ctot; p.pool_coff = a.pool_coff;
   p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;
