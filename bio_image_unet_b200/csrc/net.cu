@@ -117,7 +117,6 @@ int net_build(Net* n) {
     const bool v0 = n->kind == NET_UNET2D_V0;       // unet/unet_v0.py: ReLU blocks, skips after the first conv, decode9
     const bool att = n->kind == NET_ATTUNET2D;      // unet/attention_unet.py: gated skips, cat((attention, up))
     BIU_REQUIRE(!att || nf % 2 == 0, "AttentionUnet needs an even n_filter");
-    BIU_REQUIRE(!(siam && n->siam_mode == SIAM_CORR), "Siam_UNet mode='corr' is not implemented by this engine");
     // 'control' ignores the previous frame (siam_unet.py:122-123): its encoder pass is dead work and is skipped
     const int bm = (siam && n->siam_mode != SIAM_CONTROL) ? 2 : 1;
     int ch[5] = {nf, 2 * nf, 4 * nf, 8 * nf, 16 * nf};
@@ -161,7 +160,7 @@ int net_build(Net* n) {
       }
       if (v0) {
         b.op(OP_POOL, -1, e_a[l], 0, m[l], 0, pad16(ch[l]), l, bm);
-      } else if (l < 3 || !siam || n->siam_mode == SIAM_MAX || n->siam_mode == SIAM_CONTROL) {
+      } else if (l < 3 || !siam || n->siam_mode != SIAM_CONCAT) {
         b.op(OP_POOL, -1, cat[l], pad16(ch[l]), m[l], 0, pad16(ch[l]), l, bm);
       } else {  // concat join: pooled current -> channels [0, 8nf), pooled previous -> [8nf, 16nf)
         b.op(OP_POOL, -1, cat[l], pad16(ch[l]), joincat, 0, pad16(ch[l]), l, 1, 0, 0);
@@ -173,8 +172,10 @@ int net_build(Net* n) {
       int L = b.conv_layer("conv_concat", {{0, ch[3], 0}, {ch[3], ch[3], pad16(ch[3])}}, 2 * pad16(ch[3]), ch[3], 3);
       b.op(OP_CONV, L, joincat, 0, join, 0, 2 * pad16(ch[3]), 4);
       mid_src = join;
-    } else if (siam && n->siam_mode == SIAM_MAX) {
-      Op o; o.kind = OP_MAXJOIN; o.src = m[3]; o.dst = join; o.c = pad16(ch[3]); o.level = 4; o.src2 = 1;
+    } else if (siam && (n->siam_mode == SIAM_MAX || n->siam_mode == SIAM_CORR)) {
+      // max: element-wise maximum; corr: depth-wise cross-correlation of the two embeddings (siam_unet.py:75-83,114-117)
+      Op o; o.kind = n->siam_mode == SIAM_MAX ? OP_MAXJOIN : OP_XCORR;
+      o.src = m[3]; o.dst = join; o.c = pad16(ch[3]); o.level = 4; o.src2 = 1;
       n->ops.push_back(o);
       mid_src = join;
     }
@@ -215,8 +216,7 @@ int net_build(Net* n) {
     n->dims = 3;
     n->levels = 3;
     const bool interp = n->use_interp != 0;
-    BIU_REQUIRE(!(n->kind == NET_UNET3D && interp),
-                "UNet3D(use_interpolation=True) (trilinear upsampling) is not implemented by this engine");
+    const bool tri = n->kind == NET_UNET3D && interp;       // UNet3D(use_interpolation=True): trilinear x2, no up-conv
     const int h = nf / 2;
     // level l: first conv a[l] -> b[l] channels, second -> c[l]
     int c_in[4] = {n->in_ch, nf, 2 * nf, 4 * nf};
@@ -237,7 +237,7 @@ int net_build(Net* n) {
     for (int l = 2; l >= 0; --l) {
       d_a[l] = b.buf("d" + std::to_string(2 * (2 - l) + 1), l, pad16(dec_mid[l]));
       d_b[l] = l > 0 ? b.buf("d" + std::to_string(2 * (2 - l) + 2), l, pad16(dec_out[l])) : -1;
-      upt[l] = interp ? b.buf("upn" + std::to_string(3 - l), l, pad16(up_c[l])) : -1;
+      upt[l] = (interp && !tri) ? b.buf("upn" + std::to_string(3 - l), l, pad16(up_c[l])) : -1;
     }
     for (int l = 0; l < 3; ++l) {
       const std::string n1 = "encode" + std::to_string(2 * l + 1), n2 = "encode" + std::to_string(2 * l + 2);
@@ -248,14 +248,16 @@ int net_build(Net* n) {
         b.block(n1, m[l - 1], c_in[l], e_a[l], 0, c_a[l], l);
       }
       b.block(n2, e_a[l], c_a[l], cat[l], pad16(up_c[l]), c_b[l], l);
-      b.op(OP_POOL, -1, cat[l], pad16(up_c[l]), m[l], 0, pad16(c_b[l]), l, 1, 0, 0, interp ? 1 : 0);
+      b.op(OP_POOL, -1, cat[l], pad16(up_c[l]), m[l], 0, pad16(c_b[l]), l, 1, 0, 0, (interp && !tri) ? 1 : 0);
     }
     b.block("middle_conv1", m[2], c_in[3], mid1, 0, c_a[3], 3);
     b.block("middle_conv2", mid1, c_a[3], mid2, 0, c_b[3], 3);
     int prev = mid2, prev_c = c_b[3];
     for (int l = 2; l >= 0; --l) {
       const int k = 2 - l;
-      if (!interp) {
+      if (tri) {               // F.interpolate(scale_factor=2, mode='trilinear', align_corners=False), unet3d.py:78-92
+        b.op(OP_UPTRILINEAR, -1, prev, 0, cat[l], 0, pad16(prev_c), l + 1);
+      } else if (!interp) {
         int U = b.up_layer("up" + std::to_string(k + 1), prev_c, prev_c);
         b.op(OP_UP, U, prev, 0, cat[l], 0, pad16(prev_c), l + 1);
       } else {
@@ -564,6 +566,95 @@ __global__ void max_join_kernel(const uint4* __restrict__ a, const uint4* __rest
   }
 }
 
+// Depth-wise cross-correlation of the current and previous embeddings (siam_unet/siam_unet.py:75-83):
+// F.conv2d(curr.view(1, B*C, h, w), prev.view(B*C, 1, h, w), groups=B*C, padding='same'), i.e.
+//   out[b, y, x, c] = sum_{i, j} curr[b, y + i - (h-1)/2, x + j - (w-1)/2, c] * prev[b, i, j, c]      (zero outside;
+// for even extents PyTorch puts the extra padding at the far end). One block per (image, group of G channels):
+// both planes staged in shared memory as fp32, fp32 accumulation, 4 x 4 pixel micro-tiles per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) xcorr_join_kernel(const T* __restrict__ cur, const T* __restrict__ prev,
+                                                         T* __restrict__ out, int h, int w, int ctot, int G,
+                                                         int round_tf32) {
+  extern __shared__ float sm[];
+  float* s_cur = sm;                    // [h*w][G]
+  float* s_prev = sm + (size_t)h * w * G;
+  const int groups = ctot / G;
+  const int b = blockIdx.x / groups, c0 = (blockIdx.x % groups) * G;
+  const long long img = (long long)b * h * w * ctot;
+  for (int i = threadIdx.x; i < h * w * G; i += blockDim.x) {
+    const int pix = i / G, c = i - pix * G;
+    s_cur[i] = (float)cur[img + (long long)pix * ctot + c0 + c];
+    s_prev[i] = (float)prev[img + (long long)pix * ctot + c0 + c];
+  }
+  __syncthreads();
+  const int pt = (h - 1) / 2, pl = (w - 1) / 2;
+  for (int o = threadIdx.x; o < h * w * G; o += blockDim.x) {
+    const int pix = o / G, c = o - pix * G;
+    const int y = pix / w, x = pix - y * w;
+    float acc = 0.f;
+    const int i_lo = max(0, pt - y), i_hi = min(h, h + pt - y);      // 0 <= y + i - pt < h
+    const int j_lo = max(0, pl - x), j_hi = min(w, w + pl - x);
+    for (int i = i_lo; i < i_hi; ++i) {
+      const float* cr = s_cur + ((size_t)(y + i - pt) * w + (x - pl)) * G + c;
+      const float* pr = s_prev + (size_t)i * w * G + c;
+      for (int j = j_lo; j < j_hi; ++j) acc = fmaf(cr[(size_t)j * G], pr[(size_t)j * G], acc);
+    }
+    if (sizeof(T) == 4 && round_tf32) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(acc)); acc = __uint_as_float(u); }
+    out[img + (long long)pix * ctot + c0 + c] = (T)acc;
+  }
+}
+
+// Trilinear x2 up-sampling, align_corners=False (unet3d/unet3d.py:78-92): source coordinate (o + 0.5) / 2 - 0.5
+// clamped at 0, neighbours clamped at the far end; NDHWC, 16-byte channel vectors.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) up_trilinear_kernel(const T* __restrict__ in, int in_ctot, int in_coff, int c,
+                                                           int B, int D, int H, int W, T* __restrict__ out, int out_ctot,
+                                                           int out_coff, int round_tf32) {
+  const int oD = 2 * D, oH = 2 * H, oW = 2 * W, cv = c / VEC;
+  const long long total = (long long)B * oD * oH * oW * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int ch = (int)(r % cv) * VEC; r /= cv;
+    const int x = (int)(r % oW); r /= oW;
+    const int y = (int)(r % oH); r /= oH;
+    const int z = (int)(r % oD); r /= oD;
+    const int b = (int)r;
+    int i0[3], i1[3]; float l1[3];
+    const int o3[3] = {z, y, x}, n3[3] = {D, H, W};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float src = fmaxf(0.5f * ((float)o3[a] + 0.5f) - 0.5f, 0.f);
+      i0[a] = (int)src; i1[a] = min(i0[a] + 1, n3[a] - 1); l1[a] = src - (float)i0[a];
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float wgt = (dz ? l1[0] : 1.f - l1[0]) * (dy ? l1[1] : 1.f - l1[1]) * (dx ? l1[2] : 1.f - l1[2]);
+          const long long p = (((long long)b * D + (dz ? i1[0] : i0[0])) * H + (dy ? i1[1] : i0[1])) * W + (dx ? i1[2] : i0[2]);
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + p * in_ctot + in_coff + ch));
+          const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] = fmaf(wgt, (float)e[k], acc[k]);
+        }
+    uint4 q;
+    T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float v = acc[k];
+      if (sizeof(T) == 4 && round_tf32) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); v = __uint_as_float(u); }
+      e[k] = (T)v;
+    }
+    const long long op = (((long long)b * oD + z) * oH + y) * oW + x;
+    *reinterpret_cast<uint4*>(out + op * out_ctot + out_coff + ch) = q;
+  }
+}
+
 // skip[pix][c] *= psi[pix] on one half of a concat buffer (AttentionBlock: out = skip_connection * psi)
 __global__ void mul_psi_kernel(void* act, int ctot, int coff, int c, const float* __restrict__ psi, long long npix,
                                int esz, int round_tf32) {
@@ -795,6 +886,52 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         mul_psi_kernel<<<(int)blocks, 256, 0, stream>>>(ws + db->offset, db->ctot, o.dst_coff, o.c,
                                                         reinterpret_cast<const float*>(ws + sb->offset), npix, n->esz,
                                                         round_tf32);
+        BIU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        break;
+      }
+      case OP_XCORR: {
+        const size_t img = (size_t)d * h * w * sb->ctot * n->esz;
+        int G = 8;
+        while (G > 1 && (size_t)2 * h * w * G * sizeof(float) > 96 * 1024) G >>= 1;
+        const size_t smem = (size_t)2 * h * w * G * sizeof(float);
+        BIU_REQUIRE(smem <= 200 * 1024, "Siam_UNet mode='corr': a %dx%d embedding does not fit shared memory", h, w);
+        const int blocks = n->B * (sb->ctot / G);
+        const char* cur = ws + sb->offset;
+        const char* prv = ws + sb->offset + img * n->B;
+        if (n->esz == 2) {
+          if (smem > 48 * 1024)
+            BIU_CHECK_CUDA(cudaFuncSetAttribute(xcorr_join_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          xcorr_join_kernel<__nv_bfloat16><<<blocks, 256, smem, stream>>>(
+              reinterpret_cast<const __nv_bfloat16*>(cur), reinterpret_cast<const __nv_bfloat16*>(prv),
+              reinterpret_cast<__nv_bfloat16*>(ws + db->offset), h, w, sb->ctot, G, 0);
+        } else {
+          if (smem > 48 * 1024)
+            BIU_CHECK_CUDA(cudaFuncSetAttribute(xcorr_join_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          xcorr_join_kernel<float><<<blocks, 256, smem, stream>>>(reinterpret_cast<const float*>(cur),
+                                                                  reinterpret_cast<const float*>(prv),
+                                                                  reinterpret_cast<float*>(ws + db->offset), h, w,
+                                                                  sb->ctot, G, round_tf32);
+        }
+        BIU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        break;
+      }
+      case OP_UPTRILINEAR: {
+        const long long total = (long long)batch * 8 * d * h * w * (o.c / (16 / n->esz));
+        long long blocks = ceil_div_ll(total, 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks < 1) blocks = 1;
+        char* dst = ws + db->offset;
+        if (n->esz == 2)
+          up_trilinear_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(
+              reinterpret_cast<const __nv_bfloat16*>(src), sb->ctot, o.src_coff, o.c, batch, d, h, w,
+              reinterpret_cast<__nv_bfloat16*>(dst), db->ctot, o.dst_coff, 0);
+        else
+          up_trilinear_kernel<float, 4><<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(src), sb->ctot,
+                                                                         o.src_coff, o.c, batch, d, h, w,
+                                                                         reinterpret_cast<float*>(dst), db->ctot,
+                                                                         o.dst_coff, round_tf32);
         BIU_CHECK_CUDA(cudaGetLastError());
         count_launch();
         break;

@@ -41,7 +41,7 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   float* shift = nullptr;
 };
 
-enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN, OP_GATE, OP_MULPSI };
+enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN, OP_GATE, OP_MULPSI, OP_XCORR, OP_UPTRILINEAR };
 
 struct Op {
   OpKind kind;

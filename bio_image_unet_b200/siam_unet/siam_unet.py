@@ -17,7 +17,7 @@ class Siam_UNet(EngineModule):
         Base width.
     mode : str
         How T-1 and T are combined at the bottleneck: 'concat' (cat + conv_concat), 'max', 'corr'
-        (depth-wise cross-correlation) or 'control' (ignore T-1). The engine runs 'concat', 'max' and 'control'.
+        (depth-wise cross-correlation) or 'control' (ignore T-1); all four run on the engine.
     """
 
     def __init__(self, n_filter=32, mode='concat'):

@@ -183,8 +183,21 @@ def _body3d(sd, x, interp_updown):
     return d6
 
 
-def unet3d_forward(sd, x):
-    """UNet3D.forward with use_interpolation=False, unet3d/unet3d.py:63-99."""
+def unet3d_forward(sd, x, use_interpolation=False):
+    """UNet3D.forward, unet3d/unet3d.py:63-99 (use_interpolation=True: trilinear x2 instead of the transposed
+    convolutions, max-pooling stays)."""
+    if use_interpolation:
+        def up(t):
+            return F.interpolate(t, scale_factor=2, mode='trilinear', align_corners=False)
+        e1 = _block(sd, 'encode1', x); e2 = _block(sd, 'encode2', e1); m1 = F.max_pool3d(e2, 2, 2)
+        e3 = _block(sd, 'encode3', m1); e4 = _block(sd, 'encode4', e3); m2 = F.max_pool3d(e4, 2, 2)
+        e5 = _block(sd, 'encode5', m2); e6 = _block(sd, 'encode6', e5); m3 = F.max_pool3d(e6, 2, 2)
+        mid2 = _block(sd, 'middle_conv2', _block(sd, 'middle_conv1', m3))
+        d2 = _block(sd, 'decode2', _block(sd, 'decode1', torch.cat((up(mid2), e6), 1)))
+        d4 = _block(sd, 'decode4', _block(sd, 'decode3', torch.cat((up(d2), e4), 1)))
+        d6 = _block(sd, 'decode6', _block(sd, 'decode5', torch.cat((up(d4), e2), 1)))
+        logits = F.conv3d(d6, sd['final.weight'], sd['final.bias'])
+        return torch.sigmoid(logits), logits
     d6 = _body3d(sd, x, False)
     logits = F.conv3d(d6, sd['final.weight'], sd['final.bias'])
     return torch.sigmoid(logits), logits

@@ -251,26 +251,27 @@ def siam_predict(movie, sd, mode, resize_dim=(512, 512), invert=False, normaliza
     return np.stack(frames) if t > 1 else frames[0]
 
 
-def predict_patches_unet3d(sd, patches):
+def predict_patches_unet3d(sd, patches, use_interpolation=False):
     """unet3d.Predict.__predict (unet3d/predict.py:155-171)."""
     sd = _to_sd(sd)
     res = np.zeros_like(patches, dtype='uint8')
     with torch.no_grad():
         for i, p in enumerate(patches):
             x = torch.from_numpy(p.astype('float32') / 255).view(1, 1, *p.shape)
-            r = models.unet3d_forward(sd, x)[0].view(*p.shape).numpy()
+            r = models.unet3d_forward(sd, x, use_interpolation)[0].view(*p.shape).numpy()
             res[i] = (r * 255).astype('uint8')
     return res
 
 
-def unet3d_predict(vol, sd, resize_dim, invert=False, clip_threshold=(0., 99.8), add_patch=0, stages=None):
+def unet3d_predict(vol, sd, resize_dim, invert=False, clip_threshold=(0., 99.8), add_patch=0, stages=None,
+                   use_interpolation=False):
     """unet3d.Predict end to end (unet3d/predict.py:52-100) minus file I/O."""
     if vol.ndim == 2:
         vol = np.expand_dims(vol, 0)
     shape = vol.shape
     vol = preprocess_volume(vol, clip_threshold, invert)
     patches, grid = split_3d(vol, resize_dim, add_patch)
-    res = predict_patches_unet3d(sd, patches)
+    res = predict_patches_unet3d(sd, patches, use_interpolation)
     out = stitch_mod3(res, shape, resize_dim, grid)
     if stages is not None:
         stages.update(patches=patches, result_patches=res, grid=grid)

@@ -146,17 +146,20 @@ def gen_siam(name, shape, resize_dim, add_tile, siam_mode, norm_mode, seed, nf=4
     shutil.rmtree('temp_movie_' + name, ignore_errors=True)
 
 
-def gen_unet3d(name, shape, resize_dim, add_patch, seed, nf=4, dtype='uint16'):
+def gen_unet3d(name, shape, resize_dim, add_patch, seed, nf=4, dtype='uint16', interp=False):
     torch.manual_seed(seed)
-    model = stress_init(UNet3D(n_filter=nf), seed)
+    model = stress_init(UNet3D(n_filter=nf, use_interpolation=interp), seed)
     ckpt = f'/tmp/golden_{name}.pt'
-    torch.save({'state_dict': model.state_dict(), 'n_filter': nf, 'in_channels': 1, 'out_channels': 1}, ckpt)
+    params = {'state_dict': model.state_dict(), 'n_filter': nf, 'in_channels': 1, 'out_channels': 1}
+    if interp:                # unet3d/predict.py:82-86 reads the flag from the checkpoint
+        params['use_interpolation'] = True
+    torch.save(params, ckpt)
     vol = blobs(shape, seed, dtype)
     with Capture(Unet3dPredict, ['split', 'predict', 'stitch']) as cap:
         p = Unet3dPredict(vol.copy(), 'res_' + name, ckpt, resize_dim=resize_dim, clip_threshold=(0., 99.8),
                           add_patch=add_patch, progress_bar=False, device='cpu')
     save(name, vol=vol, resize_dim=np.array(resize_dim), add_patch=add_patch, clip=np.array([0., 99.8]), n_filter=nf,
-         N_z=p.N_z, N_x=p.N_x, N_y=p.N_y, Z_start=p.Z_start, X_start=p.X_start, Y_start=p.Y_start,
+         interp=int(interp), N_z=p.N_z, N_x=p.N_x, N_y=p.N_y, Z_start=p.Z_start, X_start=p.X_start, Y_start=p.Y_start,
          patches=cap.out['split'][0], result_patches=cap.out['predict'][0], result=cap.out['stitch'][0],
          result_file=ref_import.TIFF_STORE['res_' + name], **sd_arrays(model))
 
@@ -213,6 +216,8 @@ if __name__ == '__main__':
                 _save(name, **arrays)
     gen_unet('attunet_single', (2, 70, 90), (32, 48), 1, 'single', False, seed=15, network='AttentionUnet', nf=8)
     gen_unet('unetv0_all', (2, 64, 80), (32, 32), 1, 'all', False, seed=16, network='Unet_v0')
+    gen_siam('siam_corr', (3, 48, 64), (32, 48), 1, 'corr', 'single', seed=24)
+    gen_unet3d('unet3d_trilinear', (12, 40, 40), (8, 16, 24), 1, seed=33, interp=True)
     gen_mo2d('mo2d_single_overlap', (2, 100, 150), (64, 80), 1, 'single', seed=51)
     gen_mo2d('mo2d_all_pad', (3, 40, 70), (64, 64), 0, 'all', seed=52, dtype='uint8')
     gen_mo2d('mo2d_first_holes', (2, 96, 96), (48, 48), 2, 'first', seed=53)

@@ -20,7 +20,7 @@ FLOAT_TOL = {'fp32': 2e-4, 'tf32': 2e-2, 'bf16': 1.5e-1}
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
-@pytest.mark.parametrize('name', ['siam_concat', 'siam_max', 'siam_control_small'])
+@pytest.mark.parametrize('name', ['siam_concat', 'siam_max', 'siam_control_small', 'siam_corr'])
 def test_siam_predict_matches_reference_golden(name, precision, tmp_path):
     from bio_image_unet_b200 import tiff
     from bio_image_unet_b200.siam_unet import Predict
@@ -36,12 +36,14 @@ def test_siam_predict_matches_reference_golden(name, precision, tmp_path):
     assert (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
     assert np.array_equal(p.X_start, g['X_start']) and np.array_equal(p.Y_start, g['Y_start'])
     assert np.array_equal(p.patches, g['patches'])                    # (T, N, 2, th, tw): ch0 current, ch1 previous
+    # 'corr' sums h*w products of two bf16-rounded embeddings on top of the usual chain: a little more headroom
+    lsb = LSB_SIAM[precision] + (10 if (name == 'siam_corr' and precision == 'bf16') else 0)
     d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
-    assert d.max() <= LSB_SIAM[precision], d.max()
+    assert d.max() <= lsb, d.max()
     assert (d > 1).mean() < {'fp32': 1e-9, 'tf32': 0.02, 'bf16': 0.3}[precision]
     out = tiff.imread(res_file)
     assert out.dtype == np.uint8 and out.shape == g['result'].shape
-    assert np.abs(out.astype(np.int16) - g['result'].astype(np.int16)).max() <= LSB_SIAM[precision]
+    assert np.abs(out.astype(np.int16) - g['result'].astype(np.int16)).max() <= lsb
     # stitch exact from the engine's own tiles
     grid = (p.N_x, p.N_y, p.X_start, p.Y_start)
     for t in range(out.shape[0]):
@@ -50,14 +52,16 @@ def test_siam_predict_matches_reference_golden(name, precision, tmp_path):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
-@pytest.mark.parametrize('name', ['unet3d_overlap', 'unet3d_disjoint'])
+@pytest.mark.parametrize('name', ['unet3d_overlap', 'unet3d_disjoint', 'unet3d_trilinear'])
 def test_unet3d_predict_matches_reference_golden(name, precision, tmp_path):
     from bio_image_unet_b200 import tiff
     from bio_image_unet_b200.unet3d import Predict
     g = _golden.load(name)
     ckpt = str(tmp_path / 'model.pt')
-    torch.save({'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1,
-                'out_channels': 1}, ckpt)
+    params = {'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1, 'out_channels': 1}
+    if 'interp' in g and int(g['interp']):
+        params['use_interpolation'] = True          # unet3d/predict.py:82-86 reads the flag from the checkpoint
+    torch.save(params, ckpt)
     res_file = str(tmp_path / 'res.tif')
     rd = tuple(int(v) for v in g['resize_dim'])
     p = Predict(g['vol'].copy(), res_file, ckpt, resize_dim=rd, clip_threshold=tuple(g['clip']),

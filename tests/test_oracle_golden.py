@@ -44,7 +44,7 @@ def test_unet_pipeline_matches_reference(name):
     assert np.array_equal(st.astype('float16'), g['result_file'])
 
 
-@pytest.mark.parametrize('name', ['siam_concat', 'siam_max', 'siam_control_small'])
+@pytest.mark.parametrize('name', ['siam_concat', 'siam_max', 'siam_control_small', 'siam_corr'])
 def test_siam_pipeline_matches_reference(name):
     g = _golden.load(name)
     out = pipeline.siam_predict(g['movie'].copy(), _golden.state_dict(g), str(g['siam_mode']), tuple(g['resize_dim']),
@@ -59,12 +59,13 @@ def test_siam_pipeline_matches_reference(name):
     assert np.array_equal(grid[2], g['X_start']) and np.array_equal(grid[3], g['Y_start'])
 
 
-@pytest.mark.parametrize('name', ['unet3d_overlap', 'unet3d_disjoint'])
+@pytest.mark.parametrize('name', ['unet3d_overlap', 'unet3d_disjoint', 'unet3d_trilinear'])
 def test_unet3d_pipeline_matches_reference(name):
     g = _golden.load(name)
     stages = {}
     out = pipeline.unet3d_predict(g['vol'].copy(), _golden.state_dict(g), tuple(int(v) for v in g['resize_dim']), False,
-                                  tuple(g['clip']), int(g['add_patch']), stages)
+                                  tuple(g['clip']), int(g['add_patch']), stages,
+                                  use_interpolation=bool(g['interp']) if 'interp' in g else False)
     n_z, n_x, n_y, zs, xs, ys = stages['grid']
     assert (n_z, n_x, n_y) == (int(g['N_z']), int(g['N_x']), int(g['N_y']))
     assert np.array_equal(zs, g['Z_start']) and np.array_equal(xs, g['X_start']) and np.array_equal(ys, g['Y_start'])
