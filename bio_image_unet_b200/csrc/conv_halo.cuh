@@ -224,15 +224,16 @@ template <int ESZ, int CW, int MODE, bool POOL>
 __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const uint32_t (&acc)[32], const float* s_sc,
                                                const float* s_sh, const float* s_hw, char* out_px, char* pool_px,
                                                int n, float (&hacc)[kMaxHead], int up_plane_elems, int up_row_elems,
-                                               uint32_t stage, char* tr_ptr, long long tr_row_bytes, uint32_t tr_rows,
-                                               int lane) {
+                                               uint32_t stage, char* tr_ptr, long long tr_row_bytes, int tr_px_bytes,
+                                               uint32_t tr_mask, int lane) {
   // s_sc / s_sh / s_hw already point at the first channel of this chunk; out_px at the thread's pixel (channel of
   // the chunk for CONV, channel 0 of the output pixel (2y, 2x) for UP); nullptr = masked pixel.
-  // stage != 0 (bf16, CW = 32, one destination pixel per thread): the 64 bytes of every pixel go through a
+  // stage != 0 (CW = 32, one destination pixel per thread): the 64 / 128 bytes of every pixel go through a
   // per-warp shared-memory tile (16-byte chunks XOR-swizzled, conflict free both ways) and are written back
-  // transposed, lane = (pixel, chunk): one warp store covers 8 pixels x 64 contiguous bytes = full 32-byte sectors
-  // instead of 32 scattered 16-byte pieces. tr_ptr: destination of (row 0, pixel lane >> 2, chunk lane & 3) of the
-  // warp's 4 x 8 pixel group, tr_rows: bit s set when row s (and this lane's column) is inside the image.
+  // transposed, lane = (pixel, chunk): one warp store covers 8 (bf16) / 4 (fp32) pixels x 64 / 128 contiguous bytes =
+  // full 32-byte sectors instead of 32 scattered 16-byte pieces. tr_ptr: destination of (row 0, pixel column
+  // lane / LPP, chunk lane % LPP) of the warp's 4 x 8 pixel group; tr_mask: bit r set when the pixel written by
+  // write-back instruction r is inside the image.
 #pragma unroll
   for (int q = 0; q < CW / 16; ++q) {
     float v[16];
@@ -278,17 +279,26 @@ __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const ui
       if (p.out == nullptr) continue;
     }
     uint32_t w[8];
-    if (ESZ == 2 && CW == 32 && stage != 0) {
+    if (CW == 32 && stage != 0) {
+      if (ESZ == 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        w[i] = *reinterpret_cast<uint32_t*>(&b2);
+        for (int i = 0; i < 8; ++i) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        const uint32_t sw = (uint32_t)(lane >> 1) & 3u, row = stage + (uint32_t)lane * 64u;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2u * q) ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
+                     "r"(w[2]), "r"(w[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2u * q + 1u) ^ sw) << 4)), "r"(w[4]),
+                     "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+      } else {                                      // fp32 storage: 128 bytes per pixel, 8 chunks, XOR with lane & 7
+        const uint32_t sw = (uint32_t)lane & 7u, row = stage + (uint32_t)lane * 128u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((4u * q + i) ^ sw) << 4)),
+                       "r"(__float_as_uint(v[4 * i])), "r"(__float_as_uint(v[4 * i + 1])),
+                       "r"(__float_as_uint(v[4 * i + 2])), "r"(__float_as_uint(v[4 * i + 3])) : "memory");
       }
-      const uint32_t sw = (uint32_t)(lane >> 1) & 3u, row = stage + (uint32_t)lane * 64u;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2u * q) ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
-                   "r"(w[2]), "r"(w[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((2u * q + 1u) ^ sw) << 4)), "r"(w[4]),
-                   "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
     } else if (MODE == EPI_UP) {
       // channel n+16q of the GEMM = (kernel position qd, output channel co); qd = (az, ay, ax) bits
       const int nn = n + q * 16;
@@ -329,18 +339,21 @@ __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const ui
       }
     }
   }
-  if (ESZ == 2 && CW == 32 && stage != 0) {
+  if (CW == 32 && stage != 0) {
+    constexpr int LPP = 2 * ESZ;                      // lanes (16-byte chunks) per pixel: 4 (bf16) or 8 (fp32)
     __syncwarp();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t pp = (uint32_t)(r * 8 + (lane >> 2));
+    for (int r = 0; r < LPP; ++r) {
+      const uint32_t pp = (uint32_t)(r * (32 / LPP) + lane / LPP);          // pixel (pp >> 3, pp & 7) of the group
+      const uint32_t sw = ESZ == 2 ? ((pp >> 1) & 3u) : (pp & 7u);
       uint32_t d0, d1, d2, d3;
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                    : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3)
-                   : "r"(stage + pp * 64u + ((((uint32_t)lane & 3u) ^ ((pp >> 1) & 3u)) << 4))
+                   : "r"(stage + pp * (uint32_t)(LPP * 16) + ((((uint32_t)lane & (LPP - 1)) ^ sw) << 4))
                    : "memory");
-      if (tr_ptr != nullptr && ((tr_rows >> r) & 1u))
-        *reinterpret_cast<uint4*>(tr_ptr + r * tr_row_bytes) = make_uint4(d0, d1, d2, d3);
+      // bf16: instruction r = row r, column lane / 4; fp32: row r / 2, column (r & 1) * 4 + lane / 8
+      char* dst = ESZ == 2 ? tr_ptr + r * tr_row_bytes : tr_ptr + (r >> 1) * tr_row_bytes + (r & 1) * 4 * tr_px_bytes;
+      if (tr_ptr != nullptr && ((tr_mask >> r) & 1u)) *reinterpret_cast<uint4*>(dst) = make_uint4(d0, d1, d2, d3);
     }
     __syncwarp();
   }
@@ -366,9 +379,11 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
   const int up_row_elems = 2 * p.W * p.out_ctot;                    // EPI_UP: one output row / plane, in elements
   const int up_plane_elems = 4 * p.H * p.W * p.out_ctot;
   // staged (transposed) stores: bf16, 32-channel chunks that land in ONE destination pixel per thread
-  const bool staged = ESZ == 2 && CW == 32 && stage_base != 0 && p.out != nullptr && !dbg_nostore &&
+  constexpr int LPP = 2 * ESZ;                   // 16-byte chunks per pixel of a 32-channel chunk
+  const bool staged = CW == 32 && stage_base != 0 && p.out != nullptr && !dbg_nostore &&
                       (MODE == EPI_CONV || (MODE == EPI_UP && p.up_cout % 32 == 0));
-  const uint32_t stage = staged ? stage_base + (uint32_t)(warp - 4) * 2048u : 0u;
+  const uint32_t stage = staged ? stage_base + (uint32_t)(warp - 4) * (uint32_t)(32 * LPP * 16) : 0u;
+  const int tr_px_bytes = (MODE == EPI_UP ? 2 : 1) * p.out_ctot * ESZ;
   const long long tr_row_bytes = (MODE == EPI_UP ? 2LL * up_row_elems : (long long)p.W * p.out_ctot) * ESZ;
   int it = 0;
   PROF_DECL(warp == 4 && lane == 0);
@@ -400,14 +415,14 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
     char* tr0 = nullptr;
     uint32_t tr_rows = 0;
     if (staged) {
-      const int ty = tl.y0 + grp * 4, tx = tl.x0 + (lane >> 2);
+      const int ty = tl.y0 + grp * 4, tx = tl.x0 + lane / LPP;
       if (MODE == EPI_UP) {
         const long long oplane = p.up_dims == 3 ? (long long)tl.b0 * (2 * p.D) + 2 * tl.z0 : (long long)tl.b0 * p.D + tl.z0;
         const long long opix = (oplane * (2 * p.H) + 2 * ty) * (2 * p.W) + 2 * tx;
-        tr0 = reinterpret_cast<char*>(p.out) + (opix * p.out_ctot + p.out_coff) * ESZ + (lane & 3) * 16;
+        tr0 = reinterpret_cast<char*>(p.out) + (opix * p.out_ctot + p.out_coff) * ESZ + (lane % LPP) * 16;
       } else {
         const long long pix = (((long long)tl.b0 * p.D + tl.z0) * p.H + ty) * p.W + tx;
-        tr0 = reinterpret_cast<char*>(p.out) + (pix * p.out_ctot + p.out_coff + tl.n0) * ESZ + (lane & 3) * 16;
+        tr0 = reinterpret_cast<char*>(p.out) + (pix * p.out_ctot + p.out_coff + tl.n0) * ESZ + (lane % LPP) * 16;
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r) tr_rows |= (ty + r < p.H ? 1u : 0u) << r;
@@ -428,7 +443,18 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       char* o = (ok && out0 != nullptr) ? out0 + j * j_bytes + (MODE == EPI_UP ? 0 : c * CW * ESZ) : nullptr;
       char* po = (POOL && ok && pool_lane) ? pool0 + j * jp_bytes + c * CW * ESZ : nullptr;
       char* tr = nullptr;
-      if (staged && (tl.x0 + 8 * j + (lane >> 2)) < p.W) {
+      uint32_t tr_mask = 0;
+      if (staged) {
+        const int xb = tl.x0 + 8 * j + lane / LPP;
+        if (ESZ == 2) {
+          tr_mask = xb < p.W ? tr_rows : 0u;
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            tr_mask |= (((tr_rows >> (r >> 1)) & 1u) && (xb + (r & 1) * 4) < p.W) ? (1u << r) : 0u;
+        }
+      }
+      if (staged && tr_mask != 0) {
         if (MODE == EPI_UP) {
           const int nn = tl.n0 + c * CW;
           const int qd = nn / p.up_cout, co = nn - qd * p.up_cout;
@@ -440,7 +466,7 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       }
       halo_epi_chunk<ESZ, CW, MODE, POOL>(p, acc, sc_n0 + c * CW, sh_n0 + c * CW, s_headw + c * CW, o, po,
                                           tl.n0 + c * CW, hacc, up_plane_elems, up_row_elems, stage, tr, tr_row_bytes,
-                                          tr_rows, lane);
+                                          tr_px_bytes, tr_mask, lane);
       if (MODE == EPI_HEAD && c == nchunks - 1) {
         if (row_ok && (px0 + 8 * j) < p.W) {
           const long long plane = (long long)p.D * p.H * p.W;

@@ -149,9 +149,9 @@ static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
   const int halo = a.kw == 3 ? 1 : 0;
   const int rows = 16 + 2 * halo;
   const int taps = halo ? 9 * a.kd : 1;
-  // transposed-store staging of the epilogue: bf16, 32-channel chunks, conv / transposed conv into one pixel
-  const int stage_bytes = (a.esz == 2 && n_blk % 32 == 0 && a.mode != EPI_HEAD && a.out != nullptr &&
-                           (a.mode != EPI_UP || a.up_cout % 32 == 0)) ? 8 * 2048 : 0;
+  // transposed-store staging of the epilogue: 32-channel chunks, conv / transposed conv into one pixel per thread
+  const int stage_bytes = (n_blk % 32 == 0 && a.mode != EPI_HEAD && a.out != nullptr &&
+                           (a.mode != EPI_UP || a.up_cout % 32 == 0)) ? 8 * 1024 * a.esz : 0;
   const int extra = (2 * a.n_total + (a.mode == EPI_HEAD ? a.head_n * n_blk : 0)) * 4 + 64 + stage_bytes;   // scale/shift/head
   const int budget = 225 * 1024 - extra;
   const int ck0 = pick_ck(a.cin, a.esz);
