@@ -83,6 +83,12 @@ int biu_net_set_force_direct(biu_net* net, int on) {
   return 0;
 }
 
+int biu_net_set_first_tc(biu_net* net, int on) {
+  BIU_REQUIRE(net && net->n, "null handle");
+  net->n->no_first_tc = on ? 0 : 1;
+  return 0;
+}
+
 int biu_set_rows_kernel(int on) {
   conv_rows_set_enabled(on);
   return 0;

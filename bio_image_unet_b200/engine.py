@@ -126,6 +126,9 @@ class Engine:
     def set_force_direct(self, on):
         _lib.check(self.lib.biu_net_set_force_direct(self.handle, int(on)))
 
+    def set_first_tc(self, on):
+        _lib.check(self.lib.biu_net_set_first_tc(self.handle, int(on)))
+
     def set_fuse_pool(self, on):
         _lib.check(self.lib.biu_net_set_fuse_pool(self.handle, int(on)))
 

@@ -74,6 +74,9 @@ int biu_net_set_force_direct(biu_net* net, int on);
 /* Test hook: 0 = run MaxPool2d as its own kernel instead of fusing it into the preceding block's epilogue
  * (default 1; both give bit-identical activations). */
 int biu_net_set_fuse_pool(biu_net* net, int on);
+/* Experimental: 1 = run the first block (1 input channel, bf16 mode) as an im2col GEMM on tcgen05 (first_tc.cu)
+ * instead of the CUDA-core kernel. Parity-tested, but measured slower (2.5 vs 1.7 ms on cfg 2), hence default 0. */
+int biu_net_set_first_tc(biu_net* net, int on);
 /* Test hook (process-wide): 0 = run the narrow (Cout <= 32) 3x3 blocks on the halo-tile kernel instead of the
  * row-streaming folded-tap kernel (default 1; results agree to fp32 summation order). */
 int biu_set_rows_kernel(int on);
