@@ -41,6 +41,8 @@ SIGNATURES = {
                                    _P]),
     'biu_stitch_ramp_f32': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, _P, _P]),
+    'biu_normalize_f32_scratch_bytes': (ctypes.c_longlong, [ctypes.c_longlong, c_int]),
+    'biu_normalize_f32': (c_int, [_P, ctypes.c_longlong, c_int, c_int, ctypes.c_double, ctypes.c_double, c_int, _P, _P, _P, _P, _P]),
     'biu_stitch_margin_f32': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
                                       _P, _P]),
     'biu_conv_tc': (c_int, [c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int,

@@ -208,6 +208,18 @@ int biu_stitch_margin_f32(const float* tiles, const int* src_index, int T, int C
   return launch_stitch_margin(a, (cudaStream_t)stream);
 }
 
+long long biu_normalize_f32_scratch_bytes(long long n_per_frame, int frames) {
+  return normalize_f32_scratch_bytes(n_per_frame, frames);
+}
+int biu_normalize_f32(const float* img, long long n_per_frame, int frames, int mode, double q_lo, double q_hi, int invert,
+                      void* scratch, float* params, uint8_t* out_u8, float* out_f32, void* stream) {
+  NormF32Args a;
+  memset(&a, 0, sizeof(a));
+  a.img = img; a.n_per_frame = n_per_frame; a.frames = frames; a.mode = mode; a.q_lo = q_lo; a.q_hi = q_hi;
+  a.invert = invert; a.scratch = reinterpret_cast<char*>(scratch); a.params = params; a.out_u8 = out_u8; a.out_f32 = out_f32;
+  return launch_normalize_f32(a, (cudaStream_t)stream);
+}
+
 unsigned long long biu_launch_count(void) { return g_launch_count; }
 int biu_net_set_profile(biu_net* net, int on) {
   BIU_REQUIRE(net && net->n, "null handle");

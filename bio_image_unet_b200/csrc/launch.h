@@ -181,6 +181,20 @@ struct StitchRampArgs {         // multi_output_unet3d/predict.py:203-307
   float* out;                   // [V][C][Z][H][W]
 };
 int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream);
+struct NormF32Args {            // percentile normalisation of a float32 stack to uint8 (unet/predict.py:122-150)
+  const float* img;             // [frames][n_per_frame]
+  long long n_per_frame;
+  int frames;
+  int mode;                     // 0 'single' (per frame), 1 'first' (bounds of frame 0), 2 'all'
+  double q_lo, q_hi;
+  int invert;
+  char* scratch;                // normalize_f32_scratch_bytes() bytes
+  float* params;                // [frames or 1][4] {lo, hi, mn, mx}
+  uint8_t* out_u8;              // [frames][n_per_frame]
+  float* out_f32;               // optional: the float32 values the reference stores back into the stack
+};
+int launch_normalize_f32(const NormF32Args& a, cudaStream_t stream);
+long long normalize_f32_scratch_bytes(long long n_per_frame, int frames);
 struct StitchMarginArgs {       // multi_output_unet/predict.py:230-285 (ys/ny index image rows, xs/nx columns)
   const float* tiles;           // [P][C][ph][pw] float32 (rounded to float16 on read, as the reference stores them)
   const int* src_index;         // [T][ny][nx] flat patch index of tile (image, j, k)

@@ -705,4 +705,195 @@ int launch_stitch_margin(const StitchMarginArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// float32 stacks (unet/predict.py:122-150 on a float image: percentiles, clip, -min, /max*255 all in float32).
+// Exact order statistics by a two-level radix select on the order-preserving 32-bit key of the float:
+//   fkey_hi16 -> uint16 image of the keys' upper halves, histogrammed by histogram_kernel (shared with the integer
+//   path, incl. hist_sum for stack-wide statistics); fkey_select picks, per statistics set, the upper-half bins that
+//   hold the six ranks needed (two neighbours for each percentile, minimum, maximum); fkey_hist_lo histograms the
+//   lower halves of the elements in those bins; fkey_params resolves the six floats and evaluates numpy's float32
+//   percentile lerp; normalize_f32_kernel applies the reference's expression element-wise.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fkey(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(256) fkey_hi16_kernel(const float* __restrict__ img, long long n, uint16_t* __restrict__ hi) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    hi[i] = (uint16_t)(fkey(__ldg(img + i)) >> 16);
+}
+
+struct FkeySel {              // per statistics set
+  int bin[6];                 // upper-half bin of: lo.prev, lo.next, hi.prev, hi.next, min, max
+  long long res[6];           // rank inside that bin
+  float gamma[2];
+};
+
+// rank -> (bin, rank within bin) over a 65536-bin histogram with 256 group sums in shared memory
+__device__ void fkey_rank_to_bin(const unsigned long long* cum_sh, const unsigned int* hist, long long k, int* bin, long long* res) {
+  int g = 0;
+  while (g < 255 && (long long)cum_sh[g] <= k) ++g;
+  long long c = g == 0 ? 0 : (long long)cum_sh[g - 1];
+  int b = g * 256;
+  for (; b < g * 256 + 255; ++b) {
+    if (c + hist[b] > k) break;
+    c += hist[b];
+  }
+  *bin = b; *res = k - c;
+}
+
+__global__ void __launch_bounds__(256) fkey_select_kernel(const unsigned int* __restrict__ hist_bounds,
+                                                          const unsigned int* __restrict__ hist_range,
+                                                          long long bounds_stride, long long range_stride, float q_lo,
+                                                          float q_hi, FkeySel* __restrict__ sel) {
+  __shared__ unsigned long long cum_b[256], cum_r[256];
+  const int s = blockIdx.x;
+  const unsigned int* hb = hist_bounds + (long long)s * bounds_stride;
+  const unsigned int* hr = hist_range + (long long)s * range_stride;
+  unsigned long long sb = 0, sr = 0;
+  for (int i = 0; i < 256; ++i) { sb += hb[threadIdx.x * 256 + i]; sr += hr[threadIdx.x * 256 + i]; }
+  cum_b[threadIdx.x] = sb; cum_r[threadIdx.x] = sr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int g = 1; g < 256; ++g) { cum_b[g] += cum_b[g - 1]; cum_r[g] += cum_r[g - 1]; }
+    const long long nb = (long long)cum_b[255], nr = (long long)cum_r[255];
+    FkeySel o;
+    const float qs[2] = {q_lo, q_hi};
+    for (int w = 0; w < 2; ++w) {        // np.percentile(float32 array, python float): float32 index arithmetic
+      const float vi = __fmul_rn((float)(nb - 1), __fdiv_rn(qs[w], 100.0f));
+      long long prev = (long long)floorf(vi), next = prev + 1;
+      float gamma;
+      if (vi >= (float)(nb - 1)) { prev = nb - 1; next = nb - 1; gamma = __fsub_rn(vi, -1.0f); }
+      else if (vi < 0.0f) { prev = 0; next = 0; gamma = vi; }
+      else gamma = __fsub_rn(vi, (float)prev);
+      if (next > nb - 1) next = nb - 1;
+      fkey_rank_to_bin(cum_b, hb, prev, &o.bin[2 * w], &o.res[2 * w]);
+      fkey_rank_to_bin(cum_b, hb, next, &o.bin[2 * w + 1], &o.res[2 * w + 1]);
+      o.gamma[w] = gamma;
+    }
+    fkey_rank_to_bin(cum_r, hr, 0, &o.bin[4], &o.res[4]);
+    fkey_rank_to_bin(cum_r, hr, nr - 1, &o.bin[5], &o.res[5]);
+    sel[s] = o;
+  }
+}
+
+// hist_lo[set][6][65536]: lower key halves of the elements whose upper half is one of the set's six bins. A frame
+// contributes to the percentile ranks (0..3) of its set only if frame < bounds_frames or the sets are per frame.
+__global__ void __launch_bounds__(256) fkey_hist_lo_kernel(const float* __restrict__ img, long long n_per_frame,
+                                                           int frames, const FkeySel* __restrict__ sel, int per_frame,
+                                                           int bounds_frames, unsigned int* __restrict__ hist_lo,
+                                                           int blocks_per_frame) {
+  const int frame = blockIdx.x / blocks_per_frame, blk = blockIdx.x % blocks_per_frame;
+  const int set = per_frame ? frame : 0;
+  const FkeySel sl = sel[set];
+  const bool bounds_ok = per_frame || frame < bounds_frames;
+  unsigned int* h = hist_lo + (long long)set * 6 * kHistBins;
+  const float* src = img + (long long)frame * n_per_frame;
+  for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame; i += (long long)blocks_per_frame * blockDim.x) {
+    const uint32_t k = fkey(__ldg(src + i));
+    const int hi = (int)(k >> 16);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+      if (hi == sl.bin[r] && (r >= 4 || bounds_ok)) atomicAdd(&h[(long long)r * kHistBins + (k & 0xffffu)], 1u);
+  }
+}
+
+// params[set] = {lo, hi, mn, mx} (float32): lo / hi = percentiles, mn = min(clip(img)), mx = max(clip(img) - mn)
+__global__ void __launch_bounds__(192) fkey_params_kernel(const FkeySel* __restrict__ sel, const unsigned int* __restrict__ hist_lo,
+                                                          float* __restrict__ params) {
+  __shared__ float vals[6];
+  const int s = blockIdx.x;
+  const FkeySel sl = sel[s];
+  if (threadIdx.x < 6) {
+    const int r = threadIdx.x;
+    const unsigned int* h = hist_lo + ((long long)s * 6 + r) * kHistBins;
+    long long c = 0;
+    int b = 0;
+    for (; b < kHistBins - 1; ++b) {
+      if (c + h[b] > sl.res[r]) break;
+      c += h[b];
+    }
+    vals[r] = fkey_inv(((uint32_t)sl.bin[r] << 16) | (uint32_t)b);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float pr[2];
+    for (int w = 0; w < 2; ++w) {
+      const float a = vals[2 * w], b = vals[2 * w + 1], g = sl.gamma[w];
+      const float diff = __fsub_rn(b, a);
+      float r = __fadd_rn(a, __fmul_rn(diff, g));
+      if (g >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, g)));
+      pr[w] = r;
+    }
+    const float cmin = fminf(fmaxf(vals[4], pr[0]), pr[1]);
+    const float cmax = fminf(fmaxf(vals[5], pr[0]), pr[1]);
+    params[s * 4 + 0] = pr[0]; params[s * 4 + 1] = pr[1]; params[s * 4 + 2] = cmin; params[s * 4 + 3] = __fsub_rn(cmax, cmin);
+  }
+}
+
+// out = uint8(trunc(float32(((clip(x, lo, hi) - mn) / mx) * 255 [255 - .]))), optionally also the float32 value
+__global__ void __launch_bounds__(256) normalize_f32_kernel(const float* __restrict__ img, long long n_per_frame, int frames,
+                                                            const float* __restrict__ params, int per_frame, int invert,
+                                                            uint8_t* __restrict__ out_u8, float* __restrict__ out_f32,
+                                                            int blocks_per_frame) {
+  const int frame = blockIdx.x / blocks_per_frame, blk = blockIdx.x % blocks_per_frame;
+  const float* pp = params + (per_frame ? frame : 0) * 4;
+  const float lo = pp[0], hi = pp[1], mn = pp[2], mx = pp[3];
+  const long long base = (long long)frame * n_per_frame;
+  for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame; i += (long long)blocks_per_frame * blockDim.x) {
+    float x = fminf(fmaxf(__ldg(img + base + i), lo), hi);
+    x = __fsub_rn(x, mn);
+    x = __fmul_rn(__fdiv_rn(x, mx), 255.0f);
+    if (invert) x = __fsub_rn(255.0f, x);
+    if (out_f32) out_f32[base + i] = x;
+    out_u8[base + i] = (uint8_t)(int)x;
+  }
+}
+
+int launch_normalize_f32(const NormF32Args& a, cudaStream_t stream) {
+  BIU_REQUIRE(a.mode >= 0 && a.mode <= 2, "normalize_f32: mode must be 0 (single), 1 (first) or 2 (all)");
+  const long long n = a.n_per_frame * a.frames;
+  const int per_frame = a.mode == 0 ? 1 : 0;
+  const int sets = per_frame ? a.frames : 1;
+  uint16_t* hi16 = reinterpret_cast<uint16_t*>(a.scratch);                                   // [n]
+  unsigned int* hist = reinterpret_cast<unsigned int*>(a.scratch + ((n * 2 + 255) & ~255LL)); // [frames][65536]
+  unsigned int* hist_tot = hist + (long long)a.frames * kHistBins;                           // [65536]
+  unsigned int* hist_lo = hist_tot + kHistBins;                                              // [sets][6][65536]
+  FkeySel* sel = reinterpret_cast<FkeySel*>(hist_lo + (long long)sets * 6 * kHistBins);      // [sets]
+  long long blocks = ceil_div_ll(n, 256 * 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  fkey_hi16_kernel<<<(int)blocks, 256, 0, stream>>>(a.img, n, hi16);
+  BIU_CHECK_CUDA(cudaMemsetAsync(hist, 0, ((long long)(a.frames + 1 + sets * 6) * kHistBins) * sizeof(unsigned int), stream));
+  if (int rc = launch_histogram(hi16, 2, a.n_per_frame, a.frames, hist, stream)) return rc;
+  const unsigned int* hb = hist; const unsigned int* hr = hist;
+  long long bs = kHistBins, rs = kHistBins;
+  if (!per_frame) {
+    if (int rc = launch_hist_sum(hist, a.frames, hist_tot, stream)) return rc;
+    hr = hist_tot; rs = 0;
+    hb = a.mode == 2 ? hist_tot : hist; bs = 0;          // 'first': bounds from frame 0 only
+  }
+  fkey_select_kernel<<<sets, 256, 0, stream>>>(hb, hr, bs, rs, (float)a.q_lo, (float)a.q_hi, sel);
+  long long bpf = ceil_div_ll(a.n_per_frame, 256 * 16);
+  if (bpf > 296) bpf = 296;
+  if (bpf < 1) bpf = 1;
+  fkey_hist_lo_kernel<<<(int)(a.frames * bpf), 256, 0, stream>>>(a.img, a.n_per_frame, a.frames, sel, per_frame,
+                                                                 a.mode == 1 ? 1 : a.frames, hist_lo, (int)bpf);
+  fkey_params_kernel<<<sets, 192, 0, stream>>>(sel, hist_lo, a.params);
+  normalize_f32_kernel<<<(int)(a.frames * bpf), 256, 0, stream>>>(a.img, a.n_per_frame, a.frames, a.params, per_frame,
+                                                                  a.invert, a.out_u8, a.out_f32, (int)bpf);
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch(5);
+  return 0;
+}
+
+long long normalize_f32_scratch_bytes(long long n_per_frame, int frames) {
+  const long long n = n_per_frame * frames;
+  return ((n * 2 + 255) & ~255LL) + ((long long)(frames + 1 + frames * 6) * kHistBins) * 4 + (long long)frames * sizeof(FkeySel) + 256;
+}
+
 }  // namespace biu

@@ -318,3 +318,23 @@ def stitch_margin_f32(tiles, src_index, frames, channels, out_hw, ys, xs, tile_h
                                              int(margin), _lib.ptr(fill), _lib.ptr(out), _lib.stream_ptr()),
                    'biu_stitch_margin_f32')
     return out
+
+
+def normalize_f32(frames, mode, q_lo, q_hi, invert, want_f32=False):
+    """Percentile normalisation of a float32 (F, ...) device stack to uint8 (unet/predict.py:122-150 as numpy
+    evaluates it on float32 data). mode: 'single' | 'first' | 'all'. Returns (u8, float32 values | None, params)."""
+    lib = _lib.load()
+    assert frames.is_cuda and frames.is_contiguous() and frames.dtype == torch.float32
+    f = frames.shape[0]
+    n = frames[0].numel()
+    dev = frames.device
+    m = {'single': 0, 'first': 1, 'all': 2}[mode]
+    scratch = torch.empty(int(lib.biu_normalize_f32_scratch_bytes(n, f)), dtype=torch.uint8, device=dev)
+    params = torch.empty((f if m == 0 else 1, 4), dtype=torch.float32, device=dev)
+    out_u8 = torch.empty(frames.shape, dtype=torch.uint8, device=dev)
+    out_f32 = torch.empty(frames.shape, dtype=torch.float32, device=dev) if want_f32 else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.biu_normalize_f32(_lib.ptr(frames), n, f, m, float(q_lo), float(q_hi), int(bool(invert)),
+                                         _lib.ptr(scratch), _lib.ptr(params), _lib.ptr(out_u8), _lib.ptr(out_f32),
+                                         _lib.stream_ptr()), 'biu_normalize_f32')
+    return out_u8, out_f32, params

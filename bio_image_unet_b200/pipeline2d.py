@@ -11,10 +11,10 @@ from . import tiling
 
 
 def to_device_stack(frames_np, device):
-    """(F, H, W) uint8/uint16 host array -> device tensor, through pinned staging."""
-    if frames_np.dtype not in (np.uint8, np.uint16):
-        raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got {frames_np.dtype}. '
-                        f'Convert the stack (e.g. to uint16) before calling Predict.')
+    """(F, H, W) uint8 / uint16 / float32 host array -> device tensor, through pinned staging."""
+    if frames_np.dtype not in (np.uint8, np.uint16, np.float32):
+        raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got '
+                        f'{frames_np.dtype}. Convert the stack (e.g. to uint16 or float32) before calling Predict.')
     host = torch.from_numpy(np.ascontiguousarray(frames_np))
     try:
         host = host.pin_memory()

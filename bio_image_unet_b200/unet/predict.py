@@ -48,6 +48,12 @@ class Session:
             self.tile_batch = P.pick_tile_batch(self.engine, self.resize_dim, max(1, total_tiles), self.workspace_bytes)
 
     def normalise_device(self, frames_dev):
+        if frames_dev.dtype == torch.float32:
+            # float stacks: exact float32 percentiles by radix select; 'first' / 'all' need the whole stack in one call
+            u8, f32, _ = P.E.normalize_f32(frames_dev.contiguous(), self.normalization_mode, self.clip_threshold[0],
+                                           self.clip_threshold[1], self.invert, want_f32=True)
+            self.last_norm_f32 = f32
+            return u8
         if self.fixed_lut is not None:
             return P.E.apply_lut(frames_dev, self.fixed_lut)
         if self.normalization_mode != 'single':
@@ -66,6 +72,8 @@ class Session:
         norm = self.normalise_device(frames_dev)
         out, grid, tiles, res_tiles = P.predict_frames_2d(self.engine, norm, self.resize_dim, self.add_tile,
                                                           self.out_channels, self.tile_batch)
+        if frames_dev.dtype == torch.float32:      # what the reference stores back into a float stack (:131)
+            norm = self.last_norm_f32
         self.last = dict(grid=grid, norm=norm, tiles=tiles if keep else None, result_tiles=res_tiles if keep else None)
         return out
 
@@ -88,19 +96,22 @@ class Session:
         chunk i-1 run on their own streams while chunk i computes. Returns (result (F, C, H, W) uint8 numpy
         array backed by a pinned buffer that the next call reuses, normalised frames (F, H, W) uint8 or None)."""
         if isinstance(frames, np.ndarray):
-            if frames.dtype not in (np.uint8, np.uint16):
-                raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got '
-                                f'{frames.dtype}. Convert the stack (e.g. to uint16) before calling Predict.')
+            if frames.dtype not in (np.uint8, np.uint16, np.float32):
+                raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got '
+                                f'{frames.dtype}. Convert the stack (e.g. to uint16 or float32) before calling Predict.')
             host = torch.from_numpy(np.ascontiguousarray(frames))
         else:
-            if frames.dtype not in (torch.uint8, torch.uint16):
-                raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got {frames.dtype}')
+            if frames.dtype not in (torch.uint8, torch.uint16, torch.float32):
+                raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got {frames.dtype}')
             host = frames.contiguous()
         f, h, w = host.shape
         n_x, n_y, _, _ = P.tiling.grid_2d(h, w, self.resize_dim, self.add_tile)
         self._ensure_plan(f * n_x * n_y)
+        is_float = host.dtype == torch.float32
         if chunk_frames is None:
             chunk_frames = max(1, min(f, self.tile_batch // (n_x * n_y)))
+        if is_float and self.normalization_mode != 'single':
+            chunk_frames = f               # stack-wide float statistics are taken in one pass over the whole stack
         dev = self.device
         with torch.cuda.device(dev):
             if self._streams is None:
@@ -110,7 +121,7 @@ class Session:
             for st in self._streams:
                 st.wait_stream(cur)
             out_host = self._pinned('out', (f, self.out_channels, h, w), torch.uint8)
-            norm_host = self._pinned('norm', (f, h, w), torch.uint8) if want_norm else None
+            norm_host = self._pinned('norm', (f, h, w), torch.float32 if is_float else torch.uint8) if want_norm else None
             pinned_in = host.is_pinned()
             key = (chunk_frames, h, w, host.dtype)
             if self._dev_in is None or self._dev_in[0] != key:
@@ -266,14 +277,19 @@ class Predict:
         ses._ensure_plan(max(1, n_local * self.N_per_img))
         # frames per chunk: enough tiles to fill a few batches, bounded so the uint8 tile arrays stay small
         chunk = max(1, min(max(n_local, 1), max(1, (4 * ses.tile_batch) // self.N_per_img)))
-        if self.normalization_mode in ('first', 'all'):
+        is_float = imgs.dtype == np.float32
+        if is_float and self.normalization_mode in ('first', 'all'):
+            if self.dist.active and self.dist.world > 1:
+                raise NotImplementedError("float stacks with normalization_mode 'first' / 'all' are not sharded over ranks")
+            chunk = max(n_local, 1)        # stack-wide float statistics: one pass over the whole stack on the device
+        elif self.normalization_mode in ('first', 'all'):
             ses.fixed_lut = self.__global_lut(imgs, lo, hi, chunk)
         out = np.zeros((n_local, out_channels, h, w), dtype='uint8')
         # super-chunks bound the pinned host buffers; inside one, copies and compute are pipelined
         frames_per_call = max(chunk, min(max(n_local, 1), (1 << 30) // max(h * w * max(out_channels, 2), 1)))
         starts = range(lo, hi, frames_per_call)
         it = progress_notifier.iterator(starts) if (self.show_progress and self.dist.rank == 0) else starts
-        want_norm = ses.fixed_lut is None and mutate_input
+        want_norm = self.normalization_mode == 'single' and mutate_input
         for s in it:
             e = min(s + frames_per_call, hi)
             if self._keep is not None:     # test hook: one chunk at a time, tiles copied out

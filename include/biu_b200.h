@@ -99,6 +99,15 @@ int biu_norm_lut(const uint32_t* hist_bounds, const uint32_t* hist_range, long l
 int biu_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
                   long long lut_stride, uint8_t* out, void* stream);
 
+/* Percentile normalisation of a FLOAT32 stack to uint8, unet/predict.py:122-150 as numpy evaluates it on a float32
+ * image (float32 percentiles with linear interpolation, clip, - min, / max * 255, optional 255 - x, truncating cast).
+ * Exact order statistics by a two-level radix select on the floats' order-preserving keys. mode 0 'single' (per
+ * frame), 1 'first' (percentiles of frame 0, range of the stack), 2 'all'. scratch: biu_normalize_f32_scratch_bytes().
+ * params [frames or 1][4] = {lo, hi, min, max}; out_f32 (optional) = the float values the reference stores back. */
+long long biu_normalize_f32_scratch_bytes(long long n_per_frame, int frames);
+int biu_normalize_f32(const float* img, long long n_per_frame, int frames, int mode, double q_lo, double q_hi, int invert,
+                      void* scratch, float* params, uint8_t* out_u8, float* out_f32, void* stream);
+
 /* multi_output_unet3d/predict.py:104-125 on an integer-valued stack: float32 LUT of the float64 expression
  * (clip(v,lo,hi) - min) / (ptp + 1e-8) [mode 0, 'single'] or (clip(v,lo,hi) - lo) / (hi - lo + 1e-8) [mode 1];
  * mode 2 = multi_output_unet/predict.py:128-151: (clip(v,lo,hi) - min) / max in float32. */

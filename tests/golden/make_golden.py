@@ -64,6 +64,8 @@ def blobs(shape, seed, dtype='uint16', peak=3000):
             s = rng.uniform(3, 9)
             flat[f] += rng.uniform(0.3, 1.0) * np.exp(-((grids[0] - cy) ** 2 + (grids[1] - cx) ** 2) / (2 * s * s))
     out = out * peak + rng.uniform(80, 120) + rng.normal(0, 12, shape)
+    if np.dtype(dtype).kind == 'f':            # float stacks: non-integer values, also negative ones
+        return ((out - 150.0) / 37.0).astype(dtype)
     out = np.clip(out, 0, np.iinfo(dtype).max)
     return out.astype(dtype)
 
@@ -216,6 +218,9 @@ if __name__ == '__main__':
                 _save(name, **arrays)
     gen_unet('attunet_single', (2, 70, 90), (32, 48), 1, 'single', False, seed=15, network='AttentionUnet', nf=8)
     gen_unet('unetv0_all', (2, 64, 80), (32, 32), 1, 'all', False, seed=16, network='Unet_v0')
+    gen_unet('unet_f32_single', (2, 70, 90), (32, 48), 1, 'single', False, seed=17, dtype='float32')
+    gen_unet('unet_f32_first_invert', (3, 64, 64), (32, 32), 1, 'first', True, seed=18, dtype='float32')
+    gen_unet('unet_f32_all', (3, 48, 80), (32, 32), 0, 'all', False, seed=19, dtype='float32')
     gen_siam('siam_corr', (3, 48, 64), (32, 48), 1, 'corr', 'single', seed=24)
     gen_unet3d('unet3d_trilinear', (12, 40, 40), (8, 16, 24), 1, seed=33, interp=True)
     gen_mo2d('mo2d_single_overlap', (2, 100, 150), (64, 80), 1, 'single', seed=51)

@@ -477,3 +477,52 @@ def test_first_block_tensor_core_matches_cuda_core(kind, n_filter, tile, batch, 
     assert c1 == c1p or np.abs(e1_tc[..., c1:]).max() == 0           # padded channels stay zero
     assert (v_tc - v_cc).abs().max().item() < TOL_STRESS['bf16']
     eng.close()
+
+
+@pytest.mark.parametrize('name', ['unet_f32_single', 'unet_f32_first_invert', 'unet_f32_all'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_predict_float32_stack_matches_reference_golden(name, precision, tmp_path):
+    """float32 input stacks: percentiles by exact radix select on the device, the reference's float32 arithmetic;
+    uint8 tiles bit-exact, 'single' mode writes the float32 normalised frames back into the caller's array."""
+    from bio_image_unet_b200 import tiff
+    from bio_image_unet_b200.unet import Predict
+    g = _golden.load(name)
+    ckpt = str(tmp_path / 'model.pt')
+    torch.save({'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1,
+                'out_channels': 1}, ckpt)
+    imgs = g['imgs'].copy()
+    assert imgs.dtype == np.float32
+    res_file = str(tmp_path / 'res.tif')
+    p = Predict(imgs, res_file, ckpt, network='Unet', resize_dim=tuple(int(v) for v in g['resize_dim']),
+                invert=bool(g['invert']), normalization_mode=str(g['mode']), clip_threshold=tuple(float(v) for v in g['clip']),
+                add_tile=int(g['add_tile']), show_progress=False, device='cuda:0', precision=precision,
+                keep_intermediates=True)
+    assert np.array_equal(p.patches, g['patches'])
+    if str(g['mode']) == 'single':
+        assert np.array_equal(imgs, g['imgs_after'])
+    else:
+        assert np.array_equal(imgs, g['imgs'])
+    d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
+    if precision == 'fp32':
+        assert d.max() <= LSB_GOLDEN[precision], d.max()
+    else:      # stress net: a few pixels on the steep part of the sigmoid move far under bf16 operand rounding
+        assert (d > LSB_GOLDEN[precision]).mean() < 5e-3 and np.median(d) <= 2, (d.max(), (d > LSB_GOLDEN[precision]).mean())
+    out = tiff.imread(res_file)
+    assert out.shape == g['result_file'].shape and out.dtype == np.float16
+
+
+def test_float32_normalisation_kernel_bit_exact():
+    """biu_normalize_f32 against numpy on awkward float data: negatives, denormal-ish magnitudes, ties, constant rows."""
+    from bio_image_unet_b200 import engine as E
+    rng = np.random.default_rng(5)
+    for mode in ('single', 'first', 'all'):
+        for invert in (False, True):
+            stack = (rng.standard_normal((3, 37, 53)) * rng.choice([1e-3, 1.0, 4e4])).astype(np.float32)
+            stack[1, :5] = stack[1, 0, 0]                     # ties
+            stack[2] = np.round(stack[2], 1)
+            ref = opipe.preprocess_stack(stack.copy(), mode, (0.5, 99.3), invert)
+            u8, f32, _ = E.normalize_f32(torch.from_numpy(stack).cuda(), mode, 0.5, 99.3, invert, want_f32=True)
+            # (a constant frame gives 0 / 0 = NaN in numpy and on the device alike)
+            assert np.array_equal(f32.cpu().numpy(), ref.astype(np.float32), equal_nan=True), (mode, invert)
+            ok = ~np.isnan(ref)
+            assert np.array_equal(u8.cpu().numpy()[ok], ref.astype(np.float32)[ok].astype(np.uint8)), (mode, invert)

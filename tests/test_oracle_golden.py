@@ -20,14 +20,15 @@ from tests import _golden
 
 
 @pytest.mark.parametrize('name', ['unet_single', 'unet_all_invert', 'unet_first_u8', 'unet_small_reflect',
-                                  'attunet_single', 'unetv0_all'])
+                                  'attunet_single', 'unetv0_all', 'unet_f32_single', 'unet_f32_first_invert',
+                                  'unet_f32_all'])
 def test_unet_pipeline_matches_reference(name):
     g = _golden.load(name)
     imgs = g['imgs'].copy()
     stages = {}
     network = str(g['network']) if 'network' in g else 'Unet'      # 'AttentionUnet' / 'Unet_v0' fixtures
     out = pipeline.unet_predict(imgs, _golden.state_dict(g), tuple(g['resize_dim']), bool(g['invert']), str(g['mode']),
-                                tuple(g['clip']), int(g['add_tile']), stages, network=network)
+                                tuple(float(v) for v in g['clip']), int(g['add_tile']), stages, network=network)
     n_x, n_y, xs, ys = stages['grid']
     assert (n_x, n_y) == (int(g['N_x']), int(g['N_y']))
     assert np.array_equal(xs, g['X_start']) and np.array_equal(ys, g['Y_start'])
