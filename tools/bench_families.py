@@ -83,6 +83,9 @@ def main():
     if 'attunet' in which:
         run('attention_unet_nf32', 'attunet2d', AttentionUnet(n_filter=32), dict(n_filter=32, in_channels=1,
             heads=[('', 1, 'sigmoid')]), (512, 512), 100, 367232 + 2 * (64 * 16 + 128 * 32 / 4 + 256 * 64 / 16 + 512 * 128 / 64))
+    if 'unet' in which:      # cfg 2 network, forward only
+        run('unet_nf32', 'unet2d', Unet(n_filter=32), dict(n_filter=32, in_channels=1, heads=[('', 1, 'sigmoid')]),
+            (512, 512), 200, 367232)
     if 'unet_tf32' in which:
         run('unet_nf32', 'unet2d', Unet(n_filter=32), dict(n_filter=32, in_channels=1, heads=[('', 1, 'sigmoid')]),
             (512, 512), 100, 367232, precision='tf32')
