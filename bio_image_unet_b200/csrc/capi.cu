@@ -33,7 +33,7 @@ int biu_version(void) { return 100; }
 biu_net* biu_net_create(int kind, int n_filter, int in_channels, int n_heads, const int* head_channels,
                         const int* head_acts, const char* const* head_names, int siam_mode, int use_interpolation,
                         int precision) {
-  if (kind < 0 || kind > 6) { set_error("unknown network kind %d", kind); return nullptr; }
+  if (kind < 0 || kind > 8) { set_error("unknown network kind %d", kind); return nullptr; }
   if (precision < 0 || precision > 2) { set_error("unknown precision %d", precision); return nullptr; }
   if (n_heads < 1 || !head_channels || !head_acts) { set_error("at least one output head is required"); return nullptr; }
   Net* n = new Net();

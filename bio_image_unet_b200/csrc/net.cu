@@ -3,6 +3,7 @@
 //   Siam_UNet     siam_unet/siam_unet.py:18-148  (twin encoder, shared weights)
 //   UNet3D        unet3d/unet3d.py:18-99         (3D, depth 3)
 //   MultiOutputUnet3D  multi_output_unet3d/multi_output_unet3d.py:13-170
+//   MultiOutputNestedUNet(_3Levels)  multi_output_unet/multi_output_nested_unet.py:58-240  (U-Net++, dense skips)
 // Activations are NHWC / NDHWC with channel counts padded to 16; torch.cat((up, skip), 1) is replaced by
 // writing both producers into one buffer at channel offsets.
 #include "net.h"
@@ -273,6 +274,60 @@ int net_build(Net* n) {
         b.op(OP_CONV_HEAD, L, d_a[0], 0, -1, 0, pad16(dec_mid[0]), 0);
       }
     }
+  } else if (n->kind == NET_NESTED2D || n->kind == NET_NESTED2D_3L) {
+    // U-Net++ (multi_output_unet/multi_output_nested_unet.py:58-148 / :151-240): node x{l}_{j} = VGGBlock(cat(x{l}_0 ..
+    // x{l}_{j-1}, up(x{l+1}_{j-1}))), VGGBlock = (Conv3x3 - BatchNorm - LeakyReLU(0.1)) x 2, up = bilinear x2 with
+    // align_corners=True. All nodes of a level live in ONE buffer: physical channels [0, 2 C_l) hold the up-sampled
+    // tensor of the block being computed (always 128-byte aligned for the up-sampling kernel's stores), node j
+    // follows at 2 C_l + j C_l, so every torch.cat is a channel PREFIX of the buffer (the layer's segment table maps
+    // the reference's logical channel order onto it) and nothing is ever copied.
+    n->dims = 2;
+    const int Lv = n->kind == NET_NESTED2D ? 4 : 3;
+    n->levels = Lv;
+    int ch[5], pc[5], upw[5], dense[5], mid[5], m[5];
+    for (int l = 0; l <= Lv; ++l) { ch[l] = nf << l; pc[l] = pad16(ch[l]); }
+    for (int l = 0; l <= Lv; ++l) upw[l] = l < Lv ? pc[l + 1] : 0;      // width of the level's up-sampling slot
+    for (int l = 0; l <= Lv; ++l) {
+      const int J = Lv - l;                              // nodes x{l}_0 .. x{l}_J; x0_J feeds the heads only
+      dense[l] = b.buf("x" + std::to_string(l), l, upw[l] + (l == 0 ? J : J + 1) * pc[l]);
+      mid[l] = b.buf("v" + std::to_string(l), l, pc[l]);
+      m[l] = l < Lv ? b.buf("m" + std::to_string(l + 1), l + 1, pc[l]) : -1;
+    }
+    auto vgg_conv = [&](const std::string& node, int which, std::vector<Segment> segs, int cin_phys, int cout) {
+      int L = b.conv_layer(node, segs, cin_phys, cout, 3);
+      n->layers[L].conv_key = node + ".conv" + std::to_string(which);
+      n->layers[L].bn_key = node + ".bn" + std::to_string(which);
+      return L;
+    };
+    for (int s = 0; s <= Lv; ++s) {
+      {   // backbone node x{s}_0
+        const std::string node = "conv" + std::to_string(s) + "_0";
+        if (s == 0) {
+          int L = vgg_conv(node, 1, {{0, n->in_ch, 0}}, n->in_ch, ch[0]);
+          b.op(OP_FIRST, L, -1, 0, mid[0], 0, n->in_ch, 0);
+        } else {
+          int L = vgg_conv(node, 1, {{0, ch[s - 1], 0}}, pc[s - 1], ch[s]);
+          b.op(OP_CONV, L, m[s - 1], 0, mid[s], 0, pc[s - 1], s);
+        }
+        int L2 = vgg_conv(node, 2, {{0, ch[s], 0}}, pc[s], ch[s]);
+        b.op(OP_CONV, L2, mid[s], 0, dense[s], upw[s], pc[s], s);
+        if (s < Lv) b.op(OP_POOL, -1, dense[s], upw[s], m[s], 0, pc[s], s);
+      }
+      for (int j = 1; j <= s; ++j) {
+        const int l = s - j;
+        const std::string node = "conv" + std::to_string(l) + "_" + std::to_string(j);
+        b.op(OP_UPBILINEAR, -1, dense[l + 1], upw[l + 1] + (j - 1) * pc[l + 1], dense[l], 0, pc[l + 1], l + 1);
+        std::vector<Segment> segs;
+        for (int k = 0; k < j; ++k) segs.push_back({k * ch[l], ch[l], upw[l] + k * pc[l]});
+        segs.push_back({j * ch[l], ch[l + 1], 0});
+        const int cin_phys = upw[l] + j * pc[l];
+        int L = vgg_conv(node, 1, segs, cin_phys, ch[l]);
+        b.op(OP_CONV, L, dense[l], 0, mid[l], 0, cin_phys, l);
+        int L2 = vgg_conv(node, 2, {{0, ch[l], 0}}, pc[l], ch[l]);
+        if (l == 0 && j == Lv) b.op(OP_CONV_HEAD, L2, mid[0], 0, -1, 0, pc[0], 0);
+        else b.op(OP_CONV, L2, mid[l], 0, dense[l], upw[l] + j * pc[l], pc[l], l);
+      }
+    }
   } else {
     BIU_REQUIRE(false, "unknown network kind %d", n->kind);
   }
@@ -366,15 +421,18 @@ int net_finalize(Net* n) {
       continue;
     }
     if (!L.is_up) {
-      const HostTensor* w = find_param(n, L.name + ".0.weight");
-      const HostTensor* bias = find_param(n, L.name + ".0.bias");
-      const HostTensor* g = find_param(n, L.name + ".1.weight");
-      const HostTensor* be = find_param(n, L.name + ".1.bias");
-      const HostTensor* mu = find_param(n, L.name + ".1.running_mean");
-      const HostTensor* var = find_param(n, L.name + ".1.running_var");
-      BIU_REQUIRE(w && bias && g && be && mu && var, "state_dict is missing parameters of block '%s'", L.name.c_str());
+      const std::string ck = L.conv_key.empty() ? L.name + ".0" : L.conv_key;
+      const std::string bk = L.bn_key.empty() ? L.name + ".1" : L.bn_key;
+      const HostTensor* w = find_param(n, ck + ".weight");
+      const HostTensor* bias = find_param(n, ck + ".bias");
+      const HostTensor* g = find_param(n, bk + ".weight");
+      const HostTensor* be = find_param(n, bk + ".bias");
+      const HostTensor* mu = find_param(n, bk + ".running_mean");
+      const HostTensor* var = find_param(n, bk + ".running_var");
+      BIU_REQUIRE(w && bias && g && be && mu && var, "state_dict is missing parameters of block '%s' / '%s'", ck.c_str(),
+                  bk.c_str());
       BIU_REQUIRE((long long)w->data.size() == (long long)L.cout * L.cin_log * taps,
-                  "'%s.0.weight' has %lld elements, expected %lld", L.name.c_str(), (long long)w->data.size(),
+                  "'%s.weight' has %lld elements, expected %lld", ck.c_str(), (long long)w->data.size(),
                   (long long)L.cout * L.cin_log * taps);
       std::vector<float> scale(L.cout_pad, 0.f), shift(L.cout_pad, 0.f);
       for (int co = 0; co < L.cout; ++co) {
@@ -510,7 +568,8 @@ int net_finalize(Net* n) {
     int row = 0;
     for (size_t hi = 0; hi < n->head_channels.size(); ++hi) {
       std::string base;
-      if (n->kind == NET_MO3D || n->kind == NET_MO2D) base = "output_layers." + n->head_names[hi];
+      if (n->kind == NET_MO3D || n->kind == NET_MO2D || n->kind == NET_NESTED2D || n->kind == NET_NESTED2D_3L)
+        base = "output_layers." + n->head_names[hi];
       else if (n->kind == NET_UNET3D) base = "final";
       else base = "final.0";
       const HostTensor* w = find_param(n, base + ".weight");
@@ -665,6 +724,121 @@ __global__ void __launch_bounds__(256) up_trilinear_kernel(const T* __restrict__
     }
     const long long op = (((long long)b * oD + z) * oH + y) * oW + x;
     *reinterpret_cast<uint4*>(out + op * out_ctot + out_coff + ch) = q;
+  }
+}
+
+// Bilinear x2 up-sampling with align_corners=True (nn.Upsample in multi_output_nested_unet.py:74): source coordinate
+// o * (n - 1) / (2n - 1) in float32, the four neighbours combined in PyTorch's order
+// h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11); NHWC, 16-byte channel vectors.
+// Output rows 2p-1 and 2p (columns 2q-1 and 2q) interpolate between the SAME two source rows (columns) p-1 and p, so a
+// thread loads one 2 x 2 source neighbourhood and produces the 2 x 2 output block: a quarter of the loads and half
+// of the arithmetic of a per-output-pixel kernel. The coordinates of every output row / column are still computed
+// with PyTorch's expression; should they ever disagree inside a pair, the pixel takes the generic path.
+__device__ __forceinline__ void bilinear_coord(int o, float s, int n, int& i0, int& i1, float& l1) {
+  const float f = s * (float)o;
+  i0 = min((int)f, n - 1);
+  i1 = min(i0 + 1, n - 1);
+  l1 = fminf(fmaxf(f - (float)i0, 0.f), 1.f);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void bilinear_load(const T* p, float (&f)[VEC]) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const T* e = reinterpret_cast<const T*>(&q);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) f[k] = (float)e[k];
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void bilinear_store(T* p, const float (&t)[VEC], const float (&bt)[VEC], float h0, float h1,
+                                               int round_tf32) {
+  uint4 q;
+  T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    float v = h0 * t[k] + h1 * bt[k];
+    if (sizeof(T) == 4 && round_tf32) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v)); v = __uint_as_float(u); }
+    e[k] = (T)v;
+  }
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) up_bilinear_kernel(const T* __restrict__ in, int in_ctot, int in_coff, int c,
+                                                          int B, int H, int W, T* __restrict__ out, int out_ctot,
+                                                          int out_coff, int round_tf32) {
+  const int oH = 2 * H, oW = 2 * W, cv = c / VEC;
+  const float sh = (float)(H - 1) / (float)(oH - 1), sw = (float)(W - 1) / (float)(oW - 1);
+  const int items = B * (H + 1), per_item = (W + 1) * cv;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / (H + 1), p = item - b * (H + 1);
+    const bool va = p >= 1, vb = p < H;                 // output rows 2p-1 / 2p exist
+    const int ya = va ? 2 * p - 1 : 2 * p, yb = vb ? 2 * p : 2 * p - 1;
+    int ya0, ya1, yb0, yb1;
+    float ha1, hb1;
+    bilinear_coord(ya, sh, H, ya0, ya1, ha1);
+    bilinear_coord(yb, sh, H, yb0, yb1, hb1);
+    const bool rows_shared = ya0 == yb0 && ya1 == yb1;
+    const T* img = in + (long long)b * H * W * in_ctot + in_coff;
+    T* oimg = out + (long long)b * oH * oW * out_ctot + out_coff;
+    for (int i = threadIdx.x; i < per_item; i += blockDim.x) {
+      const int q = i / cv, chn = (i - q * cv) * VEC;
+      const bool ua = q >= 1, ub = q < W;
+      const int xa = ua ? 2 * q - 1 : 2 * q, xb = ub ? 2 * q : 2 * q - 1;
+      int xa0, xa1, xb0, xb1;
+      float wa1, wb1;
+      bilinear_coord(xa, sw, W, xa0, xa1, wa1);
+      bilinear_coord(xb, sw, W, xb0, xb1, wb1);
+      if (rows_shared && xa0 == xb0 && xa1 == xb1) {
+        float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
+        bilinear_load<T, VEC>(img + ((long long)ya0 * W + xa0) * in_ctot + chn, v00);
+        bilinear_load<T, VEC>(img + ((long long)ya0 * W + xa1) * in_ctot + chn, v01);
+        bilinear_load<T, VEC>(img + ((long long)ya1 * W + xa0) * in_ctot + chn, v10);
+        bilinear_load<T, VEC>(img + ((long long)ya1 * W + xa1) * in_ctot + chn, v11);
+        float ta[VEC], tb[VEC], ba[VEC], bb[VEC];       // horizontal lerps of the top / bottom source row at xa / xb
+        const float wa0 = 1.f - wa1, wb0 = 1.f - wb1;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          ta[k] = wa0 * v00[k] + wa1 * v01[k];
+          tb[k] = wb0 * v00[k] + wb1 * v01[k];
+          ba[k] = wa0 * v10[k] + wa1 * v11[k];
+          bb[k] = wb0 * v10[k] + wb1 * v11[k];
+        }
+        if (va) {
+          T* orow = oimg + (long long)(2 * p - 1) * oW * out_ctot + chn;
+          if (ua) bilinear_store<T, VEC>(orow + (long long)(2 * q - 1) * out_ctot, ta, ba, 1.f - ha1, ha1, round_tf32);
+          if (ub) bilinear_store<T, VEC>(orow + (long long)(2 * q) * out_ctot, tb, bb, 1.f - ha1, ha1, round_tf32);
+        }
+        if (vb) {
+          T* orow = oimg + (long long)(2 * p) * oW * out_ctot + chn;
+          if (ua) bilinear_store<T, VEC>(orow + (long long)(2 * q - 1) * out_ctot, ta, ba, 1.f - hb1, hb1, round_tf32);
+          if (ub) bilinear_store<T, VEC>(orow + (long long)(2 * q) * out_ctot, tb, bb, 1.f - hb1, hb1, round_tf32);
+        }
+      } else {
+        // generic path, one output pixel at a time (never taken for the extents this engine plans)
+        for (int r = 0; r < 2; ++r) {
+          if (!(r ? vb : va)) continue;
+          const int y = 2 * p - 1 + r;
+          int y0, y1; float h1;
+          bilinear_coord(y, sh, H, y0, y1, h1);
+          for (int cidx = 0; cidx < 2; ++cidx) {
+            if (!(cidx ? ub : ua)) continue;
+            const int x = 2 * q - 1 + cidx;
+            int x0, x1; float w1;
+            bilinear_coord(x, sw, W, x0, x1, w1);
+            float v00[VEC], v01[VEC], v10[VEC], v11[VEC], t[VEC], bt[VEC];
+            bilinear_load<T, VEC>(img + ((long long)y0 * W + x0) * in_ctot + chn, v00);
+            bilinear_load<T, VEC>(img + ((long long)y0 * W + x1) * in_ctot + chn, v01);
+            bilinear_load<T, VEC>(img + ((long long)y1 * W + x0) * in_ctot + chn, v10);
+            bilinear_load<T, VEC>(img + ((long long)y1 * W + x1) * in_ctot + chn, v11);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              t[k] = (1.f - w1) * v00[k] + w1 * v01[k];
+              bt[k] = (1.f - w1) * v10[k] + w1 * v11[k];
+            }
+            bilinear_store<T, VEC>(oimg + ((long long)y * oW + x) * out_ctot + chn, t, bt, 1.f - h1, h1, round_tf32);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -948,6 +1122,23 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
                                                                          o.src_coff, o.c, batch, d, h, w,
                                                                          reinterpret_cast<float*>(dst), db->ctot,
                                                                          o.dst_coff, round_tf32);
+        BIU_CHECK_CUDA(cudaGetLastError());
+        count_launch();
+        break;
+      }
+      case OP_UPBILINEAR: {
+        int blocks = batch * (h + 1);                      // one block iteration per pair of output rows
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        char* dst = ws + db->offset;
+        if (n->esz == 2)
+          up_bilinear_kernel<__nv_bfloat16, 8><<<blocks, 256, 0, stream>>>(
+              reinterpret_cast<const __nv_bfloat16*>(src), sb->ctot, o.src_coff, o.c, batch, h, w,
+              reinterpret_cast<__nv_bfloat16*>(dst), db->ctot, o.dst_coff, 0);
+        else
+          up_bilinear_kernel<float, 4><<<blocks, 256, 0, stream>>>(reinterpret_cast<const float*>(src), sb->ctot,
+                                                                   o.src_coff, o.c, batch, h, w,
+                                                                   reinterpret_cast<float*>(dst), db->ctot,
+                                                                   o.dst_coff, round_tf32);
         BIU_CHECK_CUDA(cudaGetLastError());
         count_launch();
         break;

@@ -10,7 +10,8 @@
 
 namespace biu {
 
-enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3, NET_UNET2D_V0 = 4, NET_ATTUNET2D = 5, NET_MO2D = 6 };
+enum NetKind { NET_UNET2D = 0, NET_SIAM2D = 1, NET_UNET3D = 2, NET_MO3D = 3, NET_UNET2D_V0 = 4, NET_ATTUNET2D = 5, NET_MO2D = 6,
+               NET_NESTED2D = 7, NET_NESTED2D_3L = 8 };
 enum Precision { PREC_BF16 = 0, PREC_TF32 = 1, PREC_FP32 = 2 };
 enum SiamMode { SIAM_CONCAT = 0, SIAM_MAX = 1, SIAM_CONTROL = 2, SIAM_CORR = 3 };
 
@@ -25,6 +26,7 @@ struct Segment {       // logical input channels [lstart, lstart+count) live at 
 
 struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the head
   std::string name;
+  std::string conv_key, bn_key;   // state_dict prefixes of the conv and its BatchNorm; empty: '<name>.0' / '<name>.1'
   int cin_log = 0, cout = 0, cin_phys = 0, cout_pad = 0;
   int kd = 1, kh = 1, kw = 1;
   bool is_up = false;
@@ -43,7 +45,7 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   float* shift = nullptr;
 };
 
-enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN, OP_GATE, OP_MULPSI, OP_XCORR, OP_UPTRILINEAR };
+enum OpKind { OP_FIRST, OP_CONV, OP_CONV_HEAD, OP_UP, OP_POOL, OP_UPNEAREST, OP_MAXJOIN, OP_GATE, OP_MULPSI, OP_XCORR, OP_UPTRILINEAR, OP_UPBILINEAR };
 
 struct Op {
   OpKind kind;

@@ -10,8 +10,9 @@ import torch
 
 from . import _lib
 
-KIND = {'unet2d': 0, 'siam2d': 1, 'unet3d': 2, 'mo3d': 3, 'unet2d_v0': 4, 'attunet2d': 5, 'mo2d': 6}
-KIND_2D = ('unet2d', 'siam2d', 'unet2d_v0', 'attunet2d', 'mo2d')
+KIND = {'unet2d': 0, 'siam2d': 1, 'unet3d': 2, 'mo3d': 3, 'unet2d_v0': 4, 'attunet2d': 5, 'mo2d': 6, 'nested2d': 7,
+        'nested2d_3l': 8}
+KIND_2D = ('unet2d', 'siam2d', 'unet2d_v0', 'attunet2d', 'mo2d', 'nested2d', 'nested2d_3l')
 PRECISION = {'bf16': 0, 'tf32': 1, 'fp32': 2}
 SIAM_MODE = {'concat': 0, 'max': 1, 'control': 2, 'corr': 3}
 ACT = {None: 0, 'none': 0, 'sigmoid': 1, 'tanh': 2, 'relu': 3}
@@ -122,6 +123,19 @@ class Engine:
         else:
             t = host.view(np.float32)
         return t.reshape(self.batch, dd, hh, ww, channels)
+
+    def set_profile(self, on):
+        """Bracket every op of the following forwards with CUDA events (read them with read_profile())."""
+        _lib.check(self.lib.biu_net_set_profile(self.handle, int(on)))
+
+    def read_profile(self, max_ops=128):
+        """(kinds, ms) of the last profiled forward: op kind (+16: ran on the CUDA-core fallback, +32: fused into the
+        previous kernel) and duration of every op of the layer program."""
+        kinds = (ctypes.c_int * max_ops)()
+        ms = (ctypes.c_float * max_ops)()
+        n_ops = ctypes.c_int(0)
+        _lib.check(self.lib.biu_net_profile_read(self.handle, max_ops, kinds, ms, ctypes.byref(n_ops)))
+        return list(kinds[:n_ops.value]), list(ms[:n_ops.value])
 
     def set_force_direct(self, on):
         _lib.check(self.lib.biu_net_set_force_direct(self.handle, int(on)))

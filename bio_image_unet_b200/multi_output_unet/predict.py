@@ -10,6 +10,7 @@ from .. import tiff
 from ..engine import Engine
 from ..progress import ProgressNotifier
 from ..utils import get_device
+from .multi_output_nested_unet import MultiOutputNestedUNet
 from .multi_output_unet import MultiOutputUnet
 
 
@@ -39,15 +40,16 @@ class Predict:
     multi_output_unet/predict.py:16-19). Results per head in ``self.result`` (float32, when result_path is None)
     or as ``<result_path>_<head>.tif``.
 
-    network : MultiOutputUnet (class of this package or of the reference, or its name). The reference's default,
-        the nested U-Net++ ``MultiOutputNestedUNet`` (InstanceNorm first block, bilinear up-sampling), is not
-        implemented by the B200 engine and raises NotImplementedError.
+    network : MultiOutputNestedUNet (U-Net++, the reference's default), MultiOutputNestedUNet_3Levels or
+        MultiOutputUnet — the class of this package or of the reference, or its name. With a checkpoint trained with
+        ``deep_supervision`` the last supervision head ('<head>_4' / '<head>_3') is used, like the reference's
+        ``train_mode=False`` (multi_output_unet/predict.py:90-94, multi_output_nested_unet.py:143-145).
     The reference runs the model in float16 on CUDA devices and stores the result patches as float16; here the
     network runs in `precision` ('tf32' default) and the patches go through the same float16 rounding before the
     margin-weighted stitch. Integer stacks (uint8 / uint16) are normalised on the device.
     """
 
-    def __init__(self, imgs, model_params, result_path=None, network=MultiOutputUnet, max_patch_size=(1024, 1024),
+    def __init__(self, imgs, model_params, result_path=None, network=MultiOutputNestedUNet, max_patch_size=(1024, 1024),
                  batch_size=1, normalization_mode='single', clip_threshold=(0., 99.98), add_tile=0,
                  compress_tif=False, show_progress=True, device: Union[torch.device, str] = 'auto',
                  progress_notifier: ProgressNotifier = ProgressNotifier.progress_notifier_tqdm(), *,
@@ -64,11 +66,11 @@ class Predict:
         self.compress_tif = compress_tif
         self.show_progress = show_progress
         name = network if isinstance(network, str) else getattr(network, '__name__', str(network))
-        if name in ('MultiOutputNestedUNet', 'MultiOutputNestedUNet_3Levels'):
-            raise NotImplementedError(f"network '{name}' (nested U-Net++) is not implemented by the B200 engine; "
-                                      f"pass network=MultiOutputUnet")
-        if name != 'MultiOutputUnet':
+        kinds = {'MultiOutputUnet': ('mo2d', 0), 'MultiOutputNestedUNet': ('nested2d', 4),
+                 'MultiOutputNestedUNet_3Levels': ('nested2d_3l', 3)}
+        if name not in kinds:
             raise ValueError(f"unknown network '{name}'")
+        kind, depth = kinds[name]
         if normalization_mode not in ('single', 'first', 'all'):
             raise ValueError(f'normalization_mode {normalization_mode} not valid!')
 
@@ -84,8 +86,10 @@ class Predict:
         self.target_keys = list(heads.keys())
         if self.model_params['in_channels'] != 1:
             raise RuntimeError('multi_output_unet.Predict feeds single-channel patches (multi_output_unet/predict.py:208-210)')
-        self.engine = Engine('mo2d', self.model_params['state_dict'], self.model_params['n_filter'], 1,
-                             [(k, heads[k]['channels'], heads[k].get('activation')
+        # deep supervision: inference reads the last supervision head (multi_output_nested_unet.py:143-145)
+        suffix = f'_{depth}' if depth and self.model_params.get('deep_supervision', False) else ''
+        self.engine = Engine(kind, self.model_params['state_dict'], self.model_params['n_filter'], 1,
+                             [(k + suffix, heads[k]['channels'], heads[k].get('activation')
                                if heads[k].get('activation') in ('sigmoid', 'tanh', 'relu') else None)
                               for k in self.target_keys], precision=precision, device=self.device)
         (self.patch_size, self.N_x, self.N_y, self.X_start, self.Y_start, self._wx, self._wy) = grid(

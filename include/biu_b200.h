@@ -28,7 +28,9 @@ enum { BIU_NET_UNET2D = 0,   /* unet/unet.py:5 Unet */
        BIU_NET_MO3D   = 3,   /* multi_output_unet3d/multi_output_unet3d.py:7 MultiOutputUnet3D */
        BIU_NET_UNET2D_V0 = 4, /* unet/unet_v0.py:5 Unet_v0 (ReLU blocks, early skips, decode9) */
        BIU_NET_ATTUNET2D = 5, /* unet/attention_unet.py:5 AttentionUnet (gated skip connections) */
-       BIU_NET_MO2D = 6 };   /* multi_output_unet/multi_output_unet.py:6 MultiOutputUnet (Unet body, named heads) */
+       BIU_NET_MO2D = 6,     /* multi_output_unet/multi_output_unet.py:6 MultiOutputUnet (Unet body, named heads) */
+       BIU_NET_NESTED2D = 7, /* multi_output_unet/multi_output_nested_unet.py:58 MultiOutputNestedUNet (U-Net++, 4 pools) */
+       BIU_NET_NESTED2D_3L = 8 }; /* multi_output_nested_unet.py:151 MultiOutputNestedUNet_3Levels (3 pools) */
 enum { BIU_PREC_BF16 = 0,    /* bf16 operands on tcgen05, fp32 accumulate */
        BIU_PREC_TF32 = 1,    /* tf32 operands on tcgen05, fp32 storage */
        BIU_PREC_FP32 = 2 };  /* fp32 CUDA-core kernels */

@@ -124,6 +124,51 @@ def mo2d_forward(sd, x, output_heads):
     return out
 
 
+def _apply_heads(sd, feat, output_heads, suffix=''):
+    out = {}
+    for name, cfg in output_heads.items():
+        logits = F.conv2d(feat, sd[f'output_layers.{name}{suffix}.weight'], sd[f'output_layers.{name}{suffix}.bias'])
+        act = cfg.get('activation')
+        if act == 'sigmoid':
+            logits = torch.sigmoid(logits)
+        elif act == 'tanh':
+            logits = torch.tanh(logits)
+        elif act == 'relu':
+            logits = torch.relu(logits)
+        out[name] = logits
+    return out
+
+
+def _vgg(sd, name, x):
+    """VGGBlock.forward (dilation 1, eval), multi_output_unet/multi_output_nested_unet.py:33-55:
+    (Conv3x3 -> BatchNorm -> LeakyReLU(0.1) -> Dropout(identity)) x 2 with parameters conv1/bn1/conv2/bn2."""
+    for k in (1, 2):
+        x = F.conv2d(x, sd[f'{name}.conv{k}.weight'], sd[f'{name}.conv{k}.bias'], padding=1)
+        x = F.batch_norm(x, sd[f'{name}.bn{k}.running_mean'], sd[f'{name}.bn{k}.running_var'], sd[f'{name}.bn{k}.weight'],
+                         sd[f'{name}.bn{k}.bias'], training=False, eps=1e-5)
+        x = F.leaky_relu(x, 0.1)
+    return x
+
+
+def nested_forward(sd, x, output_heads, depth=4, deep_supervision=False, collect=None):
+    """MultiOutputNestedUNet.forward (depth=4, multi_output_nested_unet.py:112-148) and
+    MultiOutputNestedUNet_3Levels.forward (depth=3, :207-240) in inference configuration (train_mode=False): nodes
+    x{l}_{j} = VGG(cat(x{l}_0 .. x{l}_{j-1}, up(x{l+1}_{j-1}))), up = bilinear x2 align_corners=True; heads on
+    x0_{depth} ('<head>_{depth}' with deep supervision)."""
+    def up(t):
+        return F.interpolate(t, scale_factor=2, mode='bilinear', align_corners=True)
+    nodes = {}
+    for s in range(depth + 1):
+        nodes[(s, 0)] = _vgg(sd, f'conv{s}_0', x if s == 0 else F.max_pool2d(nodes[(s - 1, 0)], 2, 2))
+        for j in range(1, s + 1):
+            l = s - j
+            cat = [nodes[(l, k)] for k in range(j)] + [up(nodes[(l + 1, j - 1)])]
+            nodes[(l, j)] = _vgg(sd, f'conv{l}_{j}', torch.cat(cat, 1))
+    if collect is not None:
+        collect.update({f'x{l}_{j}': v for (l, j), v in nodes.items()})
+    return _apply_heads(sd, nodes[(0, depth)], output_heads, f'_{depth}' if deep_supervision else '')
+
+
 FORWARD_2D = {'Unet': unet_forward, 'Unet_v0': unet_v0_forward, 'AttentionUnet': attention_unet_forward}
 
 

@@ -473,9 +473,10 @@ def mo2d_stitch(result_patches, channels, shape, info, safe_margin=20):
 
 
 def mo2d_predict(imgs, sd, output_heads, max_patch_size=(1024, 1024), batch_size=1, normalization_mode='single',
-                 clip_threshold=(0., 99.98), add_tile=0, stages=None):
-    """multi_output_unet.Predict end to end (:16-126) with network=MultiOutputUnet on the CPU (float32 model,
-    float16 result patches) minus file I/O. Returns {head: ndarray}."""
+                 clip_threshold=(0., 99.98), add_tile=0, stages=None, network='MultiOutputUnet', deep_supervision=False):
+    """multi_output_unet.Predict end to end (:16-126) on the CPU (float32 model, float16 result patches) minus file
+    I/O; network = 'MultiOutputUnet' | 'MultiOutputNestedUNet' | 'MultiOutputNestedUNet_3Levels'.
+    Returns {head: ndarray}."""
     sd = _to_sd(sd)
     imgs = imgs.astype('float32')
     if imgs.ndim == 2:
@@ -488,7 +489,11 @@ def mo2d_predict(imgs, sd, output_heads, max_patch_size=(1024, 1024), batch_size
     with torch.no_grad():
         for i in range(int(np.ceil(len(patches) / batch_size))):
             batch = torch.tensor(patches[i * batch_size:(i + 1) * batch_size], dtype=torch.float32).view(-1, 1, ph, pw)
-            preds = models.mo2d_forward(sd, batch, output_heads)
+            if network == 'MultiOutputUnet':
+                preds = models.mo2d_forward(sd, batch, output_heads)
+            else:
+                preds = models.nested_forward(sd, batch, output_heads, 4 if network == 'MultiOutputNestedUNet' else 3,
+                                              deep_supervision)
             for k in results:
                 results[k][i * batch_size:(i + 1) * batch_size] = preds[k].numpy()
     if stages is not None:

@@ -31,6 +31,8 @@ from bio_image_unet.multi_output_unet3d.predict import Predict as Mo3dPredict  #
 from bio_image_unet.multi_output_unet3d.multi_output_unet3d import MultiOutputUnet3D  # noqa: E402
 from bio_image_unet.multi_output_unet.predict import Predict as Mo2dPredict  # noqa: E402
 from bio_image_unet.multi_output_unet.multi_output_unet import MultiOutputUnet  # noqa: E402
+from bio_image_unet.multi_output_unet.multi_output_nested_unet import (MultiOutputNestedUNet,  # noqa: E402
+                                                                        MultiOutputNestedUNet_3Levels)
 
 
 def stress_init(model, seed, head_gain=4.0):
@@ -187,24 +189,29 @@ def gen_mo3d(name, shape, max_patch, overlap, norm_mode, interp, seed, nf=4, bat
          **sd_arrays(model))
 
 
-def gen_mo2d(name, shape, max_patch, add_tile, norm_mode, seed, nf=4, batch_size=2, dtype='uint16'):
+def gen_mo2d(name, shape, max_patch, add_tile, norm_mode, seed, nf=4, batch_size=2, dtype='uint16',
+             network=MultiOutputUnet, deep_supervision=False):
     torch.manual_seed(seed)
     heads = {'seg': {'channels': 1, 'activation': 'sigmoid'}, 'vec': {'channels': 2, 'activation': None},
              'dist': {'channels': 1, 'activation': 'relu'}}
-    model = stress_init(MultiOutputUnet(1, heads, nf), seed, head_gain=2.0)
+    if network is MultiOutputUnet:
+        model = stress_init(MultiOutputUnet(1, heads, nf), seed, head_gain=2.0)
+    else:
+        model = stress_init(network(1, heads, nf, deep_supervision=deep_supervision), seed, head_gain=2.0)
     ckpt = f'/tmp/golden_{name}.pt'
-    torch.save({'state_dict': model.state_dict(), 'n_filter': nf, 'in_channels': 1, 'output_heads': heads}, ckpt)
+    torch.save({'state_dict': model.state_dict(), 'n_filter': nf, 'in_channels': 1, 'output_heads': heads,
+                'deep_supervision': deep_supervision}, ckpt)
     imgs = blobs(shape, seed, dtype)
     with Capture(Mo2dPredict, ['preprocess', 'split', 'predict']) as cap:
-        p = Mo2dPredict(imgs.copy(), ckpt, result_path=None, network=MultiOutputUnet, max_patch_size=max_patch,
+        p = Mo2dPredict(imgs.copy(), ckpt, result_path=None, network=network, max_patch_size=max_patch,
                         batch_size=batch_size, normalization_mode=norm_mode, clip_threshold=(0., 99.98),
                         add_tile=add_tile, show_progress=False, device='cpu')
     arrays = {f'result/{k}': v for k, v in p.result.items()}
     arrays.update({f'result_patches/{k}': v for k, v in cap.out['predict'][0].items()})
     save(name, imgs=imgs, max_patch=np.array(max_patch), add_tile=add_tile, norm_mode=norm_mode,
          clip=np.array([0., 99.98]), n_filter=nf, patch_size=np.array(p.patch_size), N_x=p.N_x, N_y=p.N_y,
-         X_start=p.X_start, Y_start=p.Y_start, norm=cap.out['preprocess'][0], patches=cap.out['split'][0], **arrays,
-         **sd_arrays(model))
+         X_start=p.X_start, Y_start=p.Y_start, norm=cap.out['preprocess'][0], patches=cap.out['split'][0],
+         network=network.__name__, deep_supervision=int(deep_supervision), **arrays, **sd_arrays(model))
 
 
 if __name__ == '__main__':
@@ -226,6 +233,9 @@ if __name__ == '__main__':
     gen_mo2d('mo2d_single_overlap', (2, 100, 150), (64, 80), 1, 'single', seed=51)
     gen_mo2d('mo2d_all_pad', (3, 40, 70), (64, 64), 0, 'all', seed=52, dtype='uint8')
     gen_mo2d('mo2d_first_holes', (2, 96, 96), (48, 48), 2, 'first', seed=53)
+    gen_mo2d('nested_single_overlap', (2, 100, 150), (64, 80), 1, 'single', seed=54, network=MultiOutputNestedUNet)
+    gen_mo2d('nested3l_ds_all', (2, 72, 90), (48, 64), 1, 'all', seed=55, network=MultiOutputNestedUNet_3Levels,
+             deep_supervision=True, dtype='uint8')
     if only:
         sys.exit(0)
     gen_unet('unet_single', (2, 70, 90), (32, 48), 1, 'single', False, seed=11)

@@ -225,10 +225,101 @@ def test_mo2d_predict_matches_reference_golden(name, precision, tmp_path):
         c0 += c
 
 
-def test_mo2d_nested_network_is_rejected(tmp_path):
-    from bio_image_unet_b200.multi_output_unet import Predict
+@pytest.mark.parametrize('name', ['nested_single_overlap', 'nested3l_ds_all'])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+def test_nested_predict_matches_reference_golden(name, precision, tmp_path):
+    """multi_output_unet.Predict with the reference's default network, the nested U-Net++ (and its 3-level variant
+    with deep supervision), against fixtures produced by the unmodified reference."""
+    from bio_image_unet_b200 import multi_output_unet as mo
+    from oracle import pipeline as opipe
+    g = _golden.load(name)
+    ckpt = str(tmp_path / 'model.pt')
+    torch.save({'state_dict': _golden.state_dict(g), 'n_filter': int(g['n_filter']), 'in_channels': 1,
+                'output_heads': MO2D_HEADS, 'deep_supervision': bool(int(g['deep_supervision']))}, ckpt)
+    p = mo.Predict(g['imgs'].copy(), ckpt, result_path=None, network=getattr(mo, str(g['network'])),
+                   max_patch_size=tuple(int(v) for v in g['max_patch']), batch_size=2,
+                   normalization_mode=str(g['norm_mode']), clip_threshold=tuple(float(v) for v in g['clip']),
+                   add_tile=int(g['add_tile']), show_progress=False, device='cuda:0', precision=precision,
+                   keep_intermediates=True)
+    assert tuple(p.patch_size) == tuple(g['patch_size']) and (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
+    assert np.array_equal(p.norm, g['norm']) and np.array_equal(p.patches, g['patches'])
+    tol = {'fp32': 2e-3, 'tf32': 1e-2, 'bf16': 8e-2}[precision]
+    info = opipe.mo2d_grid(g['imgs'].shape, tuple(int(v) for v in g['max_patch']), int(g['add_tile']))
+    c0 = 0
+    for k, cfg in MO2D_HEADS.items():
+        c = cfg['channels']
+        ref_rp = g[f'result_patches/{k}'].astype(np.float32)
+        scale = max(1.0, np.abs(ref_rp).max())
+        got_rp = p.result_patches[:, c0:c0 + c]
 
-    class MultiOutputNestedUNet:      # stands for the reference's default network class
-        pass
+        def close(a, b):      # same criteria as test_mo2d_predict_matches_reference_golden
+            err = np.abs(a - b)
+            if cfg['activation'] == 'sigmoid' and precision != 'fp32':
+                return np.quantile(err, 0.9) <= tol
+            return err.max() <= tol * scale
+        assert close(got_rp, ref_rp), (k, np.abs(got_rp - ref_rp).max(), scale)
+        st = opipe.mo2d_stitch(got_rp.astype(np.float16), c, g['imgs'].shape, info)
+        assert np.abs(p.result[k] - st).max() <= 1e-3 * scale, k
+        assert close(p.result[k], g[f'result/{k}']), k
+        c0 += c
+
+
+@pytest.mark.parametrize('depth', [4, 3])
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+def test_nested_nodes_match_oracle(depth, precision):
+    """Every node x{l}_{j} of the dense skip pathways (conv outputs written at channel offsets of the per-level
+    buffers, bilinear align_corners=True up-sampling) against the oracle, n_filter 16 so the tcgen05 kernels run."""
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.multi_output_unet import MultiOutputNestedUNet, MultiOutputNestedUNet_3Levels
+    from oracle import models as om
+    torch.manual_seed(depth)
+    heads = {'a': {'channels': 1, 'activation': 'sigmoid'}, 'b': {'channels': 2, 'activation': 'tanh'}}
+    nf = 16
+    cls = MultiOutputNestedUNet if depth == 4 else MultiOutputNestedUNet_3Levels
+    m = cls(1, heads, nf).eval()
+    sd = m.state_dict()
+    x = torch.rand(2, 1, 64, 96)
+    nodes = {}
+    with torch.no_grad():
+        ref = om.nested_forward(sd, x, heads, depth, collect=nodes)
+    eng = Engine('nested2d' if depth == 4 else 'nested2d_3l', sd, nf, 1,
+                 [(k, v['channels'], v['activation']) for k, v in heads.items()], precision=precision, device='cuda:0')
+    eng.plan(2, (64, 96))
+    eng.set_profile(True)
+    val, _ = eng.forward(x.cuda(), want_val=True, want_u8=False)
+    kinds, _ = eng.read_profile()
+    tol = {'fp32': 1e-4, 'tf32': 5e-3, 'bf16': 4e-2}[precision]
+    for l in range(depth + 1):
+        c = nf * 2 ** l
+        upw = 2 * c if l < depth else 0                      # the level's up-sampling slot comes first (net.cu)
+        ctot = upw + c * (depth - l + (0 if l == 0 else 1))
+        buf = eng.debug_activation(f'x{l}', ctot, l)[:, 0]   # (B, H_l, W_l, ctot) NHWC
+        for j in range(depth - l + 1):
+            if l == 0 and j == depth:
+                continue                                     # x0_{depth} feeds the fused heads only
+            want = nodes[f'x{l}_{j}'].permute(0, 2, 3, 1).numpy()
+            got = buf[..., upw + j * c:upw + (j + 1) * c]
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.abs(got - want).max() <= tol * scale * (1 + l + j), (l, j, np.abs(got - want).max(), scale)
+    got = val.cpu().numpy()
+    want = np.concatenate([ref[k].numpy() for k in heads], 1)
+    assert np.abs(got - want).max() <= tol * 4, np.abs(got - want).max()
+    assert precision == 'fp32' or not any(16 <= k < 32 for k in kinds), kinds   # no CUDA-core fallback
+    eng.close()
+
+
+def test_nested_module_eval_forward_and_dilation():
+    from bio_image_unet_b200.multi_output_unet import MultiOutputNestedUNet
+    from oracle import models as om
+    torch.manual_seed(5)
+    heads = {'seg': {'channels': 1, 'activation': 'sigmoid'}}
+    m = MultiOutputNestedUNet(1, heads, 8, deep_supervision=True, train_mode=False).eval()
+    m.precision = 'fp32'
+    x = torch.rand(1, 1, 32, 48)
+    with torch.no_grad():
+        ref = om.nested_forward(m.state_dict(), x, heads, 4, deep_supervision=True)
+        out = m.cuda()(x.cuda())
+    assert list(out.keys()) == ['seg'] and (out['seg'].cpu() - ref['seg']).abs().max() < 1e-4
+    d = MultiOutputNestedUNet(1, heads, 8, dilation=(1, 2, 1, 1, 1)).eval().cuda()
     with pytest.raises(NotImplementedError):
-        Predict(np.zeros((32, 32), dtype='uint16'), 'unused.pt', network=MultiOutputNestedUNet, device='cuda:0')
+        d(x.cuda())

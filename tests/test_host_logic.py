@@ -159,11 +159,13 @@ def test_state_dict_layouts_match_reference():
     from bio_image_unet_b200.siam_unet import Siam_UNet
     from bio_image_unet_b200.unet import AttentionUnet, Unet, Unet_v0
     from bio_image_unet_b200.unet3d import UNet3D
-    from bio_image_unet_b200.multi_output_unet import MultiOutputUnet
+    from bio_image_unet_b200.multi_output_unet import MultiOutputNestedUNet, MultiOutputNestedUNet_3Levels, MultiOutputUnet
     mo2d_heads = {'seg': {'channels': 1, 'activation': 'sigmoid'}, 'vec': {'channels': 2, 'activation': None},
                   'dist': {'channels': 1, 'activation': 'relu'}}
     cases = [('unet_single', Unet(n_filter=4), 136), ('siam_concat', Siam_UNet(4, 'concat'), 143),
              ('mo2d_all_pad', MultiOutputUnet(1, mo2d_heads, 4), 140),
+             ('nested_single_overlap', MultiOutputNestedUNet(1, mo2d_heads, 4), 216),
+             ('nested3l_ds_all', MultiOutputNestedUNet_3Levels(1, mo2d_heads, 4, deep_supervision=True), 158),
              ('attunet_single', AttentionUnet(n_filter=8), 220), ('unetv0_all', Unet_v0(n_filter=4), 143),
              ('siam_max', Siam_UNet(4, 'max'), 136), ('unet3d_overlap', UNet3D(n_filter=4), 106),
              ('mo3d_interp', MultiOutputUnet3D(1, _golden.MO3D_HEADS, 4, True), 125)]

@@ -131,3 +131,21 @@ def test_mo2d_pipeline_matches_reference(name):
         st = pipeline.mo2d_stitch(ref_rp, cfg['channels'], shape, stages['info'])
         assert st.dtype == np.float32 and np.array_equal(st, g[f'result/{k}'])
         assert np.abs(out[k] - g[f'result/{k}']).max() <= 2e-3 * max(1.0, np.abs(ref_rp).max())
+
+
+@pytest.mark.parametrize('name', ['nested_single_overlap', 'nested3l_ds_all'])
+def test_nested_pipeline_matches_reference(name):
+    """multi_output_unet.Predict with its default network, the nested U-Net++ (MultiOutputNestedUNet, and the 3-level
+    variant with deep supervision): the oracle's restatement of the dense skip pathways + bilinear up-sampling
+    against the reference's float16 result patches, and the stitched result."""
+    g = _golden.load(name)
+    stages = {}
+    out = pipeline.mo2d_predict(g['imgs'].copy(), _golden.state_dict(g), MO2D_HEADS, tuple(int(v) for v in g['max_patch']),
+                                2, str(g['norm_mode']), tuple(float(v) for v in g['clip']), int(g['add_tile']), stages,
+                                network=str(g['network']), deep_supervision=bool(int(g['deep_supervision'])))
+    assert np.array_equal(stages['norm'], g['norm']) and np.array_equal(stages['patches'], g['patches'])
+    for k, cfg in MO2D_HEADS.items():
+        rp, ref_rp = stages['result_patches'][k], g[f'result_patches/{k}']
+        assert rp.dtype == np.float16 and rp.shape == ref_rp.shape
+        assert np.abs(rp.astype(np.float32) - ref_rp.astype(np.float32)).max() <= 2e-3 * max(1.0, np.abs(ref_rp).max())
+        assert np.abs(out[k] - g[f'result/{k}']).max() <= 2e-3 * max(1.0, np.abs(ref_rp).max())

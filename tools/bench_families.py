@@ -3,7 +3,7 @@
 the C-ABI engine: tile pixels / voxels per second, TFLOP/s against the reference layer FLOP counts
 and the per-op CUDA-event breakdown. Development / evidence tool; the headline contract lives in bench.py.
 
-    python tools/bench_families.py [siam] [unet3d] [unet3d64] [mo3d] [attunet] [unet_tf32]
+    python tools/bench_families.py [siam] [unet3d] [unet3d64] [mo3d] [attunet] [unet] [unet_tf32] [nested]
 """
 import ctypes
 import json
@@ -18,7 +18,7 @@ from bio_image_unet_b200 import _lib  # noqa: E402
 from bio_image_unet_b200.engine import Engine  # noqa: E402
 
 NAMES = {0: 'first_conv', 1: 'conv', 2: 'conv+head', 3: 'up', 4: 'pool', 5: 'up_nearest', 6: 'max_join', 7: 'gate',
-         8: 'mul_psi'}
+         8: 'mul_psi', 9: 'xcorr', 10: 'up_trilinear', 11: 'up_bilinear'}
 
 
 def run(name, kind, module, spec, tile, batch, flop_per_px, precision='bf16', in_float=False, reps=5, prev=False):
@@ -86,6 +86,18 @@ def main():
     if 'unet' in which:      # cfg 2 network, forward only
         run('unet_nf32', 'unet2d', Unet(n_filter=32), dict(n_filter=32, in_channels=1, heads=[('', 1, 'sigmoid')]),
             (512, 512), 200, 367232)
+    if 'nested' in which:    # multi_output_unet.Predict's default network: U-Net++ (4 pools), n_filter 32, float32 patches
+        from bio_image_unet_b200.multi_output_unet import MultiOutputNestedUNet
+        nf, depth, flop = 32, 4, 0.0
+        for l in range(depth + 1):
+            c = nf << l
+            for j in range(depth - l + 1):
+                cin = (1 if l == 0 else c // 2) if j == 0 else (j + 2) * c
+                flop += 2 * 9 * (cin * c + c * c) / 4 ** l
+        flop += 2 * nf * 1
+        heads = {'seg': {'channels': 1, 'activation': 'sigmoid'}}
+        run('nested_unet_nf32', 'nested2d', MultiOutputNestedUNet(1, heads, nf),
+            dict(n_filter=nf, in_channels=1, heads=[('seg', 1, 'sigmoid')]), (512, 512), 48, flop, in_float=True)
     if 'unet_tf32' in which:
         run('unet_nf32', 'unet2d', Unet(n_filter=32), dict(n_filter=32, in_channels=1, heads=[('', 1, 'sigmoid')]),
             (512, 512), 100, 367232, precision='tf32')
