@@ -217,9 +217,9 @@ def main():
     value = mp_per_step * args.steps * world / (dev_ms / 1e3)
 
     # per-kernel timing of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events on the launching stream:
-    # one more profiled step whose per-op events are read back (reading them needs a sync, so it is its own step)
-    ses.predict_device(dev_pool[0:f])
-    torch.cuda.synchronize()
+    # every op of every timed forward was bracketed by events (biu_net_set_profile above); the ones of the LAST forward
+    # of the timed region are read back here, after the closing synchronize - i.e. at the sustained, power-capped
+    # clocks of the timed loop, not of a cold extra step
     fwd_per_step = int(np.ceil(f * tiles_per_frame / ses.tile_batch))
     _lib.check(lib.biu_net_profile_read(ses.engine.handle, 64, kinds, ms, ctypes.byref(n_ops)))
     tc_ms = sum(ms[i] for i in range(n_ops.value) if kinds[i] in (1, 2, 3))

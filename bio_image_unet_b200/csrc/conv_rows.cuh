@@ -22,8 +22,14 @@
 // ring sees RB+4 "virtual" output rows: two dummies on either side collect the unused partial rows of the halo
 // input rows and are only zeroed again. The folded weights of the layer stay resident in shared memory.
 // Warp roles: 0 = row (A) producer, 1 = TMEM alloc + MMA issuer (warp-uniform, see conv_halo.cuh), 2 = weight
-// loader, 4..11 = epilogue: warp w drains TMEM lane quarter w % 4 (32 pixels) and channel half (w - 4) / 4; all
-// eight warps work on the same output row, a slot is released by their eight arrivals.
+// loader, 4..19 = epilogue: warp w drains TMEM lane quarter w % 4 (32 pixels, ALL channels) of every fourth PAIR of
+// output rows (group (w - 4) / 4): four groups of four warps leapfrog over the row pairs, so one group's barrier wait /
+// TMEM drain / slot zeroing overlaps the other groups' arithmetic and stores. A slot is released by the four arrivals
+// of the group that drained it. Finished rows go through a per-warp, XOR-swizzled shared-memory tile and are written
+// back transposed: consecutive lanes cover the consecutive 16-byte pieces of a pixel, so a warp store writes whole
+// pixels (full 32-byte sectors, 512 contiguous bytes when the destination is dense) instead of 32 scattered 16-byte
+// pieces - the same fix that took up4 from 1.70 to 0.93 ms in conv_halo.cuh. The 1x1 heads need no cross-warp
+// combination any more (a thread holds all channels of its pixel).
 #pragma once
 #include "conv_halo.cuh"
 
@@ -31,7 +37,7 @@ namespace biu {
 
 constexpr int kRowsMaxASlots = 24;
 constexpr int kRowsMaxTSlots = 32;
-constexpr int kRowsThreads = 384;
+constexpr int kRowsThreads = 640;
 constexpr int kRowsPx = 130;                 // 128 pixels + 1 halo column on each side
 
 struct ConvRowsParams {
@@ -128,6 +134,61 @@ __device__ __forceinline__ void tmem_zero_hc(uint32_t taddr) {
                  : "memory");
   }
 }
+// CP consecutive fp32 columns (16 or 32) of this warp's 32 TMEM lanes
+template <int CP>
+__device__ __forceinline__ void tmem_ld_cp(uint32_t taddr, uint32_t (&r)[CP]) {
+  if (CP == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16 % CP]), "=r"(r[17 % CP]), "=r"(r[18 % CP]), "=r"(r[19 % CP]), "=r"(r[20 % CP]), "=r"(r[21 % CP]),
+          "=r"(r[22 % CP]), "=r"(r[23 % CP]), "=r"(r[24 % CP]), "=r"(r[25 % CP]), "=r"(r[26 % CP]), "=r"(r[27 % CP]),
+          "=r"(r[28 % CP]), "=r"(r[29 % CP]), "=r"(r[30 % CP]), "=r"(r[31 % CP])
+        : "r"(taddr)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+}
+template <int CP>
+__device__ __forceinline__ void tmem_ld_wait_cp(uint32_t (&a)[CP]) {
+  if (CP == 32) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(a[16 % CP]), "+r"(a[17 % CP]), "+r"(a[18 % CP]), "+r"(a[19 % CP]), "+r"(a[20 % CP]),
+                   "+r"(a[21 % CP]), "+r"(a[22 % CP]), "+r"(a[23 % CP]), "+r"(a[24 % CP]), "+r"(a[25 % CP]),
+                   "+r"(a[26 % CP]), "+r"(a[27 % CP]), "+r"(a[28 % CP]), "+r"(a[29 % CP]), "+r"(a[30 % CP]),
+                   "+r"(a[31 % CP])
+                 :
+                 : "memory");
+  } else {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+                 :
+                 : "memory");
+  }
+}
+template <int CP>
+__device__ __forceinline__ void tmem_zero_cp(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(z) : "memory");
+  if (CP == 32)
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr + 16u), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -152,202 +213,221 @@ __device__ __forceinline__ RowsItem rows_decode(const ConvRowsParams& p, int t) 
   return r;
 }
 
-// Epilogue of all work items for one warp. HC = channels per warp (cp / 2).
-template <int ESZ, int HC, int MODE, bool POOL>
+// Epilogue of all work items for one warp. CP = padded output channels (all of them are handled by this warp).
+template <int ESZ, int CP, int MODE, bool POOL>
 __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t tmem_base, uint64_t* t_full,
                                               uint64_t* t_empty, const float* s_scale, const float* s_shift,
-                                              const float* s_headw, float* s_part, int warp, int lane) {
+                                              const float* s_headw, uint8_t* stage, int warp, int lane) {
+  constexpr int PXB = CP * ESZ;                  // bytes of one output pixel
+  constexpr int NV = PXB / 16;                   // 16-byte pieces per pixel: 2, 4 or 8
+  constexpr int NW = PXB / 4;                    // 32-bit words per pixel
+  constexpr int PPI = 32 / NV;                   // pixels covered by one transposed warp store
   const int q = warp & 3;                        // TMEM lane quarter: pixels 32q .. 32q+31 of the strip
-  const int hsel = (warp - 4) >> 2;              // channel half
-  const int c0 = hsel * HC;                      // first channel of this warp
+  const int grp = (warp - 4) >> 2;               // this warp's row pairs: running pair count % 4 == grp
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  int ts = 0;                                    // ring slot / use parity of the item's first virtual output row
-  uint32_t tph = 0;
-  uint32_t carry[HC / 2 * (ESZ == 2 ? 1 : 2)];   // POOL: previous (even) row, already max-ed over the x pair
-  (void)carry;
+  const int lg_slots = p.t_slots == 32 ? 5 : 4;  // the ring has 512 / cp = 16 or 32 slots
+  int ts = 0;                                    // ring position (slot + t_slots * use parity) of the item's first virtual row
+  int gcnt = 0;                                  // number of row pairs of the earlier items, mod 4
+  // staging tile of this warp: [32 pixels][PXB bytes], 16-byte pieces XOR-swizzled so that both the per-pixel
+  // writes and the transposed reads are bank-conflict free
+  uint8_t* tile = stage + (size_t)(warp - 4) * (32 * PXB);
+  const int wr_swz = NV == 8 ? (lane & 7) : (NV == 4 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+  const int rd_piece = lane % NV, rd_px = lane / NV;
 
-  // Before anything accumulates: zero this warp's part of every slot and mark all slots empty (phase 0).
-  for (int sl = 0; sl < p.t_slots; ++sl) tmem_zero_hc<HC>(tmem_base + lane_addr + (uint32_t)(sl * p.cp + c0));
-  tmem_st_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0)
-    for (int sl = 0; sl < p.t_slots; ++sl) mbar_arrive(&t_empty[sl]);
+  // Before anything accumulates: zero every slot and mark all slots empty (phase 0) - group 0 does it for all.
+  if (grp == 0) {
+    for (int sl = 0; sl < p.t_slots; ++sl) tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP));
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int sl = 0; sl < p.t_slots; ++sl) mbar_arrive(&t_empty[sl]);
+  }
 
   for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
     const RowsItem it = rows_decode(p, t);
-    const int px = it.x0 + q * 32 + lane;
+    const int px0 = it.x0 + q * 32;              // first pixel of this warp's quarter
+    const int px = px0 + lane;
 #ifdef BIU_DBG_KNOBS
-    const bool col_ok = px < p.W && !(g_rows_dbg & 8);
+    const int npix = (g_rows_dbg & 8) ? 0 : min(32, p.W - px0);
 #else
-    const bool col_ok = px < p.W;
+    const int npix = min(32, p.W - px0);         // valid pixels of the quarter (<= 0: none)
 #endif
+    const bool col_ok = lane < npix;
     const long long plane_row0 = ((long long)it.b * p.D + it.z) * p.H + it.y0;
-    char* out_px = nullptr;
+    char* out_q = nullptr;                       // pixel px0 of the item's first output row
     if (MODE == EPI_CONV)
-      out_px = reinterpret_cast<char*>(p.out) + ((plane_row0 * p.W + px) * p.out_ctot + p.out_coff + c0) * ESZ;
+      out_q = reinterpret_cast<char*>(p.out) + ((plane_row0 * p.W + px0) * p.out_ctot + p.out_coff) * ESZ;
     const long long out_row_bytes = (long long)p.W * p.out_ctot * ESZ;
+    const int out_px_bytes = p.out_ctot * ESZ;
     char* pool_px = nullptr;
     long long pool_row_bytes = 0;
     if (POOL) {
       const long long prow0 = ((long long)it.b * p.D + it.z) * (p.H >> 1) + (it.y0 >> 1);
-      pool_px = reinterpret_cast<char*>(p.pool_out) + ((prow0 * (p.W >> 1) + (px >> 1)) * p.pool_ctot + p.pool_coff + c0) * ESZ;
+      pool_px = reinterpret_cast<char*>(p.pool_out) + ((prow0 * (p.W >> 1) + (px >> 1)) * p.pool_ctot + p.pool_coff) * ESZ;
       pool_row_bytes = (long long)(p.W >> 1) * p.pool_ctot * ESZ;
     }
     const int vrows = it.rows + 4;               // virtual output rows: 2 dummies, rows real ones, 2 dummies
-    // math + stores of real output row o from its accumulator
-    auto process = [&](const uint32_t (&e)[16], int o) {
-      float v[HC];
+
+    // BatchNorm + LeakyReLU of one drained row, packed in the storage format (bf16 pairs / tf32-rounded floats)
+    auto activate = [&](const uint32_t (&e)[CP], uint32_t (&w)[NW]) {
 #pragma unroll
-      for (int i4 = 0; i4 < HC / 4; ++i4) {
-        const float4 sc = reinterpret_cast<const float4*>(s_scale + c0)[i4];
-        const float4 sh = reinterpret_cast<const float4*>(s_shift + c0)[i4];
+      for (int i4 = 0; i4 < CP / 4; ++i4) {
+        const float4 sc = reinterpret_cast<const float4*>(s_scale)[i4];
+        const float4 sh = reinterpret_cast<const float4*>(s_shift)[i4];
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+        float a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a[k] = fmaf(__uint_as_float(e[4 * i4 + k]), scv[k], shv[k]);
+          a[k] = fmaxf(a[k], a[k] * p.slope);      // LeakyReLU for 0 <= slope <= 1
+        }
+        if (ESZ == 2) {
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(a[0], a[1]), b1 = __floats2bfloat162_rn(a[2], a[3]);
+          w[(2 * i4) % NW] = *reinterpret_cast<uint32_t*>(&b0);
+          w[(2 * i4 + 1) % NW] = *reinterpret_cast<uint32_t*>(&b1);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w[(4 * i4 + k) % NW] = __float_as_uint(round_tf32(a[k]));
+        }
+      }
+    };
+    // real output row o: through the staging tile, transposed, to global memory
+    auto emit = [&](const uint32_t (&w)[NW], int o) {
+      __syncwarp();                                // the previous row's transposed reads are done
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        *reinterpret_cast<uint4*>(tile + lane * PXB + ((j ^ wr_swz) << 4)) =
+            make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      __syncwarp();
+      char* orow = out_q + o * out_row_bytes + rd_piece * 16;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int pxi = i * PPI + rd_px;
+        const int swz = NV == 8 ? (pxi & 7) : (NV == 4 ? ((pxi >> 1) & 3) : ((pxi >> 2) & 1));
+        const uint4 v4 = *reinterpret_cast<const uint4*>(tile + pxi * PXB + ((rd_piece ^ swz) << 4));
+        if (pxi < npix) *reinterpret_cast<uint4*>(orow + (long long)pxi * out_px_bytes) = v4;
+      }
+    };
+    // 1x1 heads of real output row o (a thread holds every channel of its pixel)
+    auto heads = [&](uint32_t (&e)[CP], int o) {
+      float hacc[kMaxHead];
+#pragma unroll
+      for (int i4 = 0; i4 < CP / 4; ++i4) {          // activation in place
+        const float4 sc = reinterpret_cast<const float4*>(s_scale)[i4];
+        const float4 sh = reinterpret_cast<const float4*>(s_shift)[i4];
         const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int i = 4 * i4 + k;
-          float a = fmaf(__uint_as_float(e[i]), scv[k], shv[k]);
-          a = fmaxf(a, a * p.slope);               // LeakyReLU for 0 <= slope <= 1
+          float a = fmaf(__uint_as_float(e[4 * i4 + k]), scv[k], shv[k]);
+          a = fmaxf(a, a * p.slope);
           if (ESZ == 4) a = round_tf32(a);
-          v[i] = a;
+          e[4 * i4 + k] = __float_as_uint(a);
         }
       }
-      if (MODE == EPI_HEAD) {
-        float part[kMaxHead];
+#pragma unroll
+      for (int h = 0; h < kMaxHead; ++h) {
+        if (h >= p.head_n) break;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i4 = 0; i4 < CP / 4; ++i4) {
+          const float4 hw = reinterpret_cast<const float4*>(s_headw + h * CP)[i4];
+          s0 = fmaf(__uint_as_float(e[4 * i4]), hw.x, s0);
+          s1 = fmaf(__uint_as_float(e[4 * i4 + 1]), hw.y, s1);
+          s0 = fmaf(__uint_as_float(e[4 * i4 + 2]), hw.z, s0);
+          s1 = fmaf(__uint_as_float(e[4 * i4 + 3]), hw.w, s1);
+        }
+        hacc[h] = s0 + s1;
+      }
+      if (col_ok) {
+        const long long plane = (long long)p.D * p.H * p.W;
+        const long long sp = ((long long)it.z * p.H + it.y0 + o) * p.W + px;
 #pragma unroll
         for (int h = 0; h < kMaxHead; ++h) {
           if (h >= p.head_n) break;
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < HC; ++i) s = fmaf(v[i], s_headw[h * p.cp + c0 + i], s);
-          part[h] = s;
-        }
-        // channel halves are combined through shared memory (double-buffered by row parity, one named barrier of
-        // the two warps that share a lane quarter per row)
-        float* buf = s_part + ((o & 1) * 128 + q * 32 + lane) * kMaxHead;
-        if (hsel == 1) {
-#pragma unroll
-          for (int h = 0; h < kMaxHead; ++h) { if (h >= p.head_n) break; buf[h] = part[h]; }
-        }
-        named_bar_sync(1 + q, 64);
-        if (hsel == 0 && col_ok) {
-          const long long plane = (long long)p.D * p.H * p.W;
-          const long long sp = ((long long)it.z * p.H + it.y0 + o) * p.W + px;
-#pragma unroll
-          for (int h = 0; h < kMaxHead; ++h) {
-            if (h >= p.head_n) break;
-            const float val = apply_head_act(part[h] + buf[h] + __ldg(p.head_b + h), p.head_act[h]);
-            const long long o2 = ((long long)it.b * p.head_n + h) * plane + sp;
-            if (p.out_val) p.out_val[o2] = val;
-            if (p.out_u8) p.out_u8[o2] = (uint8_t)(val * 255.0f);     // unet/predict.py:200 truncating cast
-          }
-        }
-      } else if (ESZ == 2) {
-        uint32_t w[HC / 2];
-#pragma unroll
-        for (int i = 0; i < HC / 2; ++i) {
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          w[i] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        if (col_ok) {
-          uint4* d4 = reinterpret_cast<uint4*>(out_px + o * out_row_bytes);
-          d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-          if (HC == 16) d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-        if (POOL) {                                // MaxPool2d(2): x pairs are adjacent lanes, y pairs consecutive rows
-#pragma unroll
-          for (int i = 0; i < HC / 2; ++i) {
-            __nv_bfloat162 mx = *reinterpret_cast<__nv_bfloat162*>(&w[i]);
-            const uint32_t ot = __shfl_xor_sync(0xffffffffu, w[i], 1);
-            mx = __hmax2(mx, *reinterpret_cast<const __nv_bfloat162*>(&ot));
-            if (o & 1) {
-              mx = __hmax2(mx, *reinterpret_cast<__nv_bfloat162*>(&carry[i]));
-              w[i] = *reinterpret_cast<uint32_t*>(&mx);
-            } else {
-              carry[i] = *reinterpret_cast<uint32_t*>(&mx);
-            }
-          }
-          if ((o & 1) && col_ok && !(lane & 1)) {
-            uint4* d4 = reinterpret_cast<uint4*>(pool_px + (o >> 1) * pool_row_bytes);
-            d4[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            if (HC == 16) d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-          }
-        }
-      } else {
-        if (col_ok) {
-          float4* d4 = reinterpret_cast<float4*>(out_px + o * out_row_bytes);
-#pragma unroll
-          for (int i = 0; i < HC / 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-        if (POOL) {
-#pragma unroll
-          for (int i = 0; i < HC; ++i) {
-            float mx = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
-            if (o & 1) v[i] = fmaxf(mx, __uint_as_float(carry[i]));
-            else carry[i] = __float_as_uint(mx);
-          }
-          if ((o & 1) && col_ok && !(lane & 1)) {
-            float4* d4 = reinterpret_cast<float4*>(pool_px + (o >> 1) * pool_row_bytes);
-#pragma unroll
-            for (int i = 0; i < HC / 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
+          const float val = apply_head_act(hacc[h] + __ldg(p.head_b + h), p.head_act[h]);
+          const long long o2 = ((long long)it.b * p.head_n + h) * plane + sp;
+          if (p.out_val) p.out_val[o2] = val;
+          if (p.out_u8) p.out_u8[o2] = (uint8_t)(val * 255.0f);     // unet/predict.py:200 truncating cast
         }
       }
     };
-    // Virtual rows are handled in PAIRS (one barrier wait, one TMEM drain wait, one zero-store wait per two rows):
-    // wait until the later row has all its partial rows, drain both (real rows), zero both slots for their next
-    // users and release them; the drain of the next pair is issued before this pair is processed.
-    int sl = ts; uint32_t ph = tph;
+
+    // Virtual rows are handled in PAIRS (one barrier wait and one zero-store wait per two rows): wait until the later
+    // row has all its partial rows, drain both (real rows only), zero both slots for their next users and release
+    // them, then finish the arithmetic and the stores while the other groups are already at the next pairs.
     auto is_real = [&](int v) { return v >= 2 && v < it.rows + 2; };
-    auto fetch2 = [&](uint32_t (&e0)[16], uint32_t (&e1)[16], int v) {      // rows v, v+1 (v+1 may not exist)
+    const int npairs = (vrows + 1) >> 1;
+    for (int k = (grp - gcnt) & 3; k < npairs; k += 4) {
+      const int v = 2 * k;
       const bool two = v + 1 < vrows;
-      int s1 = sl + 1; uint32_t p1 = ph;
-      if (s1 == p.t_slots) { s1 = 0; p1 ^= 1; }
+      const int r0 = ts + v, r1 = r0 + 1;
+      const int sl = r0 & (p.t_slots - 1), s1 = r1 & (p.t_slots - 1);
+      const uint32_t ph = (uint32_t)(r0 >> lg_slots) & 1u, p1 = (uint32_t)(r1 >> lg_slots) & 1u;
       if (two) mbar_wait(&t_full[s1], p1, 0xA00 + s1);                       // rows complete in order
       else mbar_wait(&t_full[sl], ph, 0xA00 + sl);
       tc_fence_after();
+      const bool real0 = is_real(v), real1 = two && is_real(v + 1);
 #ifdef BIU_DBG_KNOBS
-      if (g_rows_dbg & 2) return;
+      const bool drain = !(g_rows_dbg & 2);
+#else
+      const bool drain = true;
 #endif
-      if (is_real(v)) tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(sl * p.cp + c0), e0);
-      if (two && is_real(v + 1)) tmem_ld_hc<HC>(tmem_base + lane_addr + (uint32_t)(s1 * p.cp + c0), e1);
-    };
-    auto release2 = [&](uint32_t (&e0)[16], uint32_t (&e1)[16], int v) {     // data in registers, slots zeroed + freed
-      const bool two = v + 1 < vrows;
-      int s1 = sl + 1; uint32_t p1 = ph;
-      if (s1 == p.t_slots) { s1 = 0; p1 ^= 1; }
-      if (is_real(v) || (two && is_real(v + 1))) {
-        asm volatile("tcgen05.wait::ld.sync.aligned;"
-                     : "+r"(e0[0]), "+r"(e0[1]), "+r"(e0[2]), "+r"(e0[3]), "+r"(e0[4]), "+r"(e0[5]), "+r"(e0[6]), "+r"(e0[7]),
-                       "+r"(e0[8]), "+r"(e0[9]), "+r"(e0[10]), "+r"(e0[11]), "+r"(e0[12]), "+r"(e0[13]), "+r"(e0[14]), "+r"(e0[15]),
-                       "+r"(e1[0]), "+r"(e1[1]), "+r"(e1[2]), "+r"(e1[3]), "+r"(e1[4]), "+r"(e1[5]), "+r"(e1[6]), "+r"(e1[7]),
-                       "+r"(e1[8]), "+r"(e1[9]), "+r"(e1[10]), "+r"(e1[11]), "+r"(e1[12]), "+r"(e1[13]), "+r"(e1[14]), "+r"(e1[15])
-                     :
-                     : "memory");
+      uint32_t acc[CP];
+      uint32_t w0[NW];
+      if (real0) {
+        if (drain) tmem_ld_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP), acc);
+        tmem_ld_wait_cp<CP>(acc);
+        if (MODE == EPI_HEAD) heads(acc, v - 2);
+        else activate(acc, w0);
       }
-      tmem_zero_hc<HC>(tmem_base + lane_addr + (uint32_t)(sl * p.cp + c0));
-      if (two) tmem_zero_hc<HC>(tmem_base + lane_addr + (uint32_t)(s1 * p.cp + c0));
+      if (real1) {
+        if (drain) tmem_ld_cp<CP>(tmem_base + lane_addr + (uint32_t)(s1 * CP), acc);
+        tmem_ld_wait_cp<CP>(acc);
+      }
+      tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP));
+      if (two) tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(s1 * CP));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&t_empty[sl]); if (two) mbar_arrive(&t_empty[s1]); }
-      if (two) { sl = s1; ph = p1; }
-      if (++sl == p.t_slots) { sl = 0; ph ^= 1; }
-    };
-    uint32_t ea[16], eb[16], ec[16], ed[16];
-    fetch2(ea, eb, 0);
-    for (int v = 0; v < vrows; v += 4) {
-      release2(ea, eb, v);
-      if (v + 2 < vrows) fetch2(ec, ed, v + 2);
-      if (is_real(v)) process(ea, v - 2);
-      if (v + 1 < vrows && is_real(v + 1)) process(eb, v - 1);
-      if (v + 2 >= vrows) break;
-      release2(ec, ed, v + 2);
-      if (v + 4 < vrows) fetch2(ea, eb, v + 4);
-      if (is_real(v + 2)) process(ec, v);
-      if (v + 3 < vrows && is_real(v + 3)) process(ed, v + 1);
+#ifdef BIU_DBG_KNOBS
+      if (g_rows_dbg & 64) continue;
+#endif
+      if (MODE == EPI_HEAD) {
+        if (real1) heads(acc, v - 1);
+      } else {
+        uint32_t w1[NW];
+        if (real1) activate(acc, w1);
+        if (real0) emit(w0, v - 2);
+        if (real1) emit(w1, v - 1);
+        if (POOL && real0 && real1) {              // MaxPool2d(2): x pairs are adjacent lanes, y pairs = this row pair
+          if (ESZ == 2) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+              __nv_bfloat162 mx = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w0[i]), *reinterpret_cast<__nv_bfloat162*>(&w1[i]));
+              const uint32_t mine = *reinterpret_cast<uint32_t*>(&mx);
+              const uint32_t ot = __shfl_xor_sync(0xffffffffu, mine, 1);
+              mx = __hmax2(mx, *reinterpret_cast<const __nv_bfloat162*>(&ot));
+              w0[i] = *reinterpret_cast<uint32_t*>(&mx);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+              const float mx = fmaxf(__uint_as_float(w0[i]), __uint_as_float(w1[i]));
+              w0[i] = __float_as_uint(fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)));
+            }
+          }
+          if (col_ok && !(lane & 1)) {
+            uint4* d4 = reinterpret_cast<uint4*>(pool_px + ((v - 2) >> 1) * pool_row_bytes);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) d4[j] = make_uint4(w0[4 * j], w0[4 * j + 1], w0[4 * j + 2], w0[4 * j + 3]);
+          }
+        }
+      }
     }
-    ts = sl; tph = ph;
+    ts = (ts + vrows) & (2 * p.t_slots - 1);
+    gcnt = (gcnt + npairs) & 3;
   }
 }
 
@@ -371,7 +451,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
   float* s_scale = reinterpret_cast<float*>(tail);
   float* s_shift = s_scale + p.cp;
   float* s_headw = s_shift + p.cp;                        // [head_n][cp]
-  float* s_part = s_headw + kMaxHead * p.cp;              // [2][128][kMaxHead]
+  uint8_t* stage = reinterpret_cast<uint8_t*>(s_headw + kMaxHead * p.cp);   // 16 warps x [32 px][cp * ESZ bytes]
   const uint32_t rb = p.row_bytes;
   const int nfold = 3 * p.cp;
 
@@ -383,7 +463,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     for (int i = 0; i < p.a_slots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.t_slots; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < p.t_slots; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     mbar_init(&w_full, 1);
     fence_mbar_init();
   }
@@ -515,16 +595,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
-#define BIU_REPI(HC, MODE, POOL) \
-    rows_epilogue<ESZ, HC, MODE, POOL>(p, tmem_base, t_full, t_empty, s_scale, s_shift, s_headw, s_part, warp, lane)
+#define BIU_REPI(CP, MODE, POOL) \
+    rows_epilogue<ESZ, CP, MODE, POOL>(p, tmem_base, t_full, t_empty, s_scale, s_shift, s_headw, stage, warp, lane)
     if (p.cp == 32) {
+      if (p.mode == EPI_HEAD) BIU_REPI(32, EPI_HEAD, false);
+      else if (p.pool_out != nullptr) BIU_REPI(32, EPI_CONV, true);
+      else BIU_REPI(32, EPI_CONV, false);
+    } else {
       if (p.mode == EPI_HEAD) BIU_REPI(16, EPI_HEAD, false);
       else if (p.pool_out != nullptr) BIU_REPI(16, EPI_CONV, true);
       else BIU_REPI(16, EPI_CONV, false);
-    } else {
-      if (p.mode == EPI_HEAD) BIU_REPI(8, EPI_HEAD, false);
-      else if (p.pool_out != nullptr) BIU_REPI(8, EPI_CONV, true);
-      else BIU_REPI(8, EPI_CONV, false);
     }
 #undef BIU_REPI
   }

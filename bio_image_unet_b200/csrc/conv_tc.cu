@@ -269,7 +269,6 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   if (a.n_total != 16 && a.n_total != 32) return pl;        // N of the folded MMA = 3 * Cout = 48 or 96
   if (a.W < 128) return pl;                                  // one MMA tile = 128 consecutive pixels of a row
   if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
-  if (a.mode == EPI_HEAD && a.kd == 1) return pl;            // measured: the 2D head block is faster on the halo-tile kernel
   if (a.pool_out != nullptr && (a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1))) return pl;
   const int ck = pick_ck(a.cin, a.esz);
   if (ck == 0) return pl;
@@ -278,7 +277,7 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   pl.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
   pl.a_chunk_bytes = ((uint32_t)(kRowsPx * rb) + 1023u) & ~1023u;
   pl.a_slot_bytes = (uint32_t)chunks * pl.a_chunk_bytes;
-  const int tail = (2 * a.n_total + kMaxHead * a.n_total + 2 * 128 * kMaxHead) * 4 + 64;
+  const int tail = (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * a.n_total * a.esz + 64;   // scale/shift/heads + staging tiles
   const int budget = 225 * 1024 - tail - 1024 - (int)(a.kd * 3 * chunks * pl.w_tile_bytes);
   int slots = budget / (int)pl.a_slot_bytes;
   if (slots > kRowsMaxASlots) slots = kRowsMaxASlots;

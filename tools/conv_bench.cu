@@ -79,7 +79,9 @@ int main(int argc, char** argv) {
   printf("%-24s", "layer (ms)");
   for (auto k : knob_names) printf("%11s", k);
   printf("%10s%10s\n", "TFLOP/s", "GB/s");
+  const bool rows_only = argc > 3 && argv[3][0] == 'r';
   for (const LayerCfg& L : layers) {
+    if (rows_only) break;
     printf("%-24s", L.name);
     float full = 0;
     for (size_t k = 0; k < sizeof(knobs) / sizeof(int); ++k) {
@@ -94,7 +96,7 @@ int main(int argc, char** argv) {
     printf("%10.1f%10.0f\n", fl / full / 1e9, bytes / full / 1e6);
     fflush(stdout);
   }
-  if (argc > 3) {  // mt sweep on the first two layers
+  if (argc > 3 && !rows_only) {  // mt sweep on the first two layers
     for (int mt : {8, 4, 2, 1}) {
       g_halo_force_mt = mt; g_halo_dbg = 0;
       for (int li : {0, 1, 2, 3, 8, 9})
@@ -112,7 +114,7 @@ int main(int argc, char** argv) {
     g_halo_dbg = 0; g_use_rows = 1;
     for (int li : {0, 1}) {
       printf("rows kernel %-24s", layers[li].name);
-      for (int k : {0, 8, 16, 4, 4 | 8, 4 | 16, 4 | 8 | 16 | 2}) {
+      for (int k : {0, 8, 64, 4, 64 | 4, 116}) {
         cudaMemcpyToSymbol(g_rows_dbg, &k, sizeof(int));
         printf("  dbg%d %.3f ms", k, time_layer(layers[li], tiles, in, wgt, scale, shift, out, reps));
       }
@@ -121,7 +123,7 @@ int main(int argc, char** argv) {
     int z = 0; cudaMemcpyToSymbol(g_rows_dbg, &z, sizeof(int));
     g_use_rows = 0;
   }
-  {  // cycle accounting of CTA 0
+  if (!rows_only) {  // cycle accounting of CTA 0
     const char* slot_names[12] = {"A: wait a_empty", "A: issue TMA", "B: wait b_empty", "MMA: wait acc_empty", "MMA: wait a_full",
                                   "MMA: wait b_full", "MMA: issue+commit", "-", "EPI(w4): wait acc_full", "EPI: tmem wait",
                                   "EPI: whole tile", "EPI: arrive"};
