@@ -535,31 +535,63 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
 #else
     const bool dbg_nomma = false;
 #endif
+    // This warp's own instruction stream is what bounds the narrow layers (6 MMAs per row: ~575 cycles of
+    // bookkeeping against 504 cycles of tensor work, tools/conv_bench.cu), so the per-row path is kept lean: barrier
+    // addresses computed once, ring positions as free-running counters (slot = counter & (slots - 1), parity =
+    // next bit), no re-derivation of shared-window addresses per barrier operation.
+    uint32_t bar_af, bar_ae, bar_tf, bar_te;
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_af) : "r"(smem_u32(a_full)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_ae) : "r"(smem_u32(a_empty)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_tf) : "r"(smem_u32(t_full)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_te) : "r"(smem_u32(t_empty)));
+    auto wait_bar = [&](uint32_t addr, uint32_t parity, uint32_t code) {
+      uint32_t ok;
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+      if (ok) return;
+      const long long t0 = clock64();
+      do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) {
+          atomicExch(&g_device_fault, code);
+          __threadfence_system();
+          asm volatile("trap;");
+        }
+      } while (!ok);
+    };
+    auto commit_bar = [&](uint32_t addr) {
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+    };
+    const uint32_t t_mask = (uint32_t)p.t_slots - 1u, t_lg = p.t_slots == 32 ? 5u : 4u, t_wrap = 2u * (uint32_t)p.t_slots - 1u;
+    const int a_slots = p.a_slots, kd = p.kd, chunks = p.cin_chunks;
+    const uint32_t cp = (uint32_t)p.cp;
     int as = 0;
     uint32_t aph = 0;
-    int es = 0; uint32_t eph = 0;                      // next virtual row whose slot has to be empty (zeroed)
-    int fs = 0;                                        // next virtual row to be completed (slot of input row i)
+    uint32_t er = 0;                                   // t ring: next virtual row whose slot has to be empty (zeroed)
+    uint32_t fr = 0;                                   // t ring: next virtual row to be completed (slot of input row i)
     auto wait_empty = [&]() {
-      mbar_wait(&t_empty[es], eph, 0xD00 + es);
-      if (++es == p.t_slots) { es = 0; eph ^= 1; }
+      wait_bar(bar_te + 8u * (er & t_mask), (er >> t_lg) & 1u, 0xD00);
+      er = (er + 1u) & t_wrap;
     };
     for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
-      const RowsItem it = rows_decode(p, t);
+      const int rblk = (t / p.strips) % p.rblocks;
+      const int rows = min(p.RB, p.H - rblk * p.RB);
       wait_empty();                                    // dummy rows v = 0, 1 of this item
       wait_empty();
-      for (int i = 0; i < it.rows + 2; ++i) {
+      for (int i = 0; i < rows + 2; ++i) {
         wait_empty();                                  // virtual row i + 2 receives its first partial row now
         tc_fence_after();
         // input row i accumulates into the slots of virtual rows i, i+1, i+2 (weights ordered dy = 2, 1, 0)
-        const int s0 = fs;
-        const int wrap = s0 + 3 - p.t_slots;           // > 0: that many slots continue at slot 0
-        const uint32_t tcol = tmem_base + (uint32_t)(s0 * p.cp);
-        for (int dz = 0; dz < p.kd; ++dz) {
-          mbar_wait(&a_full[as], aph, 0xE00 + as);
+        const uint32_t s0 = fr & t_mask;
+        const int wrap = (int)s0 + 3 - p.t_slots;      // > 0: that many slots continue at slot 0
+        const uint32_t tcol = tmem_base + s0 * cp;
+        for (int dz = 0; dz < kd; ++dz) {
+          wait_bar(bar_af + 8u * (uint32_t)as, aph, 0xE00 + as);
           tc_fence_after();
-          for (int ch = 0; ch < p.cin_chunks; ++ch) {
+          for (int ch = 0; ch < chunks; ++ch) {
             const uint64_t ad0 = a_desc0 + (uint64_t)(as * aslot_step + ch * achunk_step);
-            const uint64_t wd0 = w_desc0 + (uint64_t)((dz * 3 * p.cin_chunks + ch) * wtile_step);
+            const uint64_t wd0 = w_desc0 + (uint64_t)((dz * 3 * chunks + ch) * wtile_step);
             if (!dbg_nomma && elect_one()) {
               if (wrap <= 0) {
 #pragma unroll
@@ -581,17 +613,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
               }
             }
           }
-          if (elect_one()) tc_commit(&a_empty[as]);
-          if (++as == p.a_slots) { as = 0; aph ^= 1; }
+          if (elect_one()) commit_bar(bar_ae + 8u * (uint32_t)as);
+          if (++as == a_slots) { as = 0; aph ^= 1; }
         }
-        if (elect_one()) tc_commit(&t_full[fs]);       // virtual row i has all its partial rows
-        if (++fs == p.t_slots) fs = 0;
+        if (elect_one()) commit_bar(bar_tf + 8u * s0);   // virtual row i has all its partial rows
+        fr = (fr + 1u) & t_wrap;
       }
       // the two trailing dummy rows are complete as well
-      if (elect_one()) tc_commit(&t_full[fs]);
-      if (++fs == p.t_slots) fs = 0;
-      if (elect_one()) tc_commit(&t_full[fs]);
-      if (++fs == p.t_slots) fs = 0;
+      if (elect_one()) { commit_bar(bar_tf + 8u * (fr & t_mask)); commit_bar(bar_tf + 8u * ((fr + 1u) & t_mask)); }
+      fr = (fr + 2u) & t_wrap;
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
