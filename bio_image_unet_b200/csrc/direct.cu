@@ -175,93 +175,122 @@ __global__ void __launch_bounds__(256) first_conv1_kernel(FirstConvArgs a) {
   }
 }
 
-// 2D, single input channel, second generation: a warp walks down a strip of (32/G pixels) x kFcRows rows, lane =
-// (pixel x, channel group g of 8). The 72 weights of the group stay in registers for the whole kernel, the 3x3
-// window slides down the strip (3 new input values per output row, fetched one row ahead), u8 ->
-// float32(u8)/255 comes from a 256-entry shared LUT (exact division, unet/predict.py:192), and for every row the
-// warp's 16-byte stores cover one contiguous run of the NHWC buffer (full sectors, not 16 B pieces of 32 pixels).
+// 2D, single input channel, third generation: a block stages its input patch (8 warps x 32/G pixels wide, 64 rows,
+// 1-pixel halo) in shared memory as float32(u8)/255 (exact division, unet/predict.py:192), then every warp walks down
+// its strip, lane = (pixel x, channel group g of 8). The 72 weights of the group stay in registers for the whole
+// kernel, the 3x3 window slides down the strip (3 new values per output row from shared memory - the second
+// generation fetched them from global memory one row ahead and stalled on that latency), the arithmetic runs on
+// packed float pairs (FFMA2), and for every row the warp's 16-byte stores cover one contiguous run of the NHWC
+// buffer (full sectors, not 16 B pieces of 32 pixels).
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2)
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 constexpr int kFcRows = 64;
 template <typename TIN, typename TOUT, int G>
 __global__ void __launch_bounds__(256, 2) first_conv1_2d_kernel(FirstConvArgs a) {
-  __shared__ float lut[256];
+  constexpr int PXW = 32 / G;                   // pixels per warp row
+  constexpr int TX = 8 * PXW;                   // block tile: 8 warps side by side ...
+  constexpr int TY = G >= 4 ? kFcRows : kFcRows / 2;   // ... TY rows tall
+  constexpr int PITCH = TX + 2;
+  __shared__ float tile[(TY + 2) * PITCH];      // input patch with its 1-pixel halo, already float32(u8)/255
   __shared__ __align__(16) float s_sc[64], s_sh[64];
-  if (sizeof(TIN) == 1) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
   if (threadIdx.x < 64) {
     s_sc[threadIdx.x] = threadIdx.x < a.cout ? a.scale[threadIdx.x] : 0.f;
     s_sh[threadIdx.x] = threadIdx.x < a.cout ? a.shift[threadIdx.x] : 0.f;
   }
-  constexpr int PXW = 32 / G;                   // pixels per warp row
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int g = lane % G, lx = lane / G;
-  float w[9][8];
+  // weights, accumulators and the BatchNorm affine as float PAIRS: fma.rn.f32x2 (FFMA2 on sm_100) does two IEEE
+  // fp32 FMAs per issue slot; results are bit-identical to the scalar form
+  unsigned long long w2[9][4];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w[t][j] = (g * 8 + j) < a.cout ? __ldg(a.wgt + t * a.cout + g * 8 + j) : 0.f;
-  __syncthreads();
-  const int tiles_x = (a.W + PXW - 1) / PXW, tiles_y = (a.H + kFcRows - 1) / kFcRows;
+    for (int m = 0; m < 4; ++m) {
+      const float wa = (g * 8 + 2 * m) < a.cout ? __ldg(a.wgt + t * a.cout + g * 8 + 2 * m) : 0.f;
+      const float wb = (g * 8 + 2 * m + 1) < a.cout ? __ldg(a.wgt + t * a.cout + g * 8 + 2 * m + 1) : 0.f;
+      w2[t][m] = pack_f32x2(wa, wb);
+    }
+  const int tiles_x = (a.W + TX - 1) / TX, tiles_y = (a.H + TY - 1) / TY;
   const int total = a.B * tiles_y * tiles_x;
-  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const TIN* in = reinterpret_cast<const TIN*>(a.in);
   TOUT* out = reinterpret_cast<TOUT*>(a.out);
   const int W = a.W, H = a.H;
-  for (int tile = warp0; tile < total; tile += nwarps) {
-    int r = tile;
+  const unsigned long long slope2 = pack_f32x2(a.slope, a.slope);
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    int r = t;
     const int tx = r % tiles_x; r /= tiles_x;
     const int ty = r % tiles_y; r /= tiles_y;
-    const int x = tx * PXW + lx, y0 = ty * kFcRows;
-    const int y1 = min(y0 + kFcRows, H);
-    const bool c0 = x >= 1 && x - 1 < W, c1 = x < W, c2 = x + 1 < W;
-    const TIN* p = in + ((long long)r * H + y0) * W + x;          // input pixel (y0, x) of image r
-    auto cvt = [&](TIN raw) -> float { return sizeof(TIN) == 1 ? lut[(int)raw] : (float)raw; };
-    float v0[3] = {0.f, 0.f, 0.f}, v1[3], v2[3];
-    if (y0 > 0) {
-      v0[0] = c0 ? cvt(__ldg(p - W - 1)) : 0.f;
-      v0[1] = c1 ? cvt(__ldg(p - W)) : 0.f;
-      v0[2] = c2 ? cvt(__ldg(p - W + 1)) : 0.f;
+    const int x0 = tx * TX, y0 = ty * TY;
+    __syncthreads();                                                // the previous tile has been consumed
+    // the block stages its input patch once: coalesced loads, conversion (exact division, unet/predict.py:192) and
+    // zero padding happen here, so the row loop below has no global-memory latency on its critical path
+    const TIN* img = in + (long long)r * H * W;
+    for (int i = threadIdx.x; i < (TY + 2) * PITCH; i += 256) {
+      const int yy = i / PITCH, xx = i - yy * PITCH;
+      const int gy = y0 + yy - 1, gx = x0 + xx - 1;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const TIN raw = __ldg(img + (long long)gy * W + gx);
+        v = sizeof(TIN) == 1 ? __fdiv_rn((float)raw, 255.0f) : (float)raw;
+      }
+      tile[i] = v;
     }
-    v1[0] = c0 ? cvt(__ldg(p - 1)) : 0.f;
-    v1[1] = c1 ? cvt(__ldg(p)) : 0.f;
-    v1[2] = c2 ? cvt(__ldg(p + 1)) : 0.f;
-    TIN nraw[3] = {0, 0, 0};                                       // row y + 1, fetched one iteration ahead
-    bool nvalid = y0 + 1 < H;
-    if (nvalid) {
-      if (c0) nraw[0] = __ldg(p + W - 1);
-      if (c1) nraw[1] = __ldg(p + W);
-      if (c2) nraw[2] = __ldg(p + W + 1);
-    }
+    __syncthreads();
+    const int xl = wid * PXW + lx, x = x0 + xl;                     // this thread's pixel column
+    const int y1 = min(TY, H - y0);
+    const bool c1 = x < W;
+    const float* tp = tile + xl;                                     // tile[yy][xl + dx] = input (y0 + yy - 1, x + dx - 1)
+    float v0[3], v1[3], v2[3];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) { v0[dx] = tp[dx]; v1[dx] = tp[PITCH + dx]; }
     TOUT* o = out + (((long long)r * H + y0) * W + x) * a.out_ctot + a.out_coff + g * 8;
     const long long o_step = (long long)W * a.out_ctot;
-    for (int y = y0; y < y1; ++y, p += W, o += o_step) {
-      v2[0] = (nvalid && c0) ? cvt(nraw[0]) : 0.f;
-      v2[1] = (nvalid && c1) ? cvt(nraw[1]) : 0.f;
-      v2[2] = (nvalid && c2) ? cvt(nraw[2]) : 0.f;
-      nvalid = y + 2 < H;
-      if (nvalid) {
-        if (c0) nraw[0] = __ldg(p + 2 * W - 1);
-        if (c1) nraw[1] = __ldg(p + 2 * W);
-        if (c2) nraw[2] = __ldg(p + 2 * W + 1);
+    for (int y = 0; y < y1; ++y, o += o_step) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) v2[dx] = tp[(y + 2) * PITCH + dx];
+      unsigned long long acc2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const unsigned long long b0 = pack_f32x2(v0[dx], v0[dx]), b1 = pack_f32x2(v1[dx], v1[dx]),
+                                 b2 = pack_f32x2(v2[dx], v2[dx]);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          acc2[m] = fma_f32x2(b0, w2[dx][m], acc2[m]);
+          acc2[m] = fma_f32x2(b1, w2[3 + dx][m], acc2[m]);
+          acc2[m] = fma_f32x2(b2, w2[6 + dx][m], acc2[m]);
+        }
       }
+      const ulonglong2 sc01 = *reinterpret_cast<const ulonglong2*>(s_sc + g * 8), sc23 = *reinterpret_cast<const ulonglong2*>(s_sc + g * 8 + 4);
+      const ulonglong2 sh01 = *reinterpret_cast<const ulonglong2*>(s_sh + g * 8), sh23 = *reinterpret_cast<const ulonglong2*>(s_sh + g * 8 + 4);
+      const unsigned long long sc2[4] = {sc01.x, sc01.y, sc23.x, sc23.y}, sh2[4] = {sh01.x, sh01.y, sh23.x, sh23.y};
       float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[j] = fmaf(v0[dx], w[dx][j], acc[j]);
-          acc[j] = fmaf(v1[dx], w[3 + dx][j], acc[j]);
-          acc[j] = fmaf(v2[dx], w[6 + dx][j], acc[j]);
-        }
-      const float4 sc0 = *reinterpret_cast<const float4*>(s_sc + g * 8), sc1 = *reinterpret_cast<const float4*>(s_sc + g * 8 + 4);
-      const float4 sh0 = *reinterpret_cast<const float4*>(s_sh + g * 8), sh1 = *reinterpret_cast<const float4*>(s_sh + g * 8 + 4);
-      const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-      const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(acc[j], scv[j], shv[j]);
-        acc[j] = t > 0.f ? t : t * a.slope;
+      for (int m = 0; m < 4; ++m) {
+        const unsigned long long t2 = fma_f32x2(acc2[m], sc2[m], sh2[m]);
+        const unsigned long long u2 = mul_f32x2(t2, slope2);
+        float ta, tb, ua, ub;
+        unpack_f32x2(t2, ta, tb);
+        unpack_f32x2(u2, ua, ub);
+        acc[2 * m] = ta > 0.f ? ta : ua;             // LeakyReLU / ReLU: t > 0 ? t : t * slope
+        acc[2 * m + 1] = tb > 0.f ? tb : ub;
       }
       if (c1) {
         if (sizeof(TOUT) == 2) {
@@ -291,8 +320,8 @@ __global__ void __launch_bounds__(256, 2) first_conv1_2d_kernel(FirstConvArgs a)
 template <typename TIN, typename TOUT>
 static void launch_first_conv1_2d(const FirstConvArgs& a, cudaStream_t stream) {
   const int G = a.cout_pad / 8;
-  const long long tiles = (long long)a.B * ((a.H + kFcRows - 1) / kFcRows) * ((a.W + 32 / G - 1) / (32 / G));
-  long long blocks = ceil_div_ll(tiles, 8);      // 8 warps per block
+  const int ty = G >= 4 ? kFcRows : kFcRows / 2, tx = 8 * (32 / G);          // block tile (first_conv1_2d_kernel)
+  long long blocks = (long long)a.B * ((a.H + ty - 1) / ty) * ((a.W + tx - 1) / tx);
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   if (blocks < 1) blocks = 1;
   if (G == 1) first_conv1_2d_kernel<TIN, TOUT, 1><<<(int)blocks, 256, 0, stream>>>(a);
