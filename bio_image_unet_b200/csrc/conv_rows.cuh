@@ -51,6 +51,7 @@ struct ConvRowsParams {
   uint32_t a_slot_bytes, a_chunk_bytes;
   uint32_t w_tile_bytes;         // one folded weight tile [(dy, co)][ck]; kd * 3 * cin_chunks of them
   int t_slots;                   // TMEM ring: 512 / cp slots of cp columns (one per output row)
+  int pipes;                     // 1 or 2 independent pipelines (producer + MMA warp + epilogue groups) per CTA
   int mode;                      // EPI_CONV or EPI_HEAD
   float slope;
   const float* scale;
@@ -223,28 +224,33 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
   constexpr int NW = PXB / 4;                    // 32-bit words per pixel
   constexpr int PPI = 32 / NV;                   // pixels covered by one transposed warp store
   const int q = warp & 3;                        // TMEM lane quarter: pixels 32q .. 32q+31 of the strip
-  const int grp = (warp - 4) >> 2;               // this warp's row pairs: running pair count % 4 == grp
+  const int grp = (warp - 4) >> 2;               // 0..3
+  const int gpp = 4 / p.pipes;                   // epilogue groups per pipeline
+  const int pipe = grp / gpp, gi = grp - pipe * gpp;   // this warp's row pairs: running pair count % gpp == gi
+  const int tsl = p.t_slots / p.pipes;           // TMEM ring of this pipeline: slots [pipe * tsl, (pipe + 1) * tsl)
+  const int slot0 = pipe * tsl;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-  const int lg_slots = p.t_slots == 32 ? 5 : 4;  // the ring has 512 / cp = 16 or 32 slots
-  int ts = 0;                                    // ring position (slot + t_slots * use parity) of the item's first virtual row
-  int gcnt = 0;                                  // number of row pairs of the earlier items, mod 4
+  const int lg_slots = tsl == 32 ? 5 : (tsl == 16 ? 4 : 3);
+  int ts = 0;                                    // ring position (slot + tsl * use parity) of the item's first virtual row
+  int gcnt = 0;                                  // number of row pairs of the earlier items, mod gpp
   // staging tile of this warp: [32 pixels][PXB bytes], 16-byte pieces XOR-swizzled so that both the per-pixel
   // writes and the transposed reads are bank-conflict free
   uint8_t* tile = stage + (size_t)(warp - 4) * (32 * PXB);
   const int wr_swz = NV == 8 ? (lane & 7) : (NV == 4 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
   const int rd_piece = lane % NV, rd_px = lane / NV;
 
-  // Before anything accumulates: zero every slot and mark all slots empty (phase 0) - group 0 does it for all.
-  if (grp == 0) {
-    for (int sl = 0; sl < p.t_slots; ++sl) tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP));
+  // Before anything accumulates: zero every slot and mark all slots empty (phase 0) - the first group of a pipeline
+  // does it for the pipeline.
+  if (gi == 0) {
+    for (int sl = slot0; sl < slot0 + tsl; ++sl) tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP));
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int sl = 0; sl < p.t_slots; ++sl) mbar_arrive(&t_empty[sl]);
+      for (int sl = slot0; sl < slot0 + tsl; ++sl) mbar_arrive(&t_empty[sl]);
   }
 
-  for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+  for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += p.pipes * gridDim.x) {
     const RowsItem it = rows_decode(p, t);
     const int px0 = it.x0 + q * 32;              // first pixel of this warp's quarter
     const int px = px0 + lane;
@@ -358,11 +364,11 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     // them, then finish the arithmetic and the stores while the other groups are already at the next pairs.
     auto is_real = [&](int v) { return v >= 2 && v < it.rows + 2; };
     const int npairs = (vrows + 1) >> 1;
-    for (int k = (grp - gcnt) & 3; k < npairs; k += 4) {
+    for (int k = (gi - gcnt) & (gpp - 1); k < npairs; k += gpp) {
       const int v = 2 * k;
       const bool two = v + 1 < vrows;
       const int r0 = ts + v, r1 = r0 + 1;
-      const int sl = r0 & (p.t_slots - 1), s1 = r1 & (p.t_slots - 1);
+      const int sl = slot0 + (r0 & (tsl - 1)), s1 = slot0 + (r1 & (tsl - 1));
       const uint32_t ph = (uint32_t)(r0 >> lg_slots) & 1u, p1 = (uint32_t)(r1 >> lg_slots) & 1u;
       if (two) mbar_wait(&t_full[s1], p1, 0xA00 + s1);                       // rows complete in order
       else mbar_wait(&t_full[sl], ph, 0xA00 + sl);
@@ -426,8 +432,8 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
         }
       }
     }
-    ts = (ts + vrows) & (2 * p.t_slots - 1);
-    gcnt = (gcnt + npairs) & 3;
+    ts = (ts + vrows) & (2 * tsl - 1);
+    gcnt = (gcnt + npairs) & (gpp - 1);
   }
 }
 
@@ -476,6 +482,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // Two independent pipelines (p.pipes == 2) share the resident weights and the tensor core: pipeline 0 = producer
+  // warp 0 + MMA warp 1, pipeline 1 = producer warp 2 + MMA warp 3, each with its own half of the A ring, of the TMEM
+  // slot ring and of the epilogue groups, working on alternate items. While one MMA warp is busy with its barrier
+  // bookkeeping the other one's MMAs keep the tensor core fed (a single issuing warp spends about as long on the
+  // bookkeeping of a 6-MMA row as the tensor core on its MMAs, and the two do not overlap - tools/conv_bench.cu).
+  const int pipes = p.pipes;
+  const int asl = p.a_slots / pipes, tsl = p.t_slots / pipes;
   if (warp == 2) {
     // ============================ folded weights: loaded once, resident ============================
     if (elect_one()) {
@@ -489,40 +502,43 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
               : "memory");
     }
   }
-  if (warp == 0) {
+  if (warp == 0 || (warp == 2 && pipes == 2)) {
     // ================================== input row (A) producer ===================================
+    const int pipe = warp >> 1;
     if (elect_one()) {
       const uint32_t row_tx = (uint32_t)p.cin_chunks * (uint32_t)kRowsPx * rb;
+      const int a0 = pipe * asl;                                   // this pipeline's slots: [a0, a0 + asl)
       int as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+      for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += pipes * gridDim.x) {
         const RowsItem it = rows_decode(p, t);
         for (int i = 0; i < it.rows + 2; ++i)
           for (int dz = 0; dz < p.kd; ++dz) {
-            mbar_wait(&a_empty[as], aph ^ 1, 0xB00 + as);
+            mbar_wait(&a_empty[a0 + as], aph ^ 1, 0xB00 + as);
 #ifdef BIU_DBG_KNOBS
-            if (g_rows_dbg & 16) { mbar_arrive(&a_full[as]); if (++as == p.a_slots) { as = 0; aph ^= 1; } continue; }
+            if (g_rows_dbg & 16) { mbar_arrive(&a_full[a0 + as]); if (++as == asl) { as = 0; aph ^= 1; } continue; }
 #endif
-            mbar_arrive_expect_tx(&a_full[as], row_tx);
+            mbar_arrive_expect_tx(&a_full[a0 + as], row_tx);
             for (int ch = 0; ch < p.cin_chunks; ++ch)
               asm volatile(
                   "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-                  "%5, %6, %7}], [%2];" ::"r"(a_base + as * p.a_slot_bytes + ch * p.a_chunk_bytes),
-                  "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[as])), "r"(ch * p.ck), "r"(it.x0 - 1),
+                  "%5, %6, %7}], [%2];" ::"r"(a_base + (a0 + as) * p.a_slot_bytes + ch * p.a_chunk_bytes),
+                  "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[a0 + as])), "r"(ch * p.ck), "r"(it.x0 - 1),
                   "r"(it.y0 - 1 + i), "r"(it.z - (p.kd >> 1) + dz), "r"(it.b)
                   : "memory");
-            if (++as == p.a_slots) { as = 0; aph ^= 1; }
+            if (++as == asl) { as = 0; aph ^= 1; }
           }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 3 && pipes == 2)) {
     // ====================================== MMA issuer ======================================
+    const int pipe = warp >> 1;
     const uint32_t layout = rb == 128 ? 2u : (rb == 64 ? 4u : 6u);
     const uint32_t fmt = ESZ == 2 ? 1u : 2u;
     const uint32_t idesc3 = make_idesc(fmt, (uint32_t)(3 * p.cp));      // whole folded tile
     const uint32_t idesc2 = make_idesc(fmt, (uint32_t)(2 * p.cp));      // split MMAs where the three slots wrap
     const uint32_t idesc1 = make_idesc(fmt, (uint32_t)p.cp);
-    const uint64_t a_desc0 = make_smem_desc(a_base, 8u * rb, layout);
+    const uint64_t a_desc0 = make_smem_desc(a_base + (uint32_t)(pipe * asl) * p.a_slot_bytes, 8u * rb, layout);
     const uint64_t w_desc0 = make_smem_desc(smem_base, 8u * rb, layout);
     constexpr uint32_t px_step = 2u * KS;              // one pixel = row_bytes / 16
     const uint32_t aslot_step = p.a_slot_bytes >> 4, achunk_step = p.a_chunk_bytes >> 4, wtile_step = p.w_tile_bytes >> 4;
@@ -535,15 +551,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
 #else
     const bool dbg_nomma = false;
 #endif
-    // This warp's own instruction stream is what bounds the narrow layers (6 MMAs per row: ~575 cycles of
+    // This warp's own instruction stream is what bounds the narrow layers (6 MMAs per row: ~550 cycles of
     // bookkeeping against 504 cycles of tensor work, tools/conv_bench.cu), so the per-row path is kept lean: barrier
     // addresses computed once, ring positions as free-running counters (slot = counter & (slots - 1), parity =
     // next bit), no re-derivation of shared-window addresses per barrier operation.
     uint32_t bar_af, bar_ae, bar_tf, bar_te;
-    asm volatile("mov.u32 %0, %1;" : "=r"(bar_af) : "r"(smem_u32(a_full)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(bar_ae) : "r"(smem_u32(a_empty)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(bar_tf) : "r"(smem_u32(t_full)));
-    asm volatile("mov.u32 %0, %1;" : "=r"(bar_te) : "r"(smem_u32(t_empty)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_af) : "r"(smem_u32(a_full + pipe * asl)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_ae) : "r"(smem_u32(a_empty + pipe * asl)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_tf) : "r"(smem_u32(t_full + pipe * tsl)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(bar_te) : "r"(smem_u32(t_empty + pipe * tsl)));
     auto wait_bar = [&](uint32_t addr, uint32_t parity, uint32_t code) {
       uint32_t ok;
       asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
@@ -563,9 +579,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     auto commit_bar = [&](uint32_t addr) {
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
     };
-    const uint32_t t_mask = (uint32_t)p.t_slots - 1u, t_lg = p.t_slots == 32 ? 5u : 4u, t_wrap = 2u * (uint32_t)p.t_slots - 1u;
-    const int a_slots = p.a_slots, kd = p.kd, chunks = p.cin_chunks;
+    const uint32_t t_mask = (uint32_t)tsl - 1u, t_lg = tsl == 32 ? 5u : (tsl == 16 ? 4u : 3u), t_wrap = 2u * (uint32_t)tsl - 1u;
+    const int kd = p.kd, chunks = p.cin_chunks;
     const uint32_t cp = (uint32_t)p.cp;
+    const uint32_t tmem_pipe = tmem_base + (uint32_t)(pipe * tsl) * cp;   // this pipeline's slot 0
     int as = 0;
     uint32_t aph = 0;
     uint32_t er = 0;                                   // t ring: next virtual row whose slot has to be empty (zeroed)
@@ -574,7 +591,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
       wait_bar(bar_te + 8u * (er & t_mask), (er >> t_lg) & 1u, 0xD00);
       er = (er + 1u) & t_wrap;
     };
-    for (int t = blockIdx.x; t < p.total_items; t += gridDim.x) {
+    for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += pipes * gridDim.x) {
       const int rblk = (t / p.strips) % p.rblocks;
       const int rows = min(p.RB, p.H - rblk * p.RB);
       wait_empty();                                    // dummy rows v = 0, 1 of this item
@@ -584,8 +601,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
         tc_fence_after();
         // input row i accumulates into the slots of virtual rows i, i+1, i+2 (weights ordered dy = 2, 1, 0)
         const uint32_t s0 = fr & t_mask;
-        const int wrap = (int)s0 + 3 - p.t_slots;      // > 0: that many slots continue at slot 0
-        const uint32_t tcol = tmem_base + s0 * cp;
+        const int wrap = (int)s0 + 3 - tsl;            // > 0: that many slots continue at slot 0
+        const uint32_t tcol = tmem_pipe + s0 * cp;
         for (int dz = 0; dz < kd; ++dz) {
           wait_bar(bar_af + 8u * (uint32_t)as, aph, 0xE00 + as);
           tc_fence_after();
@@ -608,13 +625,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
 #pragma unroll
                   for (int k = 0; k < KS; ++k) {
                     tc_mma_imm<ESZ, 1>(tcol, ad0 + (dx * px_step + 2 * k), wd0 + (dx * wdx_step + 2 * k), n_lo);
-                    tc_mma_imm<ESZ, 1>(tmem_base, ad0 + (dx * px_step + 2 * k), wd0 + (w_hi + dx * wdx_step + 2 * k), n_hi);
+                    tc_mma_imm<ESZ, 1>(tmem_pipe, ad0 + (dx * px_step + 2 * k), wd0 + (w_hi + dx * wdx_step + 2 * k), n_hi);
                   }
               }
             }
           }
           if (elect_one()) commit_bar(bar_ae + 8u * (uint32_t)as);
-          if (++as == a_slots) { as = 0; aph ^= 1; }
+          if (++as == asl) { as = 0; aph ^= 1; }
         }
         if (elect_one()) commit_bar(bar_tf + 8u * s0);   // virtual row i has all its partial rows
         fr = (fr + 1u) & t_wrap;

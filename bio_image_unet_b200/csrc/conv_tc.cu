@@ -260,6 +260,12 @@ static bool rows_disabled() {
 
 struct RowsPlan { int ck, a_slots, t_slots, RB, smem; uint32_t a_slot_bytes, a_chunk_bytes, w_tile_bytes; bool ok; };
 
+static bool rows_single_pipe() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BIU_ROWS_SINGLE_PIPE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static RowsPlan plan_rows(const ConvTcArgs& a) {
   RowsPlan pl{};
   pl.ok = false;
@@ -305,6 +311,9 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
   p.cp = a.n_total;
   p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.a_chunk_bytes = pl.a_chunk_bytes;
+  // two pipelines per CTA when the A ring is deep enough to be halved and there is work for both
+  p.pipes = (pl.a_slots >= 8 && p.total_items >= 2 * sm_count_cached() && !rows_single_pipe()) ? 2 : 1;
+  if (p.pipes == 2) p.a_slots &= ~1;
   p.w_tile_bytes = pl.w_tile_bytes; p.t_slots = pl.t_slots;
   p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;
   p.out = a.out; p.out_ctot = a.out_ctot; p.out_coff = a.out_coff;
