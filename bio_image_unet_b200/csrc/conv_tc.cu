@@ -312,7 +312,9 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   p.cp = a.n_total;
   p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.a_chunk_bytes = pl.a_chunk_bytes;
   // two pipelines per CTA when the A ring is deep enough to be halved and there is work for both
-  p.pipes = (pl.a_slots >= 8 && p.total_items >= 2 * sm_count_cached() && !rows_single_pipe()) ? 2 : 1;
+  static int min_slots = -1;
+  if (min_slots < 0) { const char* e = getenv("BIU_ROWS_PIPE_MIN_SLOTS"); min_slots = e ? atoi(e) : 8; }
+  p.pipes = (pl.a_slots >= min_slots && p.total_items >= 2 * sm_count_cached() && !rows_single_pipe()) ? 2 : 1;
   if (p.pipes == 2) p.a_slots &= ~1;
   p.w_tile_bytes = pl.w_tile_bytes; p.t_slots = pl.t_slots;
   p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;

@@ -175,13 +175,6 @@ __global__ void __launch_bounds__(256) first_conv1_kernel(FirstConvArgs a) {
   }
 }
 
-// 2D, single input channel, third generation: a block stages its input patch (8 warps x 32/G pixels wide, 64 rows,
-// 1-pixel halo) in shared memory as float32(u8)/255 (exact division, unet/predict.py:192), then every warp walks down
-// its strip, lane = (pixel x, channel group g of 8). The 72 weights of the group stay in registers for the whole
-// kernel, the 3x3 window slides down the strip (3 new values per output row from shared memory - the second
-// generation fetched them from global memory one row ahead and stalled on that latency), the arithmetic runs on
-// packed float pairs (FFMA2), and for every row the warp's 16-byte stores cover one contiguous run of the NHWC
-// buffer (full sectors, not 16 B pieces of 32 pixels).
 // packed fp32 pairs (sm_100: FFMA2 / FMUL2)
 __device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
   unsigned long long r;
@@ -202,6 +195,192 @@ __device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, un
   return d;
 }
 
+// 3D, single input channel. A block owns a column of ZC planes of an (8 rows x 128 voxels) tile and slides along z:
+// four input planes (10 rows x 130 voxels with the halo, already float32(u8)/255 - exact division,
+// unet3d/predict.py:161) rotate through shared memory, the plane needed two steps ahead is fetched from global
+// memory while the current plane is computed (one __syncthreads per plane, no global latency and no bounds checks in
+// the arithmetic). A thread produces a run of XR = 4 consecutive voxels along x: the 3x3x3 windows of the run share
+// their inputs, a weight vector read from shared memory serves all four voxels, the arithmetic runs on packed float
+// pairs (FFMA2), channel groups that are pure padding (UNet3D's first block has n_filter / 2 = 8 real channels in a
+// 16-channel buffer) are written as zeros without any arithmetic, and a thread's stores cover XR * C_out contiguous
+// elements.
+constexpr int kFc3Rows = 8, kFc3Cols = 128, kFc3Pitch = 136, kFc3Planes = 4, kFc3ZC = 16;
+template <typename TIN, typename TOUT, int XR>
+__global__ void __launch_bounds__(256, 2) first_conv1_3d_kernel(FirstConvArgs a) {
+  extern __shared__ float sw[];  // [27][cout_pad], scale[cout_pad], shift[cout_pad]
+  __shared__ float lut[256];
+  __shared__ __align__(16) float tile[kFc3Planes * (kFc3Rows + 2) * kFc3Pitch];
+  float* s_scale = sw + 27 * a.cout_pad;
+  float* s_shift = s_scale + a.cout_pad;
+  for (int i = threadIdx.x; i < 27 * a.cout_pad; i += blockDim.x) {
+    const int co = i % a.cout_pad, k = i / a.cout_pad;
+    sw[i] = co < a.cout ? a.wgt[k * a.cout + co] : 0.f;
+  }
+  for (int i = threadIdx.x; i < a.cout_pad; i += blockDim.x) {
+    s_scale[i] = i < a.cout ? a.scale[i] : 0.f;
+    s_shift[i] = i < a.cout ? a.shift[i] : 0.f;
+  }
+  if (sizeof(TIN) == 1) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
+  __syncthreads();
+  constexpr int PLANE = (kFc3Rows + 2) * kFc3Pitch, NVAL = (kFc3Rows + 2) * (kFc3Cols + 2), NLD = (NVAL + 255) / 256;
+  const int tiles_x = (a.W + kFc3Cols - 1) / kFc3Cols, tiles_y = (a.H + kFc3Rows - 1) / kFc3Rows;
+  const int zchunks = (a.D + kFc3ZC - 1) / kFc3ZC;
+  const int ncols = a.B * zchunks * tiles_y * tiles_x;
+  const long long plane = (long long)a.D * a.H * a.W;
+  const int real_c = (a.cout + 7) & ~7;              // channels [real_c, cout_pad) are padding
+  const TIN* in = reinterpret_cast<const TIN*>(a.in);
+  TOUT* out = reinterpret_cast<TOUT*>(a.out);
+  const unsigned long long slope2 = pack_f32x2(a.slope, a.slope);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
+    int rem = col;
+    const int xt = (rem % tiles_x) * kFc3Cols; rem /= tiles_x;
+    const int yt = (rem % tiles_y) * kFc3Rows; rem /= tiles_y;
+    const int z0 = (rem % zchunks) * kFc3ZC; const int r = rem / zchunks;
+    const int z1 = min(z0 + kFc3ZC, a.D);
+    const TIN* img = in + r * plane;
+    // one input plane zz of the tile (rows yt-1 .. yt+8, voxels xt-1 .. xt+128), zero outside the volume
+    TIN stg[NLD];                                                  // raw values: converted only when they are stashed,
+    bool stg_ok[NLD];                                              // so the global loads stay in flight during the arithmetic
+    int g_off[NLD], s_off[NLD];                                    // z-invariant part of this thread's staging work
+    bool in_ok[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = threadIdx.x + k * 256;
+      const int ry = i / (kFc3Cols + 2), rx = i - ry * (kFc3Cols + 2);
+      const int yy = yt - 1 + ry, xx = xt - 1 + rx;
+      in_ok[k] = i < NVAL && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+      g_off[k] = yy * a.W + xx;
+      s_off[k] = i < NVAL ? ry * kFc3Pitch + 3 + rx : -1;         // voxel xt - 4 + j lives at index j
+    }
+    const int hw = a.H * a.W;
+    auto fetch = [&](int zz) {
+      const bool z_ok = zz >= 0 && zz < a.D;
+      const TIN* pz = img + (long long)zz * hw;
+#pragma unroll
+      for (int k = 0; k < NLD; ++k) {
+        stg_ok[k] = z_ok && in_ok[k];
+        stg[k] = 0;
+        if (stg_ok[k]) stg[k] = __ldg(pz + g_off[k]);
+      }
+    };
+    auto stash = [&](int zz) {
+      float* pl = tile + ((zz + kFc3Planes) % kFc3Planes) * PLANE;
+#pragma unroll
+      for (int k = 0; k < NLD; ++k) {
+        float t = 0.f;
+        if (stg_ok[k]) t = sizeof(TIN) == 1 ? lut[(int)stg[k]] : (float)stg[k];
+        if (s_off[k] >= 0) pl[s_off[k]] = t;
+      }
+    };
+    __syncthreads();                                               // the previous column's planes are consumed
+    for (int zz = z0 - 1; zz <= z0 + 1; ++zz) { fetch(zz); stash(zz); }
+    __syncthreads();
+    const int y = yt + wid, x0 = xt + XR * lane;
+    const bool active = y < a.H && x0 < a.W;
+    for (int z = z0; z < z1; ++z) {
+      const bool more = z + 1 < z1;
+      if (more) fetch(z + 2);                                      // in flight while this plane is computed
+      if (active) {
+        float v[3][3][XR + 2];
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+          const float* pl = tile + ((z + dz - 1 + kFc3Planes) % kFc3Planes) * PLANE + (wid * kFc3Pitch + XR * lane);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const float* rowp = pl + dy * kFc3Pitch;
+            const float4 mid = *reinterpret_cast<const float4*>(rowp + 4);
+            v[dz][dy][0] = rowp[3];
+            v[dz][dy][1] = mid.x; v[dz][dy][2] = mid.y; v[dz][dy][3] = mid.z; v[dz][dy][4] = mid.w;
+            v[dz][dy][5] = rowp[8];
+          }
+        }
+        TOUT* o = out + ((r * plane + ((long long)z * a.H + y) * a.W + x0) * a.out_ctot + a.out_coff);
+    for (int g = 0; g < a.cout_pad; g += 8) {
+      if (g >= real_c) {
+#pragma unroll
+        for (int xi = 0; xi < XR; ++xi) {
+          if (x0 + xi >= a.W) break;
+          TOUT* ov = o + (long long)xi * a.out_ctot + g;
+          if (sizeof(TOUT) == 2) *reinterpret_cast<uint4*>(ov) = make_uint4(0, 0, 0, 0);
+          else { *reinterpret_cast<float4*>(ov) = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(reinterpret_cast<float*>(ov) + 4) = make_float4(0.f, 0.f, 0.f, 0.f); }
+        }
+        continue;
+      }
+      unsigned long long acc2[XR][4];
+#pragma unroll
+      for (int xi = 0; xi < XR; ++xi)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc2[xi][m] = 0ull;
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int t = (dz * 3 + dy) * 3 + dx;
+            const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(sw + t * a.cout_pad + g);
+            const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(sw + t * a.cout_pad + g + 4);
+#pragma unroll
+            for (int xi = 0; xi < XR; ++xi) {
+              const unsigned long long b = pack_f32x2(v[dz][dy][xi + dx], v[dz][dy][xi + dx]);
+              acc2[xi][0] = fma_f32x2(b, w01.x, acc2[xi][0]);
+              acc2[xi][1] = fma_f32x2(b, w01.y, acc2[xi][1]);
+              acc2[xi][2] = fma_f32x2(b, w23.x, acc2[xi][2]);
+              acc2[xi][3] = fma_f32x2(b, w23.y, acc2[xi][3]);
+            }
+          }
+      const ulonglong2 sc01 = *reinterpret_cast<const ulonglong2*>(s_scale + g), sc23 = *reinterpret_cast<const ulonglong2*>(s_scale + g + 4);
+      const ulonglong2 sh01 = *reinterpret_cast<const ulonglong2*>(s_shift + g), sh23 = *reinterpret_cast<const ulonglong2*>(s_shift + g + 4);
+      const unsigned long long sc2[4] = {sc01.x, sc01.y, sc23.x, sc23.y}, sh2[4] = {sh01.x, sh01.y, sh23.x, sh23.y};
+#pragma unroll
+      for (int xi = 0; xi < XR; ++xi) {
+        if (x0 + xi >= a.W) break;
+        float acc[8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const unsigned long long t2 = fma_f32x2(acc2[xi][m], sc2[m], sh2[m]);
+          const unsigned long long u2 = mul_f32x2(t2, slope2);
+          float ta, tb, ua, ub;
+          unpack_f32x2(t2, ta, tb);
+          unpack_f32x2(u2, ua, ub);
+          acc[2 * m] = ta > 0.f ? ta : ua;
+          acc[2 * m + 1] = tb > 0.f ? tb : ub;
+        }
+        TOUT* ov = o + (long long)xi * a.out_ctot + g;
+        if (sizeof(TOUT) == 2) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          *reinterpret_cast<uint4*>(ov) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+          float* of = reinterpret_cast<float*>(ov);
+          if (a.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = to_tf32(acc[j]);
+          }
+          *reinterpret_cast<float4*>(of) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(of + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+      }
+    }
+      }                                                            // active
+      if (more) stash(z + 2);
+      __syncthreads();
+    }
+  }
+}
+
+// 2D, single input channel, third generation: a block stages its input patch (8 warps x 32/G pixels wide, 64 rows,
+// 1-pixel halo) in shared memory as float32(u8)/255 (exact division, unet/predict.py:192), then every warp walks down
+// its strip, lane = (pixel x, channel group g of 8). The 72 weights of the group stay in registers for the whole
+// kernel, the 3x3 window slides down the strip (3 new values per output row from shared memory - the second
+// generation fetched them from global memory one row ahead and stalled on that latency), the arithmetic runs on
+// packed float pairs (FFMA2), and for every row the warp's 16-byte stores cover one contiguous run of the NHWC
+// buffer (full sectors, not 16 B pieces of 32 pixels).
 constexpr int kFcRows = 64;
 template <typename TIN, typename TOUT, int G>
 __global__ void __launch_bounds__(256, 2) first_conv1_2d_kernel(FirstConvArgs a) {
@@ -359,10 +538,14 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
     long long fb = ceil_div_ll((long long)a.B * a.D * a.H * a.W, 256);
     if (fb > 148LL * 16) fb = 148LL * 16;
     if (fb < 1) fb = 1;
+    long long rb3 = (long long)a.B * ((a.D + kFc3ZC - 1) / kFc3ZC) * ((a.H + kFc3Rows - 1) / kFc3Rows) *
+                    ((a.W + kFc3Cols - 1) / kFc3Cols);                                 // tile columns (3D kernel)
+    if (rb3 > 148LL * 2) rb3 = 148LL * 2;
+    if (rb3 < 1) rb3 = 1;
 #define BIU_FC1(TIN, TOUT)                                                                               \
   do {                                                                                                   \
     if (a.kd == 1) first_conv1_kernel<TIN, TOUT, 9><<<(int)fb, 256, smem, stream>>>(a);                  \
-    else first_conv1_kernel<TIN, TOUT, 27><<<(int)fb, 256, smem, stream>>>(a);                           \
+    else first_conv1_3d_kernel<TIN, TOUT, 4><<<(int)rb3, 256, smem, stream>>>(a);                        \
   } while (0)
     if (a.in_kind == 0 && a.esz == 2) BIU_FC1(uint8_t, __nv_bfloat16);
     else if (a.in_kind == 0 && a.esz == 4) BIU_FC1(uint8_t, float);
