@@ -220,9 +220,12 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
                                               uint64_t* t_empty, const float* s_scale, const float* s_shift,
                                               const float* s_headw, uint8_t* stage, int warp, int lane) {
   constexpr int PXB = CP * ESZ;                  // bytes of one output pixel
-  constexpr int NV = PXB / 16;                   // 16-byte pieces per pixel: 2, 4 or 8
   constexpr int NW = PXB / 4;                    // 32-bit words per pixel
-  constexpr int PPI = 32 / NV;                   // pixels covered by one transposed warp store
+  constexpr int NV = PXB / 16;                   // 16-byte pieces per pixel: 2, 4 or 8
+  constexpr int SB = PXB < 64 ? PXB : 64;        // bytes of a pixel staged per pass (128-byte pixels go in two passes)
+  constexpr int SV = SB / 16;                    // 16-byte pieces per pixel and pass: 2 or 4
+  constexpr int PASSES = PXB / SB;
+  constexpr int PPI = 32 / SV;                   // pixels covered by one transposed warp store
   const int q = warp & 3;                        // TMEM lane quarter: pixels 32q .. 32q+31 of the strip
   const int grp = (warp - 4) >> 2;               // 0..3
   const int gpp = 4 / p.pipes;                   // epilogue groups per pipeline
@@ -233,11 +236,11 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
   const int lg_slots = tsl == 32 ? 5 : (tsl == 16 ? 4 : 3);
   int ts = 0;                                    // ring position (slot + tsl * use parity) of the item's first virtual row
   int gcnt = 0;                                  // number of row pairs of the earlier items, mod gpp
-  // staging tile of this warp: [32 pixels][PXB bytes], 16-byte pieces XOR-swizzled so that both the per-pixel
-  // writes and the transposed reads are bank-conflict free
-  uint8_t* tile = stage + (size_t)(warp - 4) * (32 * PXB);
-  const int wr_swz = NV == 8 ? (lane & 7) : (NV == 4 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
-  const int rd_piece = lane % NV, rd_px = lane / NV;
+  // staging tile of this warp: [32 pixels][SB bytes], 16-byte pieces XOR-swizzled so that both the per-pixel writes
+  // and the transposed reads are bank-conflict free
+  uint8_t* tile = stage + (size_t)(warp - 4) * (32 * SB);
+  const int wr_swz = SV == 4 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+  const int rd_piece = lane % SV, rd_px = lane / SV;
 
   // Before anything accumulates: zero every slot and mark all slots empty (phase 0) - the first group of a pipeline
   // does it for the pipeline.
@@ -300,19 +303,22 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     };
     // real output row o: through the staging tile, transposed, to global memory
     auto emit = [&](const uint32_t (&w)[NW], int o) {
-      __syncwarp();                                // the previous row's transposed reads are done
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        *reinterpret_cast<uint4*>(tile + lane * PXB + ((j ^ wr_swz) << 4)) =
-            make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-      __syncwarp();
-      char* orow = out_q + o * out_row_bytes + rd_piece * 16;
+      for (int h = 0; h < PASSES; ++h) {
+        __syncwarp();                              // the previous transposed reads are done
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int pxi = i * PPI + rd_px;
-        const int swz = NV == 8 ? (pxi & 7) : (NV == 4 ? ((pxi >> 1) & 3) : ((pxi >> 2) & 1));
-        const uint4 v4 = *reinterpret_cast<const uint4*>(tile + pxi * PXB + ((rd_piece ^ swz) << 4));
-        if (pxi < npix) *reinterpret_cast<uint4*>(orow + (long long)pxi * out_px_bytes) = v4;
+        for (int j = 0; j < SV; ++j)
+          *reinterpret_cast<uint4*>(tile + lane * SB + ((j ^ wr_swz) << 4)) =
+              make_uint4(w[4 * (h * SV + j)], w[4 * (h * SV + j) + 1], w[4 * (h * SV + j) + 2], w[4 * (h * SV + j) + 3]);
+        __syncwarp();
+        char* orow = out_q + o * out_row_bytes + (h * SV + rd_piece) * 16;
+#pragma unroll
+        for (int i = 0; i < SV; ++i) {
+          const int pxi = i * PPI + rd_px;
+          const int swz = SV == 4 ? ((pxi >> 1) & 3) : ((pxi >> 2) & 1);
+          const uint4 v4 = *reinterpret_cast<const uint4*>(tile + pxi * SB + ((rd_piece ^ swz) << 4));
+          if (pxi < npix) *reinterpret_cast<uint4*>(orow + (long long)pxi * out_px_bytes) = v4;
+        }
       }
     };
     // 1x1 heads of real output row o (a thread holds every channel of its pixel)
@@ -404,9 +410,8 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
         if (real1) heads(acc, v - 1);
       } else {
         uint32_t w1[NW];
-        if (real1) activate(acc, w1);
-        if (real0) emit(w0, v - 2);
-        if (real1) emit(w1, v - 1);
+        if (real0) emit(w0, v - 2);                // before row 1 is activated: keeps the live registers at two rows
+        if (real1) { activate(acc, w1); emit(w1, v - 1); }
         if (POOL && real0 && real1) {              // MaxPool2d(2): x pairs are adjacent lanes, y pairs = this row pair
           if (ESZ == 2) {
 #pragma unroll
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
   float* s_scale = reinterpret_cast<float*>(tail);
   float* s_shift = s_scale + p.cp;
   float* s_headw = s_shift + p.cp;                        // [head_n][cp]
-  uint8_t* stage = reinterpret_cast<uint8_t*>(s_headw + kMaxHead * p.cp);   // 16 warps x [32 px][cp * ESZ bytes]
+  uint8_t* stage = reinterpret_cast<uint8_t*>(s_headw + kMaxHead * p.cp);   // 16 warps x [32 px][min(cp * ESZ, 64) bytes]
   const uint32_t rb = p.row_bytes;
   const int nfold = 3 * p.cp;
 

@@ -283,7 +283,8 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   pl.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
   pl.a_chunk_bytes = ((uint32_t)(kRowsPx * rb) + 1023u) & ~1023u;
   pl.a_slot_bytes = (uint32_t)chunks * pl.a_chunk_bytes;
-  const int tail = (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * a.n_total * a.esz + 64;   // scale/shift/heads + staging tiles
+  const int px_bytes = a.n_total * a.esz;
+  const int tail = (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * (px_bytes < 64 ? px_bytes : 64) + 64;   // scale/shift/heads + staging tiles
   const int budget = 225 * 1024 - tail - 1024 - (int)(a.kd * 3 * chunks * pl.w_tile_bytes);
   int slots = budget / (int)pl.a_slot_bytes;
   if (slots > kRowsMaxASlots) slots = kRowsMaxASlots;
