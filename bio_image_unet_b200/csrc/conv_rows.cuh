@@ -182,13 +182,11 @@ __device__ __forceinline__ void tmem_ld_wait_cp(uint32_t (&a)[CP]) {
 template <int CP>
 __device__ __forceinline__ void tmem_zero_cp(uint32_t taddr) {
   const uint32_t z = 0;
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-      ::"r"(taddr), "r"(z) : "memory");
-  if (CP == 32)
+#pragma unroll
+  for (int c = 0; c < CP; c += 16)
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-        ::"r"(taddr + 16u), "r"(z) : "memory");
+        ::"r"(taddr + (uint32_t)c), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -220,6 +218,8 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
                                               uint64_t* t_empty, const float* s_scale, const float* s_shift,
                                               const float* s_headw, uint8_t* stage, int warp, int lane) {
   constexpr int PXB = CP * ESZ;                  // bytes of one output pixel
+  constexpr int HC = CP > 32 ? 32 : CP;          // TMEM columns per drain (64-channel rows are drained in two halves)
+  constexpr int NH = CP / HC;
   constexpr int NW = PXB / 4;                    // 32-bit words per pixel
   constexpr int NV = PXB / 16;                   // 16-byte pieces per pixel: 2, 4 or 8
   constexpr int SB = PXB < 64 ? PXB : 64;        // bytes of a pixel staged per pass (128-byte pixels go in two passes)
@@ -279,11 +279,12 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     const int vrows = it.rows + 4;               // virtual output rows: 2 dummies, rows real ones, 2 dummies
 
     // BatchNorm + LeakyReLU of one drained row, packed in the storage format (bf16 pairs / tf32-rounded floats)
-    auto activate = [&](const uint32_t (&e)[CP], uint32_t (&w)[NW]) {
+    auto activate = [&](const uint32_t (&e)[HC], uint32_t (&w)[NW], int hh) {     // channels hh * HC .. hh * HC + HC - 1
+      constexpr int NWH = HC * ESZ / 4;
 #pragma unroll
-      for (int i4 = 0; i4 < CP / 4; ++i4) {
-        const float4 sc = reinterpret_cast<const float4*>(s_scale)[i4];
-        const float4 sh = reinterpret_cast<const float4*>(s_shift)[i4];
+      for (int i4 = 0; i4 < HC / 4; ++i4) {
+        const float4 sc = reinterpret_cast<const float4*>(s_scale + hh * HC)[i4];
+        const float4 sh = reinterpret_cast<const float4*>(s_shift + hh * HC)[i4];
         const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
         float a[4];
 #pragma unroll
@@ -293,11 +294,11 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
         }
         if (ESZ == 2) {
           __nv_bfloat162 b0 = __floats2bfloat162_rn(a[0], a[1]), b1 = __floats2bfloat162_rn(a[2], a[3]);
-          w[(2 * i4) % NW] = *reinterpret_cast<uint32_t*>(&b0);
-          w[(2 * i4 + 1) % NW] = *reinterpret_cast<uint32_t*>(&b1);
+          w[(hh * NWH + 2 * i4) % NW] = *reinterpret_cast<uint32_t*>(&b0);
+          w[(hh * NWH + 2 * i4 + 1) % NW] = *reinterpret_cast<uint32_t*>(&b1);
         } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) w[(4 * i4 + k) % NW] = __float_as_uint(round_tf32(a[k]));
+          for (int k = 0; k < 4; ++k) w[(hh * NWH + 4 * i4 + k) % NW] = __float_as_uint(round_tf32(a[k]));
         }
       }
     };
@@ -322,10 +323,10 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
       }
     };
     // 1x1 heads of real output row o (a thread holds every channel of its pixel)
-    auto heads = [&](uint32_t (&e)[CP], int o) {
+    auto heads = [&](uint32_t (&e)[HC], int o) {     // MODE == EPI_HEAD is only instantiated for CP <= 32 (HC == CP)
       float hacc[kMaxHead];
 #pragma unroll
-      for (int i4 = 0; i4 < CP / 4; ++i4) {          // activation in place
+      for (int i4 = 0; i4 < HC / 4; ++i4) {          // activation in place
         const float4 sc = reinterpret_cast<const float4*>(s_scale)[i4];
         const float4 sh = reinterpret_cast<const float4*>(s_shift)[i4];
         const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
@@ -342,7 +343,7 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
         if (h >= p.head_n) break;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int i4 = 0; i4 < CP / 4; ++i4) {
+        for (int i4 = 0; i4 < HC / 4; ++i4) {
           const float4 hw = reinterpret_cast<const float4*>(s_headw + h * CP)[i4];
           s0 = fmaf(__uint_as_float(e[4 * i4]), hw.x, s0);
           s1 = fmaf(__uint_as_float(e[4 * i4 + 1]), hw.y, s1);
@@ -385,17 +386,24 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
 #else
       const bool drain = true;
 #endif
-      uint32_t acc[CP];
-      uint32_t w0[NW];
+      uint32_t acc[HC];
+      uint32_t w0[NW], w1[NW];
       if (real0) {
-        if (drain) tmem_ld_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP), acc);
-        tmem_ld_wait_cp<CP>(acc);
-        if (MODE == EPI_HEAD) heads(acc, v - 2);
-        else activate(acc, w0);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          if (drain) tmem_ld_cp<HC>(tmem_base + lane_addr + (uint32_t)(sl * CP + hh * HC), acc);
+          tmem_ld_wait_cp<HC>(acc);
+          if (MODE == EPI_HEAD) heads(acc, v - 2);
+          else activate(acc, w0, hh);
+        }
       }
       if (real1) {
-        if (drain) tmem_ld_cp<CP>(tmem_base + lane_addr + (uint32_t)(s1 * CP), acc);
-        tmem_ld_wait_cp<CP>(acc);
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          if (drain) tmem_ld_cp<HC>(tmem_base + lane_addr + (uint32_t)(s1 * CP + hh * HC), acc);
+          tmem_ld_wait_cp<HC>(acc);
+          if (NH > 1) activate(acc, w1, hh);       // 64-channel rows: activated half by half before the release
+        }
       }
       tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP));
       if (two) tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(s1 * CP));
@@ -409,9 +417,8 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
       if (MODE == EPI_HEAD) {
         if (real1) heads(acc, v - 1);
       } else {
-        uint32_t w1[NW];
         if (real0) emit(w0, v - 2);                // before row 1 is activated: keeps the live registers at two rows
-        if (real1) { activate(acc, w1); emit(w1, v - 1); }
+        if (real1) { if (NH == 1) activate(acc, w1, 0); emit(w1, v - 1); }
         if (POOL && real0 && real1) {              // MaxPool2d(2): x pairs are adjacent lanes, y pairs = this row pair
           if (ESZ == 2) {
 #pragma unroll
@@ -649,7 +656,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     // ======================================= epilogue =======================================
 #define BIU_REPI(CP, MODE, POOL) \
     rows_epilogue<ESZ, CP, MODE, POOL>(p, tmem_base, t_full, t_empty, s_scale, s_shift, s_headw, stage, warp, lane)
-    if (p.cp == 32) {
+    if (p.cp == 64) {                                  // plan_rows: bf16, 2D, EPI_CONV only
+      if (ESZ == 2) {
+        if (p.pool_out != nullptr) BIU_REPI(64, EPI_CONV, true);
+        else BIU_REPI(64, EPI_CONV, false);
+      }
+    } else if (p.cp == 32) {
       if (p.mode == EPI_HEAD) BIU_REPI(32, EPI_HEAD, false);
       else if (p.pool_out != nullptr) BIU_REPI(32, EPI_CONV, true);
       else BIU_REPI(32, EPI_CONV, false);

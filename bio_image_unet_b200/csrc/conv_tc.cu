@@ -266,13 +266,21 @@ static bool rows_single_pipe() {
   return v == 1;
 }
 
+static bool rows_no_wide() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BIU_ROWS_NO_WIDE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static RowsPlan plan_rows(const ConvTcArgs& a) {
   RowsPlan pl{};
   pl.ok = false;
   if (rows_disabled() || halo_disabled() || a.wgt_fold == nullptr) return pl;
   if (a.mode != EPI_CONV && a.mode != EPI_HEAD) return pl;
   if (a.kw != 3 || a.kh != 3 || (a.kd != 1 && a.kd != 3)) return pl;
-  if (a.n_total != 16 && a.n_total != 32) return pl;        // N of the folded MMA = 3 * Cout = 48 or 96
+  // N of the folded MMA = 3 * Cout = 48 or 96; 192 (Cout = 64) for 2D bf16 blocks: 8 TMEM slots, one pipeline
+  const bool wide = a.n_total == 64 && a.esz == 2 && a.kd == 1 && a.mode == EPI_CONV && !rows_no_wide();
+  if (a.n_total != 16 && a.n_total != 32 && !wide) return pl;
   if (a.W < 128) return pl;                                  // one MMA tile = 128 consecutive pixels of a row
   if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
   if (a.pool_out != nullptr && (a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1))) return pl;
@@ -315,7 +323,7 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   // two pipelines per CTA when the A ring is deep enough to be halved and there is work for both
   static int min_slots = -1;
   if (min_slots < 0) { const char* e = getenv("BIU_ROWS_PIPE_MIN_SLOTS"); min_slots = e ? atoi(e) : 8; }
-  p.pipes = (pl.a_slots >= min_slots && p.total_items >= 2 * sm_count_cached() && !rows_single_pipe()) ? 2 : 1;
+  p.pipes = (pl.a_slots >= min_slots && p.total_items >= 2 * sm_count_cached() && !rows_single_pipe() && a.n_total <= 32) ? 2 : 1;
   if (p.pipes == 2) p.a_slots &= ~1;
   p.w_tile_bytes = pl.w_tile_bytes; p.t_slots = pl.t_slots;
   p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;

@@ -490,7 +490,7 @@ int net_finalize(Net* n) {
         }
         // narrow blocks (Cout <= 32): second packing with the dy taps folded into the GEMM's N, in the order
         // dy = 2, 1, 0 = output rows r-1, r, r+1 of input row r (conv_rows.cuh)
-        if (L.kw == 3 && L.cout_pad <= 32) {
+        if (L.kw == 3 && (L.cout_pad <= 32 || (L.cout_pad == 64 && L.kd == 1 && n->esz == 2))) {
           const int tz = L.kd * 3, nfold = 3 * L.cout_pad;
           std::vector<float> wf((size_t)tz * nfold * L.cin_phys, 0.f);
           for (int dz = 0; dz < L.kd; ++dz)
