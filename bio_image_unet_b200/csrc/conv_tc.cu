@@ -252,7 +252,8 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
 // Row-streaming folded-tap kernel (conv_rows.cuh): eligibility, plan and launch
 // ---------------------------------------------------------------------------------------------------------------
 static int g_rows_enabled = -1;     // -1: from the environment (BIU_CONV_NOROWS=1 disables), else 0 / 1
-void conv_rows_set_enabled(int on) { g_rows_enabled = on ? 1 : 0; }
+static int g_rows_force_dual = 0;   // test hook (biu_set_rows_kernel(2)): two pipelines even when there are few work items
+void conv_rows_set_enabled(int on) { g_rows_enabled = on ? 1 : 0; g_rows_force_dual = on == 2 ? 1 : 0; }
 static bool rows_disabled() {
   if (g_rows_enabled < 0) { const char* e = getenv("BIU_CONV_NOROWS"); g_rows_enabled = (e && e[0] == '1') ? 0 : 1; }
   return g_rows_enabled == 0;
@@ -323,7 +324,8 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   // two pipelines per CTA when the A ring is deep enough to be halved and there is work for both
   static int min_slots = -1;
   if (min_slots < 0) { const char* e = getenv("BIU_ROWS_PIPE_MIN_SLOTS"); min_slots = e ? atoi(e) : 8; }
-  p.pipes = (pl.a_slots >= min_slots && p.total_items >= 2 * sm_count_cached() && !rows_single_pipe() && a.n_total <= 32) ? 2 : 1;
+  p.pipes = (pl.a_slots >= min_slots && (p.total_items >= 2 * sm_count_cached() || g_rows_force_dual) && !rows_single_pipe() &&
+             a.n_total <= 32) ? 2 : 1;
   if (p.pipes == 2) p.a_slots &= ~1;
   p.w_tile_bytes = pl.w_tile_bytes; p.t_slots = pl.t_slots;
   p.mode = a.mode; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;

@@ -80,7 +80,8 @@ int biu_net_set_fuse_pool(biu_net* net, int on);
  * instead of the CUDA-core kernel. Parity-tested, but measured slower (2.5 vs 1.7 ms on cfg 2), hence default 0. */
 int biu_net_set_first_tc(biu_net* net, int on);
 /* Test hook (process-wide): 0 = run the narrow (Cout <= 32) 3x3 blocks on the halo-tile kernel instead of the
- * row-streaming folded-tap kernel (default 1; results agree to fp32 summation order). */
+ * row-streaming folded-tap kernel (default 1; results agree to fp32 summation order); 2 = row kernel with its two
+ * pipelines per CTA forced on even for workloads with few work items (they are only chosen for large batches). */
 int biu_set_rows_kernel(int on);
 void biu_net_destroy(biu_net* net);
 

@@ -357,7 +357,7 @@ def test_variant_predict_matches_reference_golden(name, precision, as_class, tmp
 def rows_kernel_toggle():
     from bio_image_unet_b200 import _lib
     lib = _lib.load()
-    yield lambda on: lib.biu_set_rows_kernel(int(on))
+    yield lambda on: lib.biu_set_rows_kernel(int(on))   # 0: halo kernel, 1: row kernel, 2: row kernel, both pipelines forced
     lib.biu_set_rows_kernel(1)
 
 
@@ -375,13 +375,17 @@ def test_rows_kernel_matches_halo_kernel_2d(precision, n_filter, tile, batch, ro
         ref, _ = omodels.unet_forward(sd, tiles.float() / 255)
     names = [('cat4', 2 * n_filter, 0), ('m1', n_filter, 1), ('d7', n_filter, 0)]
     got = {}
-    for on in (1, 0):
+    for on in (2, 1, 0):                  # 2: both pipelines of the row kernel forced on (default only for big batches)
         rows_kernel_toggle(on)
         eng = Engine('unet2d', sd, n_filter, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
         eng.plan(batch, tile)
         val, u8 = eng.forward(tiles.cuda(), want_val=True, want_u8=True)
         got[on] = (val.cpu(), u8.cpu(), {n: eng.debug_activation(n, c, l).copy() for n, c, l in names})
         eng.close()
+    # one or two pipelines: the same MMAs in the same order per output row -> bit-identical
+    assert torch.equal(got[2][0], got[1][0]) and torch.equal(got[2][1], got[1][1])
+    for n, _, _ in names:
+        assert np.array_equal(got[2][2][n], got[1][2][n]), n
     rel = 2 ** -7 if precision == 'bf16' else 2 ** -9       # one ulp of the stored format
     for n, _, _ in names:
         a, b = got[1][2][n], got[0][2][n]
@@ -426,13 +430,14 @@ def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, bat
             o = omodels.mo3d_forward(sd, x, cfg, True)
             ref = torch.cat([o['seg'], o['flow']], 1)
     got = {}
-    for on in (1, 0):
+    for on in (2, 1, 0):                  # 2: both pipelines of the row kernel forced on
         rows_kernel_toggle(on)
         eng = Engine(kind, sd, precision=precision, device='cuda:0', **spec)
         eng.plan(batch, tile)
         val, _ = eng.forward(x.cuda(), want_val=True, want_u8=False)
         got[on] = val.cpu()
         eng.close()
+    assert torch.equal(got[2], got[1])    # one or two pipelines: bit-identical
     tol = 2e-3 if precision == 'tf32' else 2e-2
     assert (got[1] - got[0]).abs().max().item() < 0.5 * tol
     assert (got[1] - ref).abs().max().item() < tol, (got[1] - ref).abs().max().item()
