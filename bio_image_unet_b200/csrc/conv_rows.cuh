@@ -46,6 +46,8 @@ struct ConvRowsParams {
   int total_items;               // strips * rblocks * D * B
   int kd;                        // 1 (2D) or 3
   int cin_chunks, ck, row_bytes;
+  int stage_px;                  // bytes of a pixel staged per epilogue pass (64, or 32 to save shared memory)
+  int cps;                       // channel chunks per A-ring slot (cin_chunks, or 1 when a whole row does not fit)
   int cp;                        // padded output channels (16 or 32); N of the folded MMA = 3 * cp
   int a_slots;                   // shared-memory ring: one slot = one input row of one plane, all channel chunks
   uint32_t a_slot_bytes, a_chunk_bytes;
@@ -213,7 +215,7 @@ __device__ __forceinline__ RowsItem rows_decode(const ConvRowsParams& p, int t) 
 }
 
 // Epilogue of all work items for one warp. CP = padded output channels (all of them are handled by this warp).
-template <int ESZ, int CP, int MODE, bool POOL>
+template <int ESZ, int CP, int MODE, bool POOL, int SBW = 64>
 __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t tmem_base, uint64_t* t_full,
                                               uint64_t* t_empty, const float* s_scale, const float* s_shift,
                                               const float* s_headw, uint8_t* stage, int warp, int lane) {
@@ -222,7 +224,8 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
   constexpr int NH = CP / HC;
   constexpr int NW = PXB / 4;                    // 32-bit words per pixel
   constexpr int NV = PXB / 16;                   // 16-byte pieces per pixel: 2, 4 or 8
-  constexpr int SB = PXB < 64 ? PXB : 64;        // bytes of a pixel staged per pass (128-byte pixels go in two passes)
+  constexpr int SB = PXB < SBW ? PXB : SBW;      // bytes of a pixel staged per pass (wider pixels go in several passes; SBW = 32
+                                                 // keeps the tiles small when a 64-channel block's weights need the room)
   constexpr int SV = SB / 16;                    // 16-byte pieces per pixel and pass: 2 or 4
   constexpr int PASSES = PXB / SB;
   constexpr int PPI = 32 / SV;                   // pixels covered by one transposed warp store
@@ -518,28 +521,30 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     // ================================== input row (A) producer ===================================
     const int pipe = warp >> 1;
     if (elect_one()) {
-      const uint32_t row_tx = (uint32_t)p.cin_chunks * (uint32_t)kRowsPx * rb;
+      const int cps = p.cps, groups = p.cin_chunks / cps;          // a slot holds cps channel chunks of one input row
+      const uint32_t slot_tx = (uint32_t)cps * (uint32_t)kRowsPx * rb;
       const int a0 = pipe * asl;                                   // this pipeline's slots: [a0, a0 + asl)
       int as = 0;
       uint32_t aph = 0;
       for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += pipes * gridDim.x) {
         const RowsItem it = rows_decode(p, t);
         for (int i = 0; i < it.rows + 2; ++i)
-          for (int dz = 0; dz < p.kd; ++dz) {
-            mbar_wait(&a_empty[a0 + as], aph ^ 1, 0xB00 + as);
+          for (int dz = 0; dz < p.kd; ++dz)
+            for (int g = 0; g < groups; ++g) {
+              mbar_wait(&a_empty[a0 + as], aph ^ 1, 0xB00 + as);
 #ifdef BIU_DBG_KNOBS
-            if (g_rows_dbg & 16) { mbar_arrive(&a_full[a0 + as]); if (++as == asl) { as = 0; aph ^= 1; } continue; }
+              if (g_rows_dbg & 16) { mbar_arrive(&a_full[a0 + as]); if (++as == asl) { as = 0; aph ^= 1; } continue; }
 #endif
-            mbar_arrive_expect_tx(&a_full[a0 + as], row_tx);
-            for (int ch = 0; ch < p.cin_chunks; ++ch)
-              asm volatile(
-                  "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-                  "%5, %6, %7}], [%2];" ::"r"(a_base + (a0 + as) * p.a_slot_bytes + ch * p.a_chunk_bytes),
-                  "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[a0 + as])), "r"(ch * p.ck), "r"(it.x0 - 1),
-                  "r"(it.y0 - 1 + i), "r"(it.z - (p.kd >> 1) + dz), "r"(it.b)
-                  : "memory");
-            if (++as == asl) { as = 0; aph ^= 1; }
-          }
+              mbar_arrive_expect_tx(&a_full[a0 + as], slot_tx);
+              for (int c = 0; c < cps; ++c)
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+                    "%5, %6, %7}], [%2];" ::"r"(a_base + (a0 + as) * p.a_slot_bytes + c * p.a_chunk_bytes),
+                    "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[a0 + as])), "r"((g * cps + c) * p.ck),
+                    "r"(it.x0 - 1), "r"(it.y0 - 1 + i), "r"(it.z - (p.kd >> 1) + dz), "r"(it.b)
+                    : "memory");
+              if (++as == asl) { as = 0; aph ^= 1; }
+            }
       }
     }
   } else if (warp == 1 || (warp == 3 && pipes == 2)) {
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
     };
     const uint32_t t_mask = (uint32_t)tsl - 1u, t_lg = tsl == 32 ? 5u : (tsl == 16 ? 4u : 3u), t_wrap = 2u * (uint32_t)tsl - 1u;
-    const int kd = p.kd, chunks = p.cin_chunks;
+    const int kd = p.kd, chunks = p.cin_chunks, cps = p.cps;
     const uint32_t cp = (uint32_t)p.cp;
     const uint32_t tmem_pipe = tmem_base + (uint32_t)(pipe * tsl) * cp;   // this pipeline's slot 0
     int as = 0;
@@ -615,11 +620,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
         const uint32_t s0 = fr & t_mask;
         const int wrap = (int)s0 + 3 - tsl;            // > 0: that many slots continue at slot 0
         const uint32_t tcol = tmem_pipe + s0 * cp;
-        for (int dz = 0; dz < kd; ++dz) {
+        for (int dz = 0; dz < kd; ++dz)
+         for (int g0 = 0; g0 < chunks; g0 += cps) {      // one A slot = cps channel chunks of the row
           wait_bar(bar_af + 8u * (uint32_t)as, aph, 0xE00 + as);
           tc_fence_after();
-          for (int ch = 0; ch < chunks; ++ch) {
-            const uint64_t ad0 = a_desc0 + (uint64_t)(as * aslot_step + ch * achunk_step);
+          for (int c = 0; c < cps; ++c) {
+            const int ch = g0 + c;
+            const uint64_t ad0 = a_desc0 + (uint64_t)(as * aslot_step + c * achunk_step);
             const uint64_t wd0 = w_desc0 + (uint64_t)((dz * 3 * chunks + ch) * wtile_step);
             if (!dbg_nomma && elect_one()) {
               if (wrap <= 0) {
@@ -658,8 +665,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     rows_epilogue<ESZ, CP, MODE, POOL>(p, tmem_base, t_full, t_empty, s_scale, s_shift, s_headw, stage, warp, lane)
     if (p.cp == 64) {                                  // plan_rows: bf16, 2D, EPI_CONV only
       if (ESZ == 2) {
-        if (p.pool_out != nullptr) BIU_REPI(64, EPI_CONV, true);
-        else BIU_REPI(64, EPI_CONV, false);
+#define BIU_REPI64(POOL, SBW) \
+        rows_epilogue<ESZ, 64, EPI_CONV, POOL, SBW>(p, tmem_base, t_full, t_empty, s_scale, s_shift, s_headw, stage, warp, lane)
+        if (p.stage_px == 32) { if (p.pool_out != nullptr) BIU_REPI64(true, 32); else BIU_REPI64(false, 32); }
+        else { if (p.pool_out != nullptr) BIU_REPI64(true, 64); else BIU_REPI64(false, 64); }
+#undef BIU_REPI64
       }
     } else if (p.cp == 32) {
       if (p.mode == EPI_HEAD) BIU_REPI(32, EPI_HEAD, false);

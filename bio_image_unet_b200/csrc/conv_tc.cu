@@ -259,7 +259,7 @@ static bool rows_disabled() {
   return g_rows_enabled == 0;
 }
 
-struct RowsPlan { int ck, a_slots, t_slots, RB, smem; uint32_t a_slot_bytes, a_chunk_bytes, w_tile_bytes; bool ok; };
+struct RowsPlan { int ck, cps, stage_px, a_slots, t_slots, RB, smem; uint32_t a_slot_bytes, a_chunk_bytes, w_tile_bytes; bool ok; };
 
 static bool rows_single_pipe() {
   static int v = -1;
@@ -291,11 +291,25 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   pl.ck = ck;
   pl.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
   pl.a_chunk_bytes = ((uint32_t)(kRowsPx * rb) + 1023u) & ~1023u;
+  pl.cps = chunks;
   pl.a_slot_bytes = (uint32_t)chunks * pl.a_chunk_bytes;
   const int px_bytes = a.n_total * a.esz;
-  const int tail = (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * (px_bytes < 64 ? px_bytes : 64) + 64;   // scale/shift/heads + staging tiles
-  const int budget = 225 * 1024 - tail - 1024 - (int)(a.kd * 3 * chunks * pl.w_tile_bytes);
+  int stage_px = px_bytes < 64 ? px_bytes : 64;                                          // conv_rows.cuh: SB
+  auto tail_of = [&](int spx) { return (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * spx + 64; };   // scale/shift/heads + staging tiles
+  const int wbytes = (int)(a.kd * 3 * chunks * pl.w_tile_bytes);
+  int tail = tail_of(stage_px);
+  int budget = 225 * 1024 - tail - 1024 - wbytes;
   int slots = budget / (int)pl.a_slot_bytes;
+  if (slots < 2 * a.kd + 1 && chunks > 1) {
+    // a whole input row (all channel chunks) per slot does not leave enough slots: one chunk per slot, and for the
+    // 64-channel blocks half-size staging tiles
+    pl.cps = 1;
+    pl.a_slot_bytes = pl.a_chunk_bytes;
+    if (a.n_total == 64) { stage_px = 32; tail = tail_of(stage_px); budget = 225 * 1024 - tail - 1024 - wbytes; }
+    slots = budget / (int)pl.a_slot_bytes;
+    if (slots < 3 * a.kd) return pl;
+  }
+  pl.stage_px = stage_px;
   if (slots > kRowsMaxASlots) slots = kRowsMaxASlots;
   if (slots < 2 * a.kd + 1) return pl;                       // weights + a few rows in flight must fit
   pl.a_slots = slots;
@@ -320,7 +334,7 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   p.kd = a.kd;
   p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
   p.cp = a.n_total;
-  p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.a_chunk_bytes = pl.a_chunk_bytes;
+  p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.a_chunk_bytes = pl.a_chunk_bytes; p.cps = pl.cps; p.stage_px = pl.stage_px;
   // two pipelines per CTA when the A ring is deep enough to be halved and there is work for both
   static int min_slots = -1;
   if (min_slots < 0) { const char* e = getenv("BIU_ROWS_PIPE_MIN_SLOTS"); min_slots = e ? atoi(e) : 8; }
