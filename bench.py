@@ -31,7 +31,7 @@ ADD_TILE = 1
 N_FILTER = 32
 FLOP_PER_TILE_PX = 367232          # 2 * sum(M*N*K) per tile pixel, Unet(n_filter=32)
 FLOP_PER_TILE_PX_TC = 367232 - 2 * (9 * 32 + 32)   # minus encode1 and the 1x1 head, which are not tcgen05 launches
-NCU_CONV_DRAM_BYTES_PER_FORWARD = 58.35e9          # measured DRAM traffic of those launches, 200 tiles (profiles/r01f_*)
+NCU_CONV_DRAM_BYTES_PER_FORWARD = 58.50e9          # measured DRAM traffic of those launches, 200 tiles (profiles/r01g_*)
 
 
 def synth_frames(n, seed0=0):
@@ -244,7 +244,7 @@ def main():
                 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1.4 PFLOP/s sustained',
                 'traffic': NCU_CONV_DRAM_BYTES_PER_FORWARD * ses.tile_batch / 200 if args.precision == 'bf16' else None,
-                'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 launches of a 200-tile forward (profiles/r01f_ncu_conv_kernels_full.csv)',
+                'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum summed over the 21 launches of a 200-tile forward (profiles/r01g_ncu_conv_kernels_full.csv)',
                 'tc_ms_per_forward': tc_ms, 'all_ops_ms_per_forward': all_ms,
                 'tc_launches_per_forward': tc_launches, 'tiles_per_forward': ses.tile_batch,
                 'cuda_core_fallback_ops': fallback_ops,
