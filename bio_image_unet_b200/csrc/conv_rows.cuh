@@ -1,4 +1,5 @@
-// Row-streaming 3x3(x3) convolution for NARROW layers (Cout <= 32) on tcgen05: the dy taps are folded into N.
+// Row-streaming 3x3(x3) convolution for NARROW layers (Cout <= 32; 2D bf16 also Cout = 64) on tcgen05: the dy taps
+// are folded into N.
 //
 // Why: with M = 128 the tensor core fetches its operands from shared memory at ~85 B/clk (measured,
 // tools/conv_bench.cu): an MMA of N = 32 costs ~60 cycles for 16 cycles of math, so the 9-tap / 27-tap form of
@@ -21,8 +22,13 @@
 // channel chunk; out-of-image rows / columns / planes are zero-filled = the convolution's padding). Per item the
 // ring sees RB+4 "virtual" output rows: two dummies on either side collect the unused partial rows of the halo
 // input rows and are only zeroed again. The folded weights of the layer stay resident in shared memory.
+// (When a whole input row - all channel chunks - does not fit beside them, the ring's slots hold one channel chunk
+// each: ConvRowsParams::cps.) Cout = 64: N = 192, eight TMEM slots of 64 columns, a row is drained in two halves.
 // Warp roles: 0 = row (A) producer, 1 = TMEM alloc + MMA issuer (warp-uniform, see conv_halo.cuh), 2 = weight
-// loader, 4..19 = epilogue: warp w drains TMEM lane quarter w % 4 (32 pixels, ALL channels) of every fourth PAIR of
+// loader; with ConvRowsParams::pipes == 2 warps 2 and 3 are the producer and the MMA issuer of a SECOND, independent
+// pipeline (own half of the A ring, of the TMEM slots and of the epilogue groups, alternate work items) that shares
+// the resident weights and the tensor core - one issuing warp spends as long on a row's barrier bookkeeping as the
+// tensor core on its six MMAs and the two do not overlap. 4..19 = epilogue: warp w drains TMEM lane quarter w % 4 (32 pixels, ALL channels) of every fourth PAIR of
 // output rows (group (w - 4) / 4): four groups of four warps leapfrog over the row pairs, so one group's barrier wait /
 // TMEM drain / slot zeroing overlaps the other groups' arithmetic and stores. A slot is released by the four arrivals
 // of the group that drained it. Finished rows go through a per-warp, XOR-swizzled shared-memory tile and are written
