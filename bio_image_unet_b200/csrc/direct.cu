@@ -571,40 +571,45 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) pool2_kernel(PoolArgs a) {
+  // output rows flattened over the threads, one 64-bit division per thread and 32-bit arithmetic below it;
+  // consecutive threads read consecutive vectors of
+  // consecutive input voxels (x = 2 ox, 2 ox + 1 are adjacent), i.e. contiguous runs of the 2 (x 2) input rows
   const int oW = a.W / 2, oH = a.H / 2, oD = a.dims == 3 ? a.D / 2 : a.D;
   const int cv = a.c / VEC;
-  const long long total = (long long)a.B * oD * oH * oW * cv;
+  const int rows = a.B * oD * oH, per_row = oW * cv;
   const T* in = reinterpret_cast<const T*>(a.in);
   T* out = reinterpret_cast<T*>(a.out);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long r = idx;
-    const int c = (int)(r % cv) * VEC; r /= cv;
-    const int x = (int)(r % oW); r /= oW;
-    const int y = (int)(r % oH); r /= oH;
-    const int z = (int)(r % oD); r /= oD;
-    const int b = (int)r;
-    float m[VEC];
+  const int nz = (a.dims == 3 && a.mode == 0) ? 2 : 1;
+  const int nyx = a.mode == 0 ? 2 : 1;
+  const int zs = a.dims == 3 ? 2 : 1;
+  const long long i_y = (long long)a.W * a.in_ctot, i_z = (long long)a.H * a.W * a.in_ctot;
+  const long long total = (long long)rows * per_row;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    {
+      const int row = (int)(idx / per_row), i = (int)(idx - (long long)row * per_row);
+      const int y = row % oH, bz = row / oH;
+      const int z = bz % oD, b = bz / oD;
+      const T* i00 = in + ((((long long)b * a.D + zs * z) * a.H + 2 * y) * a.W) * a.in_ctot + a.in_coff;
+      T* orow = out + (long long)row * oW * a.out_ctot + a.out_coff;
+      const int x = i / cv, c = (i - x * cv) * VEC;
+      float m[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
-    const int nz = (a.dims == 3 && a.mode == 0) ? 2 : 1;
-    const int nyx = a.mode == 0 ? 2 : 1;
-    for (int dz = 0; dz < nz; ++dz)
-      for (int dy = 0; dy < nyx; ++dy)
-        for (int dx = 0; dx < nyx; ++dx) {
-          const int iz = a.dims == 3 ? 2 * z + dz : z;
-          const long long p = (((long long)b * a.D + iz) * a.H + (2 * y + dy)) * a.W + (2 * x + dx);
-          const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + p * a.in_ctot + a.in_coff + c));
-          const T* e = reinterpret_cast<const T*>(&q);
+      for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+      const T* ip = i00 + (long long)(2 * x) * a.in_ctot + c;
+      for (int dz = 0; dz < nz; ++dz)
+        for (int dy = 0; dy < nyx; ++dy)
+          for (int dx = 0; dx < nyx; ++dx) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(ip + dz * i_z + dy * i_y + dx * a.in_ctot));
+            const T* e = reinterpret_cast<const T*>(&q);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) m[k] = fmaxf(m[k], (float)e[k]);
-        }
-    uint4 q;
-    T* e = reinterpret_cast<T*>(&q);
+            for (int k = 0; k < VEC; ++k) m[k] = fmaxf(m[k], (float)e[k]);
+          }
+      uint4 q;
+      T* e = reinterpret_cast<T*>(&q);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) e[k] = (T)m[k];
-    const long long op = (((long long)b * oD + z) * oH + y) * oW + x;
-    *reinterpret_cast<uint4*>(out + op * a.out_ctot + a.out_coff + c) = q;
+      for (int k = 0; k < VEC; ++k) e[k] = (T)m[k];
+      *reinterpret_cast<uint4*>(orow + x * a.out_ctot + c) = q;
+    }
   }
 }
 
@@ -613,8 +618,7 @@ int launch_pool2(const PoolArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(a.c % vec == 0 && a.in_ctot % vec == 0 && a.in_coff % vec == 0 && a.out_ctot % vec == 0 &&
                   a.out_coff % vec == 0,
               "pool2: channel counts must be multiples of %d", vec);
-  const long long total = (long long)a.B * (a.dims == 3 ? a.D / 2 : a.D) * (a.H / 2) * (a.W / 2) * (a.c / vec);
-  long long blocks = ceil_div_ll(total, 256);
+  long long blocks = ceil_div_ll((long long)a.B * (a.dims == 3 ? a.D / 2 : a.D) * (a.H / 2) * (a.W / 2) * (a.c / vec), 256);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (blocks < 1) blocks = 1;
   if (a.esz == 2) pool2_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);
@@ -625,26 +629,35 @@ int launch_pool2(const PoolArgs& a, cudaStream_t stream) {
 }
 
 // nearest x2 upsampling: out[2z+a, 2y+b, 2x+c] = in[z, y, x] (multi_output_unet3d.py:138,147,156)
+// One block iteration per INPUT row: a thread reads one 16-byte channel vector and writes its 4 (2D) / 8 (3D) copies;
+// consecutive threads cover consecutive vectors of consecutive voxels, so every output row receives one contiguous
+// run. 32-bit index arithmetic (the output-indexed first version spent its time in 64-bit divisions: 2.6 TB/s).
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) up_nearest_kernel(UpNearestArgs a) {
-  const int oW = a.W * 2, oH = a.H * 2, oD = a.dims == 3 ? a.D * 2 : a.D;
+  const int oW = a.W * 2, oH = a.H * 2;
+  const int zc = a.dims == 3 ? 2 : 1, oD = a.D * zc;
   const int cv = a.c / VEC;
-  const long long total = (long long)a.B * oD * oH * oW * cv;
+  const int rows = a.B * a.D * a.H, per_row = a.W * cv;
   const T* in = reinterpret_cast<const T*>(a.in);
   T* out = reinterpret_cast<T*>(a.out);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long r = idx;
-    const int c = (int)(r % cv) * VEC; r /= cv;
-    const int x = (int)(r % oW); r /= oW;
-    const int y = (int)(r % oH); r /= oH;
-    const int z = (int)(r % oD); r /= oD;
-    const int b = (int)r;
-    const int iz = a.dims == 3 ? z / 2 : z;
-    const long long p = (((long long)b * a.D + iz) * a.H + y / 2) * a.W + x / 2;
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + p * a.in_ctot + a.in_coff + c));
-    const long long op = (((long long)b * oD + z) * oH + y) * oW + x;
-    *reinterpret_cast<uint4*>(out + op * a.out_ctot + a.out_coff + c) = q;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int y = row % a.H, bz = row / a.H;
+    const int z = bz % a.D, b = bz / a.D;
+    const T* irow = in + (long long)row * a.W * a.in_ctot + a.in_coff;
+    T* o00 = out + ((((long long)b * oD + zc * z) * oH + 2 * y) * oW) * a.out_ctot + a.out_coff;
+    const long long o_y = (long long)oW * a.out_ctot, o_z = (long long)oH * oW * a.out_ctot;
+    for (int i = threadIdx.x; i < per_row; i += blockDim.x) {
+      const int x = i / cv, c = (i - x * cv) * VEC;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(irow + x * a.in_ctot + c));
+      T* o = o00 + (long long)(2 * x) * a.out_ctot + c;
+      for (int dz = 0; dz < zc; ++dz)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          T* orow = o + dz * o_z + dy * o_y;
+          *reinterpret_cast<uint4*>(orow) = q;
+          *reinterpret_cast<uint4*>(orow + a.out_ctot) = q;
+        }
+    }
   }
 }
 int launch_up_nearest(const UpNearestArgs& a, cudaStream_t stream) {
@@ -652,8 +665,7 @@ int launch_up_nearest(const UpNearestArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(a.c % vec == 0 && a.in_ctot % vec == 0 && a.in_coff % vec == 0 && a.out_ctot % vec == 0 &&
                   a.out_coff % vec == 0,
               "up_nearest: channel counts must be multiples of %d", vec);
-  const long long total = (long long)a.B * (a.dims == 3 ? a.D * 2 : a.D) * a.H * 2 * a.W * 2 * (a.c / vec);
-  long long blocks = ceil_div_ll(total, 256);
+  long long blocks = (long long)a.B * a.D * a.H;             // one block iteration per input row
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (blocks < 1) blocks = 1;
   if (a.esz == 2) up_nearest_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);
