@@ -362,11 +362,14 @@ def rows_kernel_toggle():
 
 
 @pytest.mark.parametrize('precision', ['tf32', 'bf16'])
-@pytest.mark.parametrize('n_filter,tile,batch', [(32, (64, 256), 2), (32, (48, 144), 3), (16, (80, 128), 2), (32, (16, 640), 1)])
+@pytest.mark.parametrize('n_filter,tile,batch', [(32, (64, 256), 2), (32, (48, 144), 3), (16, (80, 128), 2), (32, (16, 640), 1),
+                                                 (32, (80, 400), 1)])
 def test_rows_kernel_matches_halo_kernel_2d(precision, n_filter, tile, batch, rows_kernel_toggle):
     """Same network, narrow blocks (encode2 + fused pool, decode7, decode8 + head) through conv_rows vs conv_halo:
     identical up to the fp32 summation order of the three partial rows (one ulp of the stored format), and both
-    within tolerance of the oracle. W = 144 / 640 exercise a partial last strip, H = 48 / 80 / 16 partial row blocks."""
+    within tolerance of the oracle. W = 144 / 640 exercise a partial last strip, H = 48 / 80 / 16 partial row blocks;
+    (80, 400) puts the 64-channel blocks of level 1 (200 px wide: a partial second strip) and decode5's channel-chunk
+    slots on ragged extents."""
     from bio_image_unet_b200.engine import Engine
     sd = stress_state_dict(n_filter, seed=21)
     tiles = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=torch.Generator().manual_seed(4))
