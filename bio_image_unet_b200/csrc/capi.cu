@@ -83,10 +83,11 @@ int biu_net_set_force_direct(biu_net* net, int on) {
   return 0;
 }
 
-int biu_net_set_first_tc(biu_net* net, int on) {
+int biu_net_fallback_ops(biu_net* net) {
   BIU_REQUIRE(net && net->n, "null handle");
-  net->n->no_first_tc = on ? 0 : 1;
-  return 0;
+  int cnt = 0;
+  for (int k : net->n->op_kinds) cnt += (k & 16) ? 1 : 0;
+  return cnt;
 }
 
 int biu_set_rows_kernel(int on) {

@@ -92,12 +92,8 @@ struct FirstConvArgs {          // planar u8 / f32 input with few channels -> NH
   void* out;                    // NHWC, channels [coff, coff+cout_pad) written (pad = zeros)
   int out_ctot, out_coff, cout_pad;
   int round_tf32;
-  const void* wgt_tc;           // optional (1 input channel, bf16): [cout_pad][16 or 32] bf16, tap-major (first_tc.cu)
-  const float* scale255;        // optional: scale / 255 (uint8 tiles on the tensor-core path)
 };
 int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream);
-bool first_tc_supported(const FirstConvArgs& a);
-int launch_first_tc(const FirstConvArgs& a, cudaStream_t stream);
 
 struct PoolArgs {
   int esz;

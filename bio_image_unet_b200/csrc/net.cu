@@ -452,19 +452,6 @@ int net_finalize(Net* n) {
       if (upload(n, wd, &L.w_direct)) return -1;
       if (upload(n, scale, &L.scale)) return -1;
       if (upload(n, shift, &L.shift)) return -1;
-      if (n->precision == PREC_BF16 && L.cin_log == 1 && L.kw == 3 && L.cout_pad <= 64) {
-        // first block on the tensor cores (first_tc.cu): one im2col row of K = 16 (9 taps) / 32 (27 taps) per pixel
-        const int K = L.kd == 1 ? 16 : 32;
-        std::vector<uint16_t> wf((size_t)L.cout_pad * K, 0);
-        for (int co = 0; co < L.cout; ++co)
-          for (int t = 0; t < taps; ++t) wf[(size_t)co * K + t] = host_bf16(w->data[(size_t)co * taps + t]);
-        uint16_t* d = nullptr;
-        if (upload(n, wf, &d)) return -1;
-        L.w_first = d;
-        std::vector<float> s255(L.cout_pad, 0.f);
-        for (int co = 0; co < L.cout_pad; ++co) s255[co] = scale[co] / 255.0f;
-        if (upload(n, s255, &L.scale255)) return -1;
-      }
       if (n->precision != PREC_FP32 && L.cin_phys % 16 == 0) {
         const size_t cnt = (size_t)taps * L.cout_pad * L.cin_phys;
         if (n->esz == 2) {
@@ -919,10 +906,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         a.wgt = L.w_direct; a.cout = L.cout_pad; a.slope = L.slope; a.scale = L.scale; a.shift = L.shift;
         a.esz = n->esz; a.out = dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
         a.cout_pad = L.cout_pad; a.round_tf32 = round_tf32;
-        a.wgt_tc = (tc_allowed && !n->no_first_tc) ? L.w_first : nullptr; a.scale255 = L.scale255;
-        if (first_tc_supported(a)) {
-          if (int rc = launch_first_tc(a, stream)) return rc;
-        } else if (int rc = launch_first_conv(a, stream)) return rc;
+        if (int rc = launch_first_conv(a, stream)) return rc;
         break;
       }
       case OP_CONV:

@@ -37,8 +37,6 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   float* gate_b = nullptr;
   std::vector<Segment> segs;
   void* w_tc = nullptr;      // packed [tap][n][cin_phys] bf16 / tf32
-  void* w_first = nullptr;   // first block (1 input channel, bf16): [cout_pad][16 | 32] bf16 im2col weights (first_tc.cu)
-  float* scale255 = nullptr; // scale / 255 for uint8 tiles on that path
   void* w_fold = nullptr;    // narrow 3x3 blocks: [dz*3+dx][(2-dy)*cout_pad + co][cin_phys] for the row-streaming kernel
   float* w_direct = nullptr; // fp32 [tap or q][cin_phys][cout_pad]
   float* scale = nullptr;    // [n_total]
@@ -89,8 +87,6 @@ struct Net {
   size_t ws_bytes = 0;
 
   int force_direct = 0;             // debugging: run every conv on the CUDA-core kernels
-  int no_first_tc = 1;              // the tcgen05 im2col first block (first_tc.cu) is correct but measured SLOWER than the
-                                    // CUDA-core kernel (2.5 vs 1.7 ms on cfg 2): off unless biu_net_set_first_tc(net, 1)
   int no_fuse = 0;                  // debugging: keep the max-pool as its own kernel
   int profile = 0;                  // bracket every op with CUDA events
   std::vector<cudaEvent_t> events;  // 2 per op

@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and (in the multi-GPU driver) torch.d
 that touches data is launched through ``libbiu_b200.so``. There is no CPU fallback.
 """
 import ctypes
+import warnings
 
 import numpy as np
 import torch
@@ -68,6 +69,8 @@ class Engine:
         self.batch = 0
         self.tile = None
         self.workspace = None
+        self.fallback_ops = 0
+        self._fallback_checked = False
 
     def plan(self, batch, tile):
         """tile: (h, w) or (d, h, w)."""
@@ -85,6 +88,7 @@ class Engine:
             else:
                 self.workspace.zero_()
         self.batch, self.tile = int(batch), (int(d), int(h), int(w))
+        self._fallback_checked = False
         return nbytes
 
     def forward(self, tiles, tiles_prev=None, want_val=False, want_u8=True):
@@ -105,6 +109,14 @@ class Engine:
             _lib.check(self.lib.biu_net_forward(self.handle, _lib.ptr(tiles), in_kind, _lib.ptr(tiles_prev),
                                                 _lib.ptr(val), _lib.ptr(u8), _lib.ptr(self.workspace),
                                                 _lib.stream_ptr()), 'biu_net_forward')
+        if not self._fallback_checked:
+            self._fallback_checked = True
+            self.fallback_ops = int(self.lib.biu_net_fallback_ops(self.handle))
+            if self.fallback_ops > 0 and self.precision != 'fp32':
+                warnings.warn(f"bio_image_unet_b200: {self.fallback_ops} layer(s) of this {self.kind} network "
+                              f"(n_filter / channel counts or tile shape outside what the tcgen05 kernels take) run on "
+                              f"the roughly 10x slower CUDA-core kernels in precision='{self.precision}'; results are "
+                              f"unaffected.", RuntimeWarning, stacklevel=3)
         return val, u8
 
     def debug_activation(self, name, channels, level):
@@ -140,9 +152,6 @@ class Engine:
     def set_force_direct(self, on):
         _lib.check(self.lib.biu_net_set_force_direct(self.handle, int(on)))
 
-    def set_first_tc(self, on):
-        _lib.check(self.lib.biu_net_set_first_tc(self.handle, int(on)))
-
     def set_fuse_pool(self, on):
         _lib.check(self.lib.biu_net_set_fuse_pool(self.handle, int(on)))
 
@@ -175,6 +184,21 @@ def _dev_i32(values, device):
             _I32_CACHE.clear()
         t = torch.tensor(list(key[0]), dtype=torch.int32, device=device)
         _I32_CACHE[key] = t
+    return t
+
+
+_I64_CACHE = {}
+
+
+def _dev_i64(values, device):
+    """Device int64 index tensor (frame selections of the Siam pairs), cached like _dev_i32."""
+    key = (tuple(int(v) for v in values), str(device))
+    t = _I64_CACHE.get(key)
+    if t is None:
+        if len(_I64_CACHE) > 64:
+            _I64_CACHE.clear()
+        t = torch.tensor(list(key[0]), dtype=torch.int64, device=device)
+        _I64_CACHE[key] = t
     return t
 
 

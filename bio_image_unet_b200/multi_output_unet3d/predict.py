@@ -15,6 +15,158 @@ from ..utils import get_device
 from .multi_output_unet3d import MultiOutputUnet3D
 
 
+class Session:
+    """Reusable multi-output 3D predictor (checkpoint folded / packed once, workspace resident)."""
+
+    def __init__(self, model_params, max_patch_size=(64, 256, 256), overlap_factor=0.1, normalization_mode='single',
+                 clip_threshold=(0., 99.98), device='cuda:0', precision='tf32', workspace_gb=24.0, dist=None):
+        if normalization_mode not in ('single', 'first', 'all'):
+            raise ValueError(f'Invalid normalization mode: {normalization_mode}')
+        params = torch.load(model_params, map_location='cpu') if isinstance(model_params, str) else model_params
+        self.device = torch.device(device)
+        self.max_patch_size, self.overlap_factor = max_patch_size, overlap_factor
+        self.normalization_mode, self.clip_threshold = normalization_mode, clip_threshold
+        self.workspace_bytes = int(workspace_gb * 2 ** 30)
+        self.dist = dist if dist is not None else DistContext(False)
+        self.output_heads = params['output_heads']
+        self.target_keys = list(self.output_heads.keys())
+        self.engine = Engine('mo3d', params['state_dict'], params['n_filter'], params['in_channels'],
+                             [(k, self.output_heads[k]['channels'], self.output_heads[k].get('activation'))
+                              for k in self.target_keys],
+                             use_interpolation=params.get('use_interpolation', True), precision=precision,
+                             device=self.device)
+        self.tile_batch, self._budget_batch, self._plan_key = None, None, None
+        self._out = P.PinnedOut()
+        self._host_out, self._s_out = None, None
+
+    def _plan(self, tile, n_tiles):
+        if self._plan_key != tuple(tile):
+            per_tile = self.engine.plan(1, tile)
+            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
+            self._plan_key, self.tile_batch = tuple(tile), None
+        target = min(max(1, n_tiles), self._budget_batch)
+        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
+            self.engine.plan(target, tile)
+            self.tile_batch = target
+        return self.tile_batch
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    def _normalise(self, vols_dev, lo):
+        """float32 normalised copy of this rank's volumes (multi_output_unet3d/predict.py:104-125)."""
+        q_lo, q_hi = self.clip_threshold
+        n = vols_dev.shape[0]
+        hist = P.E.histogram(vols_dev.reshape(n, -1)) if n else torch.zeros((0, P.E.HIST_BINS), dtype=torch.int32,
+                                                                             device=self.device)
+        if self.normalization_mode == 'single':
+            lut, _ = P.E.norm_lut_f32(hist, hist, n, q_lo, q_hi, 0)
+        else:
+            part = P.E.hist_sum(hist) if n else torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32, device=self.device)
+            if self.normalization_mode == 'all':
+                bounds = self.dist.all_reduce_sum(part)
+            else:   # 'first': the statistics of volume 0, owned by rank 0
+                bounds = hist[0:1].clone() if (lo == 0 and n) else torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32,
+                                                                               device=self.device)
+                bounds = self.dist.all_reduce_sum(bounds)
+            lut, _ = P.E.norm_lut_f32(bounds, bounds, 1, q_lo, q_hi, 1)
+        return P.E.apply_lut_f32(vols_dev.reshape(n, -1), lut).reshape(vols_dev.shape) if n else \
+            torch.zeros(vols_dev.shape, dtype=torch.float32, device=self.device)
+
+    def predict(self, imgs, keep=False, progress_notifier=None, show_progress=False):
+        """imgs: (N, D, H, W) (or (D, H, W)) uint8 / uint16 host stack -> {head: float32 array} on rank 0 (None
+        elsewhere). Results are views of a pinned buffer that the next call reuses."""
+        if imgs.ndim == 3:
+            imgs = imgs[None]
+        elif imgs.ndim != 4:
+            raise ValueError(f'Unsupported input shape: {imgs.shape}')
+        self.imgs_shape = tuple(imgs.shape)
+        n_vol, d_img, h_img, w_img = imgs.shape
+        self.patch_size = tuple(min(a, b) for a, b in zip((d_img, h_img, w_img), self.max_patch_size))
+        self.Z_start = tiling.strided_starts(d_img, self.patch_size[0], self.overlap_factor)
+        self.Y_start = tiling.strided_starts(h_img, self.patch_size[1], self.overlap_factor)
+        self.X_start = tiling.strided_starts(w_img, self.patch_size[2], self.overlap_factor)
+        self.N_z, self.N_y, self.N_x = len(self.Z_start), len(self.Y_start), len(self.X_start)
+        self.N_per_vol = self.N_z * self.N_y * self.N_x
+        lo, hi = self.dist.shard(n_vol)
+        dev = self.device
+        head_total = self.engine.head_total
+        if imgs.dtype not in (np.uint8, np.uint16, torch.uint8, torch.uint16):
+            raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got {imgs.dtype}')
+        vols = P.to_device_stack(imgs[lo:hi].reshape(hi - lo, d_img * h_img, w_img), dev).reshape(hi - lo, d_img, h_img, w_img)
+        norm = self._normalise(vols, lo)
+        # multi-GPU: the stitched float32 volumes stay in HBM until the NCCL gather on rank 0
+        on_device = self.dist.multi
+        shape = (hi - lo, head_total, d_img, h_img, w_img)
+        if on_device:
+            out_local = torch.zeros(shape, dtype=torch.float32, device=dev)
+        else:
+            # single process: chunks are copied back on a side stream into one (pinned, if it is not huge) host buffer
+            # while the next chunk computes
+            if self._host_out is None or tuple(self._host_out.shape) != shape:
+                nbytes = 4 * int(np.prod(shape))
+                self._host_out = torch.zeros(shape, dtype=torch.float32, pin_memory=nbytes <= (8 << 30))
+            out_local = self._host_out
+            if self._s_out is None:
+                self._s_out = torch.cuda.Stream(dev)
+            self._s_out.wait_stream(torch.cuda.current_stream(dev))
+        if hi > lo:
+            tile_batch = self._plan(self.patch_size, (hi - lo) * self.N_per_vol)
+            vols_per_chunk = max(1, (2 * tile_batch) // self.N_per_vol)
+            it = range(0, hi - lo, vols_per_chunk)
+            if show_progress and self.dist.rank == 0 and progress_notifier is not None:
+                it = progress_notifier.iterator(it)
+            kept_p, kept_r = [], []
+            for s in it:
+                e = min(s + vols_per_chunk, hi - lo)
+                patches = P.E.gather_tiles_f32(norm[s:e], self.Z_start, self.Y_start, self.X_start, self.patch_size)
+                patches = patches.reshape(-1, 1, *self.patch_size)
+                vals = []
+                for b0 in range(0, patches.shape[0], tile_batch):
+                    t = patches[b0:b0 + tile_batch]
+                    cnt = t.shape[0]
+                    if cnt < tile_batch:
+                        t = torch.cat((t, torch.zeros((tile_batch - cnt, *t.shape[1:]), dtype=t.dtype, device=dev)))
+                    v, _ = self.engine.forward(t.contiguous(), want_val=True, want_u8=False)
+                    vals.append(v[:cnt])
+                vals = vals[0] if len(vals) == 1 else torch.cat(vals)         # (n, head_total, pd, ph, pw)
+                st = P.E.stitch_ramp_f32(vals, e - s, head_total, (d_img, h_img, w_img), self.Z_start, self.Y_start,
+                                         self.X_start, self.patch_size, 16)
+                if on_device:
+                    out_local[s:e].copy_(st)
+                else:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(self._s_out):
+                        self._s_out.wait_event(ev)
+                        out_local[s:e].copy_(st, non_blocking=True)
+                        st.record_stream(self._s_out)
+                if keep:
+                    kept_p.append(patches.cpu().numpy())
+                    kept_r.append(vals.cpu().numpy())
+            if keep:
+                self.patches = np.concatenate(kept_p)
+                self.result_patches = np.concatenate(kept_r)
+        if on_device:
+            full = self.dist.gather_slabs(out_local, self.dist.shards(n_vol))
+            full = None if full is None else self._out.fetch(full)
+        else:
+            if self._s_out is not None:
+                self._s_out.synchronize()
+            full = out_local.numpy()
+        if full is None:
+            return None
+        result, c0 = {}, 0
+        heads = self.output_heads
+        for key in self.target_keys:
+            c = heads[key]['channels']
+            result[key] = np.squeeze(full[:, c0:c0 + c])
+            c0 += c
+        return result
+
+
 class Predict:
     """Prediction of volumetric (3D) data with the multi-output 3D U-Net (constructor surface of
     multi_output_unet3d/predict.py:16-27). Results per head in ``self.result`` (when result_path is None) or as
@@ -57,25 +209,20 @@ class Predict:
         self.imgs_shape = imgs.shape
 
         self.model_params = torch.load(model_params, map_location='cpu')
-        heads = self.model_params['output_heads']
-        self.target_keys = list(heads.keys())
-        self.engine = Engine('mo3d', self.model_params['state_dict'], self.model_params['n_filter'],
-                             self.model_params['in_channels'],
-                             [(k, heads[k]['channels'], heads[k].get('activation')) for k in self.target_keys],
-                             use_interpolation=self.model_params.get('use_interpolation', True), precision=precision,
-                             device=self.device)
-
-        n_vol, d_img, h_img, w_img = imgs.shape
-        self.patch_size = tuple(min(a, b) for a, b in zip((d_img, h_img, w_img), max_patch_size))
-        self.Z_start = tiling.strided_starts(d_img, self.patch_size[0], overlap_factor)
-        self.Y_start = tiling.strided_starts(h_img, self.patch_size[1], overlap_factor)
-        self.X_start = tiling.strided_starts(w_img, self.patch_size[2], overlap_factor)
-        self.N_z, self.N_y, self.N_x = len(self.Z_start), len(self.Y_start), len(self.X_start)
-        self.N_per_vol = self.N_z * self.N_y * self.N_x
-
-        result = self.__run(imgs, workspace_gb, keep_intermediates, progress_notifier)
-        self.engine.close()
-        del self.engine, self.model_params
+        ses = Session(self.model_params, max_patch_size, overlap_factor, normalization_mode, clip_threshold,
+                      self.device, precision, workspace_gb, self.dist)
+        self.target_keys = ses.target_keys
+        result = ses.predict(imgs, keep=keep_intermediates, progress_notifier=progress_notifier,
+                             show_progress=show_progress)
+        for k in ('patch_size', 'Z_start', 'Y_start', 'X_start', 'N_z', 'N_y', 'N_x', 'N_per_vol'):
+            setattr(self, k, getattr(ses, k))
+        if keep_intermediates and hasattr(ses, 'patches'):
+            self.patches, self.result_patches = ses.patches, ses.result_patches
+        if result is not None:           # the session's pinned result buffer dies with it
+            result = {k: np.array(v) for k, v in result.items()}
+        self.fallback_ops = ses.engine.fallback_ops
+        ses.close()
+        del ses, self.model_params
 
         if result is None:
             self.result = None
@@ -88,74 +235,3 @@ class Predict:
         else:
             self.result = result
         torch.cuda.empty_cache()
-
-    def __normalise(self, vols_dev, lo):
-        """float32 normalised copy of this rank's volumes (multi_output_unet3d/predict.py:104-125)."""
-        q_lo, q_hi = self.clip_threshold
-        n = vols_dev.shape[0]
-        hist = P.E.histogram(vols_dev.reshape(n, -1)) if n else torch.zeros((0, P.E.HIST_BINS), dtype=torch.int32,
-                                                                             device=self.device)
-        if self.normalization_mode == 'single':
-            lut, _ = P.E.norm_lut_f32(hist, hist, n, q_lo, q_hi, 0)
-        else:
-            part = P.E.hist_sum(hist) if n else torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32, device=self.device)
-            if self.normalization_mode == 'all':
-                bounds = self.dist.all_reduce_sum(part)
-            else:   # 'first': the statistics of volume 0, owned by rank 0
-                bounds = hist[0:1].clone() if (lo == 0 and n) else torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32,
-                                                                               device=self.device)
-                bounds = self.dist.all_reduce_sum(bounds)
-            lut, _ = P.E.norm_lut_f32(bounds, bounds, 1, q_lo, q_hi, 1)
-        return P.E.apply_lut_f32(vols_dev.reshape(n, -1), lut).reshape(vols_dev.shape) if n else \
-            torch.zeros(vols_dev.shape, dtype=torch.float32, device=self.device)
-
-    def __run(self, imgs, workspace_gb, keep, progress_notifier):
-        n_vol, d_img, h_img, w_img = imgs.shape
-        lo, hi = self.dist.shard(n_vol)
-        dev = self.device
-        head_total = self.engine.head_total
-        if imgs.dtype not in (np.uint8, np.uint16):
-            raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 stacks on the device; got {imgs.dtype}')
-        vols = P.to_device_stack(imgs[lo:hi].reshape(hi - lo, d_img * h_img, w_img), dev).reshape(hi - lo, d_img, h_img, w_img)
-        norm = self.__normalise(vols, lo)
-        out_local = np.zeros((hi - lo, head_total, d_img, h_img, w_img), dtype='float32')
-        if hi > lo:
-            tile_batch = P.pick_tile_batch(self.engine, self.patch_size, (hi - lo) * self.N_per_vol,
-                                           int(workspace_gb * 2 ** 30))
-            vols_per_chunk = max(1, (2 * tile_batch) // self.N_per_vol)
-            it = range(0, hi - lo, vols_per_chunk)
-            if self.show_progress and self.dist.rank == 0 and progress_notifier is not None:
-                it = progress_notifier.iterator(it)
-            kept_p, kept_r = [], []
-            for s in it:
-                e = min(s + vols_per_chunk, hi - lo)
-                patches = P.E.gather_tiles_f32(norm[s:e], self.Z_start, self.Y_start, self.X_start, self.patch_size)
-                patches = patches.reshape(-1, 1, *self.patch_size)
-                vals = []
-                for b0 in range(0, patches.shape[0], tile_batch):
-                    t = patches[b0:b0 + tile_batch]
-                    cnt = t.shape[0]
-                    if cnt < tile_batch:
-                        t = torch.cat((t, torch.zeros((tile_batch - cnt, *t.shape[1:]), dtype=t.dtype, device=dev)))
-                    v, _ = self.engine.forward(t.contiguous(), want_val=True, want_u8=False)
-                    vals.append(v[:cnt])
-                vals = vals[0] if len(vals) == 1 else torch.cat(vals)         # (n, head_total, pd, ph, pw)
-                st = P.E.stitch_ramp_f32(vals, e - s, head_total, (d_img, h_img, w_img), self.Z_start, self.Y_start,
-                                         self.X_start, self.patch_size, 16)
-                out_local[s:e] = st.cpu().numpy()
-                if keep:
-                    kept_p.append(patches.cpu().numpy())
-                    kept_r.append(vals.cpu().numpy())
-            if keep:
-                self.patches = np.concatenate(kept_p)
-                self.result_patches = np.concatenate(kept_r)
-        full = self.dist.gather_frames(out_local, n_vol, dev)
-        if full is None:
-            return None
-        result, c0 = {}, 0
-        heads = self.model_params['output_heads']
-        for key in self.target_keys:
-            c = heads[key]['channels']
-            result[key] = np.squeeze(full[:, c0:c0 + c])
-            c0 += c
-        return result

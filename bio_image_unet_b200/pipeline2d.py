@@ -11,7 +11,11 @@ from . import tiling
 
 
 def to_device_stack(frames_np, device):
-    """(F, H, W) uint8 / uint16 / float32 host array -> device tensor, through pinned staging."""
+    """(F, H, W) uint8 / uint16 / float32 host array (numpy, or a torch tensor - ideally pinned) -> device tensor."""
+    if torch.is_tensor(frames_np):
+        if frames_np.dtype not in (torch.uint8, torch.uint16, torch.float32):
+            raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got {frames_np.dtype}')
+        return frames_np.contiguous().to(device, non_blocking=True)
     if frames_np.dtype not in (np.uint8, np.uint16, np.float32):
         raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got '
                         f'{frames_np.dtype}. Convert the stack (e.g. to uint16 or float32) before calling Predict.')
@@ -21,6 +25,22 @@ def to_device_stack(frames_np, device):
     except RuntimeError:
         pass
     return host.to(device, non_blocking=True)
+
+
+class PinnedOut:
+    """Reusable pinned host buffer for the final D2H copy of a result (grown on demand)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def fetch(self, t):
+        n = t.numel() * t.element_size()
+        if self.buf is None or self.buf.numel() < n:
+            self.buf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        host = self.buf[:n].view(t.dtype).view(t.shape)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host.numpy()
 
 
 class Normalizer2D:

@@ -1,2 +1,2 @@
 from .siam_unet import Siam_UNet  # noqa: F401
-from .predict import Predict  # noqa: F401
+from .predict import Predict, Session  # noqa: F401

@@ -47,3 +47,36 @@ def shard_range(n_items, rank, world_size):
     base, rem = divmod(n_items, world_size)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def zslab_plan(z_starts, patch_d, vol_z, world_size):
+    """Sharding of the z-rows of a 3D patch grid (the outermost loop of unet3d/predict.py:146,180) over ranks.
+
+    Returns one dict per rank: rows (lo, hi) = its z-rows; slab (a, b) = the input planes those rows touch; own
+    (lo, hi) = the output planes it stitches (the planes of its slab that no lower rank covers: the `own` ranges
+    partition [0, vol_z)); borrow = {higher rank: [z-rows]} whose patches reach down into `own` and must be received
+    before stitching. Rows never need to travel upwards: a rank's `own` starts where the previous rank's last row
+    ends."""
+    zs = [int(v) for v in z_starts]
+    n_z = len(zs)
+    rows = [shard_range(n_z, r, world_size) for r in range(world_size)]
+
+    def row_end(zi):
+        return min(vol_z, zs[zi] + patch_d)
+
+    plans = []
+    for lo, hi in rows:
+        if hi <= lo:
+            plans.append(dict(rows=(lo, hi), slab=(0, 0), own=(0, 0), borrow={}))
+            continue
+        a, b = zs[lo], row_end(hi - 1)
+        own_lo = min(max(a, row_end(lo - 1)) if lo > 0 else 0, b)
+        plans.append(dict(rows=(lo, hi), slab=(a, b), own=(own_lo, b), borrow={}))
+    for r, p in enumerate(plans):
+        if p['own'][1] <= p['own'][0]:
+            continue
+        for s in range(r + 1, world_size):
+            need = [zi for zi in range(*rows[s]) if zs[zi] < p['own'][1]]
+            if need:
+                p['borrow'][s] = need
+    return plans

@@ -39,37 +39,74 @@ class Session:
         self.engine = Engine(self.KINDS[network], params['state_dict'], params['n_filter'], params['in_channels'],
                              [('', self.out_channels, 'sigmoid')], precision=precision, device=self.device)
         self.tile_batch = None
-        self.fixed_lut = None          # set for 'first' / 'all' (stack-wide statistics)
+        self._budget_batch = None
+        self._graphs = {}
+        self.fixed_lut = None          # set by Predict for 'first' / 'all' (stack-wide statistics incl. other ranks)
         self.last = {}
         self._pin, self._streams, self._dev_in = {}, None, None
 
     def _ensure_plan(self, total_tiles):
-        if self.tile_batch is None or (total_tiles < self.tile_batch):
-            self.tile_batch = P.pick_tile_batch(self.engine, self.resize_dim, max(1, total_tiles), self.workspace_bytes)
+        """Tile batch of the engine plan: min(tiles of the job, what the workspace budget holds). The plan only grows
+        between calls; it shrinks when a later job is at most half the planned batch (padding a 25-tile image to a
+        200-tile batch would cost 8x), never for the shorter tail chunk of a movie (run_tiles pads that one)."""
+        total_tiles = max(1, int(total_tiles))
+        if self._budget_batch is None:
+            per_tile = self.engine.plan(1, self.resize_dim)
+            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
+        target = min(total_tiles, self._budget_batch)
+        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
+            self.engine.plan(target, self.resize_dim)
+            self.tile_batch = target
+            self._graphs = {}
 
-    def normalise_device(self, frames_dev):
+    def stack_lut(self, frames, chunk_frames, reduce=None, first_frame=None):
+        """LUT of the 'first' / 'all' modes for a WHOLE integer stack (host or device, any length): bounds from frame 0
+        / the whole stack, min / max from the whole stack (unet/predict.py:132-147). The stack is histogrammed chunk
+        by chunk; `reduce` sums the totals over ranks; `first_frame` is frame 0 of the global stack when this rank's
+        `frames` do not start there. Per-bin totals are kept in 64 bits and must fit the kernels' 32-bit counters."""
+        dev = self.device
+        total = torch.zeros((1, P.E.HIST_BINS), dtype=torch.int64, device=dev)
+        for s0 in range(0, len(frames), max(1, chunk_frames)):
+            chunk = frames[s0:s0 + chunk_frames]
+            chunk = chunk.to(dev) if torch.is_tensor(chunk) else P.to_device_stack(chunk, dev)
+            total += P.E.hist_sum(P.E.histogram(chunk.contiguous())).to(torch.int64) & 0xffffffff
+        if reduce is not None:
+            total = reduce(total)
+        if int(total.max().item()) >= 2 ** 32:
+            raise OverflowError('a single intensity value occurs in more than 2**32 pixels of the stack: the stack-wide '
+                                "histogram of normalization_mode 'first' / 'all' does not fit its 32-bit counters")
+        total = total.to(torch.int32)
+        if self.normalization_mode == 'all':
+            bounds = total
+        else:
+            f0 = frames[0:1] if first_frame is None else first_frame
+            f0 = f0.to(dev) if torch.is_tensor(f0) else P.to_device_stack(f0, dev)
+            bounds = P.E.histogram(f0.contiguous())
+        lut, _ = P.E.norm_lut(bounds, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
+        return lut
+
+    def normalise_device(self, frames_dev, lut=None):
         if frames_dev.dtype == torch.float32:
             # float stacks: exact float32 percentiles by radix select; 'first' / 'all' need the whole stack in one call
             u8, f32, _ = P.E.normalize_f32(frames_dev.contiguous(), self.normalization_mode, self.clip_threshold[0],
                                            self.clip_threshold[1], self.invert, want_f32=True)
             self.last_norm_f32 = f32
             return u8
-        if self.fixed_lut is not None:
-            return P.E.apply_lut(frames_dev, self.fixed_lut)
-        if self.normalization_mode != 'single':
-            hist = P.E.histogram(frames_dev)
-            total = P.E.hist_sum(hist)
-            bounds = total if self.normalization_mode == 'all' else hist[0:1].contiguous()
-            lut, _ = P.E.norm_lut(bounds, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
+        lut = lut if lut is not None else self.fixed_lut
+        if lut is None and self.normalization_mode != 'single':     # the stack given here IS the whole stack
+            lut = self.stack_lut(frames_dev, max(1, frames_dev.shape[0]))
+        if lut is not None:
             return P.E.apply_lut(frames_dev, lut)
         return P.Normalizer2D('single', self.clip_threshold, self.invert)(frames_dev)
 
-    def predict_device(self, frames_dev, keep=False):
-        """(F, H, W) uint8/uint16 device tensor -> (F, C, H, W) uint8 device tensor."""
+    def predict_device(self, frames_dev, keep=False, lut=None, planned=False):
+        """(F, H, W) uint8/uint16/float32 device tensor -> (F, C, H, W) uint8 device tensor. `lut`: stack-wide LUT when
+        the frames are one chunk of a longer stack ('first' / 'all'); `planned`: the caller already sized the plan."""
         f, h, w = frames_dev.shape
-        n_x, n_y, _, _ = P.tiling.grid_2d(h, w, self.resize_dim, self.add_tile)
-        self._ensure_plan(f * n_x * n_y)
-        norm = self.normalise_device(frames_dev)
+        if not planned:
+            n_x, n_y, _, _ = P.tiling.grid_2d(h, w, self.resize_dim, self.add_tile)
+            self._ensure_plan(f * n_x * n_y)
+        norm = self.normalise_device(frames_dev, lut)
         out, grid, tiles, res_tiles = P.predict_frames_2d(self.engine, norm, self.resize_dim, self.add_tile,
                                                           self.out_channels, self.tile_batch)
         if frames_dev.dtype == torch.float32:      # what the reference stores back into a float stack (:131)
@@ -90,11 +127,13 @@ class Session:
             self._pin[key] = buf
         return buf[:n].view(*shape)
 
-    def predict_movie(self, frames, chunk_frames=None, want_norm=False):
+    def predict_movie(self, frames, chunk_frames=None, want_norm=False, out_dev=None):
         """Pipelined prediction of a host (F, H, W) uint8/uint16 stack (numpy array or torch tensor, ideally
         pinned): the frames go through the device in chunks, and the H2D copy of chunk i+1 and the D2H copy of
         chunk i-1 run on their own streams while chunk i computes. Returns (result (F, C, H, W) uint8 numpy
-        array backed by a pinned buffer that the next call reuses, normalised frames (F, H, W) uint8 or None)."""
+        array backed by a pinned buffer that the next call reuses, normalised frames (F, H, W) uint8 or None).
+        With `out_dev` (a (F, C, H, W) uint8 device tensor) the stitched frames stay on the device (multi-GPU runs
+        gather them over NVLink before the one D2H copy on rank 0) and the first return value is `out_dev`."""
         if isinstance(frames, np.ndarray):
             if frames.dtype not in (np.uint8, np.uint16, np.float32):
                 raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got '
@@ -113,6 +152,10 @@ class Session:
         if is_float and self.normalization_mode != 'single':
             chunk_frames = f               # stack-wide float statistics are taken in one pass over the whole stack
         dev = self.device
+        lut = self.fixed_lut
+        if lut is None and not is_float and self.normalization_mode != 'single' and f > chunk_frames:
+            with torch.cuda.device(dev):   # stack-wide statistics first: the chunks must not use their own
+                lut = self.stack_lut(host, chunk_frames)
         with torch.cuda.device(dev):
             if self._streams is None:
                 self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
@@ -120,7 +163,7 @@ class Session:
             cur = torch.cuda.current_stream(dev)
             for st in self._streams:
                 st.wait_stream(cur)
-            out_host = self._pinned('out', (f, self.out_channels, h, w), torch.uint8)
+            out_host = self._pinned('out', (f, self.out_channels, h, w), torch.uint8) if out_dev is None else None
             norm_host = self._pinned('norm', (f, h, w), torch.float32 if is_float else torch.uint8) if want_norm else None
             pinned_in = host.is_pinned()
             key = (chunk_frames, h, w, host.dtype)
@@ -144,19 +187,22 @@ class Session:
                     ev_in[b].record(s_in)
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(ev_in[b])
-                    res = self.predict_device(dev_in[b][:n])
+                    res = self.predict_device(dev_in[b][:n], lut=lut, planned=True)
                     norm = self.last['norm'] if want_norm else None
+                    if out_dev is not None:
+                        out_dev[s0:s0 + n].copy_(res)
                     ev_done[b].record(s_comp)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_done[b])
-                    out_host[s0:s0 + n].copy_(res, non_blocking=True)
-                    res.record_stream(s_out)
+                    if out_dev is None:
+                        out_host[s0:s0 + n].copy_(res, non_blocking=True)
+                        res.record_stream(s_out)
                     if want_norm:
                         norm_host[s0:s0 + n].copy_(norm, non_blocking=True)
                         norm.record_stream(s_out)
             s_out.synchronize()
             cur.wait_stream(s_comp)
-        return out_host.numpy(), (norm_host.numpy() if want_norm else None)
+        return (out_host.numpy() if out_dev is None else out_dev), (norm_host.numpy() if want_norm else None)
 
     def close(self):
         if self.engine is not None:
@@ -252,10 +298,16 @@ class Predict:
         print('Predicting data ...') if self.show_progress and self.dist.rank == 0 else None
 
         result_local = self.__run(imgs, lo, hi, out_channels, workspace_gb, mutate_input, progress_notifier)
+        self.fallback_ops = self.session.engine.fallback_ops
         self.session.close()
         del self.session
 
-        imgs_result = self.dist.gather_frames(result_local, t_total, self.device)
+        if self.dist.multi:
+            # stitched uint8 slabs: NCCL send / recv over NVLink straight into rank 0's full-movie buffer, one D2H there
+            full = self.dist.gather_slabs(result_local, self.dist.shards(t_total))
+            imgs_result = None if full is None else full.cpu().numpy()
+        else:
+            imgs_result = result_local
         if imgs_result is not None:
             imgs_result = np.squeeze(imgs_result)
             save_as_tif(imgs_result, self.result_name, normalize=normalize_result)
@@ -283,8 +335,11 @@ class Predict:
                 raise NotImplementedError("float stacks with normalization_mode 'first' / 'all' are not sharded over ranks")
             chunk = max(n_local, 1)        # stack-wide float statistics: one pass over the whole stack on the device
         elif self.normalization_mode in ('first', 'all'):
-            ses.fixed_lut = self.__global_lut(imgs, lo, hi, chunk)
-        out = np.zeros((n_local, out_channels, h, w), dtype='uint8')
+            ses.fixed_lut = ses.stack_lut(imgs[lo:hi], chunk, reduce=self.dist.all_reduce_sum, first_frame=imgs[0:1])
+        # multi-GPU: the stitched frames stay in HBM until the gather (a device tensor under NCCL; gloo gathers from the host)
+        on_device = self.dist.multi and self._keep is None
+        out = torch.zeros((n_local, out_channels, h, w), dtype=torch.uint8, device=self.device) if on_device else \
+            np.zeros((n_local, out_channels, h, w), dtype='uint8')
         # super-chunks bound the pinned host buffers; inside one, copies and compute are pipelined
         frames_per_call = max(chunk, min(max(n_local, 1), (1 << 30) // max(h * w * max(out_channels, 2), 1)))
         starts = range(lo, hi, frames_per_call)
@@ -302,29 +357,16 @@ class Predict:
                     self._keep['patches'].append(ses.last['tiles'].cpu().numpy())
                     self._keep['result_patches'].append(ses.last['result_tiles'].cpu().numpy())
                 continue
-            res, norm = ses.predict_movie(imgs[s:e], chunk_frames=chunk, want_norm=want_norm)
+            res, norm = ses.predict_movie(imgs[s:e], chunk_frames=chunk, want_norm=want_norm,
+                                          out_dev=out[s - lo:e - lo] if on_device else None)
             if want_norm:
                 imgs[s:e] = norm                                # unet/predict.py:131 (cast back to the input dtype)
-            out[s - lo:e - lo] = res
+            if not on_device:
+                out[s - lo:e - lo] = res
         if self._keep is not None:   # test hook: what the reference's __split / __predict return
             self.patches = np.concatenate(self._keep['patches'])
             self.result_patches = np.concatenate(self._keep['result_patches'])
+        if self.dist.multi and not on_device:
+            out = torch.from_numpy(out)
+            out = out.to(self.device) if self.dist.backend == 'nccl' else out
         return out
-
-    def __global_lut(self, imgs, lo, hi, chunk):
-        """'first' / 'all': bounds from frame 0 / the whole stack, min/max from the whole stack
-        (unet/predict.py:132-147). Histograms are summed over chunks and over ranks."""
-        total = None
-        for s in range(lo, hi, chunk):
-            frames = P.to_device_stack(imgs[s:min(s + chunk, hi)], self.device)
-            part = P.E.hist_sum(P.E.histogram(frames))
-            total = part if total is None else total + part
-        if total is None:
-            total = torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32, device=self.device)
-        total = self.dist.all_reduce_sum(total)
-        if self.normalization_mode == 'all':
-            bounds = total
-        else:
-            bounds = P.E.histogram(P.to_device_stack(imgs[0:1], self.device))
-        lut, _ = P.E.norm_lut(bounds, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
-        return lut

@@ -1,2 +1,2 @@
 from .unet3d import UNet3D  # noqa: F401
-from .predict import Predict  # noqa: F401
+from .predict import Predict, Session  # noqa: F401

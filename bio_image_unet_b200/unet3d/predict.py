@@ -14,13 +14,137 @@ from ..utils import get_device, save_as_tif
 from .unet3d import UNet3D
 
 
+class Session:
+    """Reusable 3D predictor: checkpoint folded / packed once; ``predict(vol)`` runs a (Z, X, Y) uint8 / uint16 host
+    volume through normalise -> split -> forward -> mod-3 stitch and returns the uint8 result (on rank 0)."""
+
+    def __init__(self, model_params, resize_dim, invert=False, clip_threshold=(0., 99.8), add_patch=0, device='cuda:0',
+                 precision='tf32', workspace_gb=24.0, dist=None):
+        if len(resize_dim) != 3:
+            raise IndexError('tuple index out of range')      # the reference indexes resize_dim[2] (:123)
+        params = torch.load(model_params, map_location='cpu') if isinstance(model_params, str) else model_params
+        self.device = torch.device(device)
+        self.resize_dim, self.invert, self.clip_threshold, self.add_patch = resize_dim, invert, clip_threshold, add_patch
+        self.workspace_bytes = int(workspace_gb * 2 ** 30)
+        self.dist = dist if dist is not None else DistContext(False)
+        self.engine = Engine('unet3d', params['state_dict'], params['n_filter'], params['in_channels'],
+                             [('', params['out_channels'], 'sigmoid')],
+                             use_interpolation=params.get('use_interpolation', False), precision=precision,
+                             device=self.device)
+        self.tile_batch, self._budget_batch = None, None
+        self.exchanged_bytes = 0
+        self._out = P.PinnedOut()
+
+    def _plan(self, tile, n_tiles):
+        if self._budget_batch is None:
+            per_tile = self.engine.plan(1, tile)
+            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
+        target = min(max(1, n_tiles), self._budget_batch)
+        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
+            self.engine.plan(target, tile)
+            self.tile_batch = target
+        return self.tile_batch
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    def predict(self, vol, keep=False):
+        """Single process: the whole volume. Multi-GPU: the z-rows of the patch grid (the outermost loop of
+        unet3d/predict.py:146,180) are sharded contiguously; a rank uploads and normalises only the z-slab its rows
+        touch, predicts its patches, receives from the ranks above it the uint8 result patches of the z-rows that
+        reach down into its slab (their global patch index decides the mod-3 slot), stitches the output planes it
+        owns, and the slabs are gathered on rank 0 - all device to device."""
+        if vol.ndim == 2:
+            vol = np.expand_dims(vol, axis=0)
+        self.vol_shape = vol.shape
+        (self.N_z, self.N_x, self.N_y, self.Z_start, self.X_start, self.Y_start) = tiling.grid_3d(
+            self.vol_shape, self.resize_dim, self.add_patch)
+        self.N = self.N_x * self.N_y * self.N_z
+        d, h, w = (int(v) for v in self.resize_dim)
+        z, x, y = self.vol_shape
+        for starts, t, ext in ((self.Z_start, d, z), (self.X_start, h, x), (self.Y_start, w, y)):
+            P.check_starts(starts, t, ext)
+        dev = self.device
+        ctx = self.dist
+        zs = [int(v) for v in self.Z_start]
+        n_xy = self.N_x * self.N_y
+        plans = tiling.zslab_plan(zs, d, z, ctx.world)
+        rows = [p['rows'] for p in plans]
+        mine = plans[ctx.rank]
+        (r_lo, r_hi), (a, b), (own_lo, own_hi) = mine['rows'], mine['slab'], mine['own']
+        # global percentile normalisation: every rank histograms the planes it owns, one all-reduce, same LUT everywhere
+        if b > a:
+            slab_dev = P.to_device_stack(vol[a:b], dev)
+            part = P.E.hist_sum(P.E.histogram(slab_dev[own_lo - a:own_hi - a].contiguous())) if own_hi > own_lo else None
+        else:
+            slab_dev, part = None, None
+        if part is None:
+            part = torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32, device=dev)
+        total = part.to(torch.int64) & 0xffffffff
+        total = ctx.all_reduce_sum(total)
+        if ctx.multi and int(total.max().item()) >= 2 ** 32:
+            raise OverflowError('a single intensity value occurs in more than 2**32 voxels: the global histogram does '
+                                'not fit its 32-bit counters')
+        total = total.to(torch.int32)
+        lut, _ = P.E.norm_lut(total, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
+        n_local = (r_hi - r_lo) * n_xy
+        if n_local > 0:
+            norm = P.E.apply_lut(slab_dev, lut)                                  # (b - a, X, Y) uint8
+            del slab_dev
+            patches = P.E.gather_tiles(norm.view(1, b - a, x, y), [v - a for v in zs[r_lo:r_hi]], self.X_start,
+                                       self.Y_start, (d, h, w), 0)
+            tile_batch = self._plan((d, h, w), n_local)
+            res_local, _ = P.run_tiles(self.engine, patches.reshape(n_local, 1, d, h, w), tile_batch)
+            res_local = res_local.reshape(n_local, d, h, w)
+        else:
+            patches = torch.zeros((0, d, h, w), dtype=torch.uint8, device=dev)
+            res_local = torch.zeros((0, d, h, w), dtype=torch.uint8, device=dev)
+
+        # rows of higher ranks that reach into a lower rank's slab travel down (NCCL send / recv of uint8 patches)
+        sends, recvs, extra_rows = [], [], []
+        if ctx.multi:
+            for r in range(ctx.rank):
+                need = plans[r]['borrow'].get(ctx.rank)
+                if need:
+                    i0, i1 = (need[0] - r_lo) * n_xy, (need[-1] + 1 - r_lo) * n_xy
+                    sends.append((r, res_local[i0:i1]))
+            for s in range(ctx.rank + 1, ctx.world):
+                need = mine['borrow'].get(s)
+                if need:
+                    buf = torch.empty((len(need) * n_xy, d, h, w), dtype=torch.uint8, device=dev)
+                    recvs.append((s, buf))
+                    extra_rows += need
+            ctx.exchange(sends, recvs)
+            self.exchanged_bytes = sum(int(t.numel()) for _, t in sends) + sum(int(t.numel()) for _, t in recvs)
+        # stitch the planes this rank owns from its own rows + the borrowed ones (consecutive rows r_lo .. r_lo + k - 1:
+        # their local patch index is the global one minus r_lo * N_x * N_y, which only relabels the three slots)
+        if own_hi > own_lo:
+            assert extra_rows == list(range(r_hi, r_hi + len(extra_rows)))
+            tiles = torch.cat([res_local] + [t for _, t in recvs]) if recvs else res_local
+            st_rows = list(range(r_lo, r_hi + len(extra_rows)))
+            st = P.E.stitch_mod3_u8(tiles, (own_hi - own_lo, x, y), [zs[zi] - own_lo for zi in st_rows], self.X_start,
+                                    self.Y_start, (d, h, w))
+        else:
+            st = torch.zeros((0, x, y), dtype=torch.uint8, device=dev)
+        if keep:       # test hook: what the reference's __split / __predict return (gathered on rank 0)
+            bounds_p = [(lo * n_xy, hi * n_xy) for lo, hi in rows]
+            allp, allr = ctx.gather_slabs(patches.reshape(n_local, d, h, w), bounds_p), ctx.gather_slabs(res_local, bounds_p)
+            if allp is not None:
+                self.patches, self.result_patches = allp.cpu().numpy(), allr.cpu().numpy()
+        full = ctx.gather_slabs(st, [p['own'] for p in plans], n_total=z) if ctx.multi else st
+        return None if full is None else self._out.fetch(full)
+
+
 class Predict:
     """Prediction of movies or 3D stacks with 3D U-Net (constructor surface of unet3d/predict.py:52-55).
 
     `normalization_mode` is accepted and unused, as in the reference: percentiles are always taken over the whole
     volume (unet3d/predict.py:109-117). Engine-only keyword arguments as in unet.Predict; with `distributed=True`
-    the patch list is sharded over ranks (contiguous ranges of the z -> x -> y ordered list), the intensity
-    histogram is all-reduced, and rank 0 gathers the uint8 patches and stitches.
+    the z-rows of the patch grid are sharded over ranks: each rank uploads only its z-slab, the intensity histogram
+    is all-reduced, boundary patches are exchanged point to point, every rank stitches the planes it owns and rank
+    0 gathers the uint8 slabs (all device to device).
     """
 
     def __init__(self, vol, result_name, model_params, network=UNet3D, resize_dim=(512, 512),
@@ -48,59 +172,20 @@ class Predict:
         if len(self.vol_shape) == 2:
             vol = np.expand_dims(vol, axis=0)
             self.vol_shape = vol.shape
-        if len(resize_dim) != 3:
-            raise IndexError('tuple index out of range')      # the reference indexes resize_dim[2] (:123)
 
         self.model_params = torch.load(model_params, map_location='cpu')
-        use_interp = self.model_params.get('use_interpolation', False)
-        self.engine = Engine('unet3d', self.model_params['state_dict'], self.model_params['n_filter'],
-                             self.model_params['in_channels'], [('', self.model_params['out_channels'], 'sigmoid')],
-                             use_interpolation=use_interp, precision=precision, device=self.device)
-
-        (self.N_z, self.N_x, self.N_y, self.Z_start, self.X_start, self.Y_start) = tiling.grid_3d(
-            self.vol_shape, resize_dim, add_patch)
-        self.N = self.N_x * self.N_y * self.N_z
+        ses = Session(self.model_params, resize_dim, invert, clip_threshold, add_patch, self.device, precision,
+                      workspace_gb, self.dist)
         print('Predicting data ...') if self.progress_bar and self.dist.rank == 0 else None
-
-        vol_result = self.__run(vol, workspace_gb, keep_intermediates, progress_notifier)
-        self.engine.close()
-        del self.engine
+        vol_result = ses.predict(vol, keep=keep_intermediates)
+        for k in ('N_z', 'N_x', 'N_y', 'Z_start', 'X_start', 'Y_start', 'N'):
+            setattr(self, k, getattr(ses, k))
+        if keep_intermediates and hasattr(ses, 'patches'):
+            self.patches, self.result_patches = ses.patches, ses.result_patches
+        self.fallback_ops = ses.engine.fallback_ops
+        ses.close()
+        del ses
         if vol_result is not None:
             save_as_tif(np.squeeze(vol_result), self.result_name, normalize=normalize_result)
         del self.model_params
         torch.cuda.empty_cache()
-
-    def __run(self, vol, workspace_gb, keep, progress_notifier):
-        d, h, w = (int(v) for v in self.resize_dim)
-        z, x, y = self.vol_shape
-        for starts, t, ext in ((self.Z_start, d, z), (self.X_start, h, x), (self.Y_start, w, y)):
-            P.check_starts(starts, t, ext)
-        dev = self.device
-        # global percentile normalisation: every rank histograms its z-slab, one all-reduce, identical LUT everywhere
-        vol_dev = P.to_device_stack(vol, dev)
-        zlo, zhi = self.dist.shard(z)
-        part = P.E.hist_sum(P.E.histogram(vol_dev[zlo:zhi])) if zhi > zlo else \
-            torch.zeros((1, P.E.HIST_BINS), dtype=torch.int32, device=dev)
-        total = self.dist.all_reduce_sum(part)
-        lut, _ = P.E.norm_lut(total, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
-        norm = P.E.apply_lut(vol_dev, lut)                                       # (Z, X, Y) uint8
-        del vol_dev
-        patches = P.E.gather_tiles(norm.view(1, z, x, y), self.Z_start, self.X_start, self.Y_start, (d, h, w), 0)
-        # this rank's contiguous share of the patch list
-        lo, hi = self.dist.shard(self.N)
-        mine = patches[lo:hi].reshape(hi - lo, 1, d, h, w)
-        if hi > lo:
-            tile_batch = P.pick_tile_batch(self.engine, (d, h, w), hi - lo, int(workspace_gb * 2 ** 30))
-            res_local, _ = P.run_tiles(self.engine, mine, tile_batch)
-            res_local = res_local.reshape(hi - lo, d, h, w)
-        else:
-            res_local = torch.zeros((0, d, h, w), dtype=torch.uint8, device=dev)
-        res_all = self.dist.gather_frames(res_local.cpu().numpy(), self.N, dev)
-        if keep:
-            self.patches = patches.cpu().numpy()
-            self.result_patches = res_all
-        if res_all is None:
-            return None
-        st = P.E.stitch_mod3_u8(torch.from_numpy(res_all).to(dev), (z, x, y), self.Z_start, self.X_start, self.Y_start,
-                                (d, h, w))
-        return st.cpu().numpy()

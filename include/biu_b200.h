@@ -76,9 +76,11 @@ int biu_net_set_force_direct(biu_net* net, int on);
 /* Test hook: 0 = run MaxPool2d as its own kernel instead of fusing it into the preceding block's epilogue
  * (default 1; both give bit-identical activations). */
 int biu_net_set_fuse_pool(biu_net* net, int on);
-/* Experimental: 1 = run the first block (1 input channel, bf16 mode) as an im2col GEMM on tcgen05 (first_tc.cu)
- * instead of the CUDA-core kernel. Parity-tested, but measured slower (2.5 vs 1.7 ms on cfg 2), hence default 0. */
-int biu_net_set_first_tc(biu_net* net, int on);
+/* Number of convolution / transposed-convolution / gate ops of the most recent biu_net_forward that a tensor-core
+ * mode (bf16 / tf32) had to run on the CUDA-core kernels because the tile shape is outside what the tcgen05 kernels
+ * take (planes narrower than 8 px, ...). 0 in the exact-fp32 mode's sense of "as requested"; the Python Predict
+ * classes turn a non-zero count into a RuntimeWarning (the result is the same, the speed is not). */
+int biu_net_fallback_ops(biu_net* net);
 /* Test hook (process-wide): 0 = run the narrow (Cout <= 32) 3x3 blocks on the halo-tile kernel instead of the
  * row-streaming folded-tap kernel (default 1; results agree to fp32 summation order); 2 = row kernel with its two
  * pipelines per CTA forced on even for workloads with few work items (they are only chosen for large batches). */

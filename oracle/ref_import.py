@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference package from /root/reference (authoring container only).
+"""Import the UNMODIFIED reference package: from /root/reference in the authoring container, else from the
+git-ignored install baseline/_ref that __graft_entry__.build() makes (that copy travels to the GPU box, where it is
+the CPU arm of bench.py: `--impl reference` and `cpu_baseline`, kind "reference").
 
 The reference needs tifffile, skimage, albumentations, matplotlib and napari at import time; none is installed
 here. tifffile gets an in-memory stand-in (the Predict classes read/write through it); the other four are only
 touched by training / GUI code and get attribute-swallowing stubs. Test infrastructure: never imported by the
-product package and never used on the GPU box (the reference tree does not travel).
+product package; only tests/golden/make_golden.py and bench.py's CPU legs use it.
 """
 import os
 import sys
@@ -11,7 +13,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('BIU_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pick_root():
+    for cand in (os.environ.get('BIU_REFERENCE_ROOT'), '/root/reference', os.path.join(_REPO, 'baseline', '_ref')):
+        if cand and os.path.isdir(os.path.join(cand, 'bio_image_unet')):
+            return cand
+    return os.environ.get('BIU_REFERENCE_ROOT', '/root/reference')
+
+
+REFERENCE_ROOT = _pick_root()
 
 TIFF_STORE = {}   # filename -> ndarray (what the reference "wrote" / will "read")
 

@@ -18,8 +18,15 @@ from tests import _golden  # noqa: E402
 
 def main(out_dir):
     rank, local = int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
-    torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    world = int(os.environ['WORLD_SIZE'])
+    if torch.cuda.device_count() >= world:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:       # 1-GPU box: both ranks share cuda:0, collectives go through gloo (NCCL refuses two ranks on a device)
+        local = local % torch.cuda.device_count()
+        torch.cuda.set_device(local)
+        dist.init_process_group('gloo')
+    print(f'[dist] rank {rank}: cuda:{local}, backend {dist.get_backend()}', flush=True)
     from bio_image_unet_b200.multi_output_unet3d import Predict as PredictMO
     from bio_image_unet_b200.siam_unet import Predict as PredictSiam
     from bio_image_unet_b200.unet import Predict as PredictUnet
@@ -66,6 +73,25 @@ def main(out_dir):
         same = np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= 1
         print(f'[dist] unet3d_overlap: distributed within 1 LSB of the reference golden: {same}')
         ok &= bool(same)
+    # ---- unet3d, several z-rows per rank with overlap: boundary patches travel between ranks, every rank stitches
+    #      its own planes; must equal the single-process run bit for bit ----
+    from bio_image_unet_b200.unet3d import UNet3D
+    torch.manual_seed(5)
+    sd3 = UNet3D(n_filter=4).state_dict()
+    ckpt = os.path.join(out_dir, f'u3d_syn_{rank}.pt')
+    torch.save({'state_dict': sd3, 'n_filter': 4, 'in_channels': 1, 'out_channels': 1}, ckpt)
+    vol = np.random.default_rng(11).integers(0, 3000, (44, 40, 48)).astype('uint16')
+    for add_patch in (1, 0):
+        kw = dict(resize_dim=(8, 16, 16), add_patch=add_patch, progress_bar=False, precision='fp32')
+        res_d = os.path.join(out_dir, f'u3d_syn{add_patch}_dist.tif')
+        p3 = Predict3D(vol.copy(), res_d, ckpt, distributed=True, **kw)
+        dist.barrier()
+        if rank == 0:
+            res_s = os.path.join(out_dir, f'u3d_syn{add_patch}_single.tif')
+            Predict3D(vol.copy(), res_s, ckpt, device=f'cuda:{local}', **kw)
+            same = np.array_equal(tiff.imread(res_d), tiff.imread(res_s))
+            print(f'[dist] unet3d synthetic add_patch={add_patch} (N_z={p3.N_z}): z-slab sharded == single: {same}')
+            ok &= bool(same)
     # ---- multi-output 3D (volumes sharded) ----
     g = _golden.load('mo3d_interp')
     ckpt = os.path.join(out_dir, f'mo_{rank}.pt')
@@ -81,7 +107,7 @@ def main(out_dir):
         ok &= bool(same)
     else:
         assert p.result is None
-    flag = torch.tensor([1 if ok else 0], device='cuda')
+    flag = torch.tensor([1 if ok else 0], device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
     if rank == 0:

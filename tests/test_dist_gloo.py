@@ -44,12 +44,40 @@ def _worker(rank, world, port, out_dir):
         fullv = ctx.gather_frames(vols[vlo:vhi], 3, torch.device('cpu'))
         if rank == 0:
             assert np.array_equal(fullv, vols)
+        # ragged slabs straight into place (3D: output planes owned per rank; trailing ranks may own nothing)
+        slabs = [(0, 5), (5, 7)]
+        vol = torch.arange(7 * 3 * 2, dtype=torch.uint8).reshape(7, 3, 2)
+        got = ctx.gather_slabs(vol[slabs[rank][0]:slabs[rank][1]].clone(), slabs, n_total=7)
+        assert (got is None) if rank else torch.equal(got, vol)
+        got = ctx.gather_slabs(vol[:7 if rank == 0 else 0].clone(), [(0, 7), (0, 0)], n_total=7)
+        assert (got is None) if rank else torch.equal(got, vol)
+        # point-to-point exchange (3D boundary patches travel from the higher to the lower rank)
+        if rank == 1:
+            ctx.exchange([(0, torch.full((4, 2), 9, dtype=torch.uint8))], [])
+        else:
+            buf = torch.zeros((4, 2), dtype=torch.uint8)
+            ctx.exchange([], [(1, buf)])
+            assert int(buf.sum()) == 72
         # Siam: a rank's first pair needs the last frame of the previous rank (read from the input, no exchange)
         prev = [(1 if i == 0 else i - 1) for i in range(lo, hi)]
         assert prev == ([1, 0, 1, 2] if rank == 0 else [3, 4, 5])
         open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
     finally:
         dist.destroy_process_group()
+
+
+def test_distributed_without_process_group_is_loud(monkeypatch):
+    """distributed=True with no process group: a warning single-process, an error under a multi-process launch (every
+    rank would otherwise predict the whole stack and write the same file)."""
+    import pytest
+    from bio_image_unet_b200.dist import DistContext
+    monkeypatch.delenv('WORLD_SIZE', raising=False)
+    with pytest.warns(RuntimeWarning):
+        ctx = DistContext(True)
+    assert not ctx.active and ctx.world == 1
+    monkeypatch.setenv('WORLD_SIZE', '2')
+    with pytest.raises(RuntimeError):
+        DistContext(True)
 
 
 def test_two_rank_sharding_gloo(tmp_path):

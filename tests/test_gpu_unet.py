@@ -446,47 +446,6 @@ def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, bat
     assert (got[1] - ref).abs().max().item() < tol, (got[1] - ref).abs().max().item()
 
 
-@pytest.mark.parametrize('kind,n_filter,tile,batch,in_float', [('unet2d', 32, (64, 96), 2, False), ('unet2d', 16, (48, 64), 3, False),
-                                                               ('unet3d', 16, (8, 16, 24), 2, False), ('mo3d', 32, (8, 24, 16), 1, True)])
-def test_first_block_tensor_core_matches_cuda_core(kind, n_filter, tile, batch, in_float):
-    """First block (1 input channel) as an im2col GEMM on tcgen05 (bf16 mode) vs the CUDA-core kernel: the e1
-    activations agree to bf16 rounding of the weights / float inputs, the network output stays within tolerance."""
-    from bio_image_unet_b200.engine import Engine
-    from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
-    from bio_image_unet_b200.unet import Unet
-    from bio_image_unet_b200.unet3d import UNet3D
-    torch.manual_seed(41)
-    heads = [('', 1, 'sigmoid')]
-    if kind == 'unet2d':
-        sd, c1 = stress_state_dict(n_filter, seed=13), n_filter
-    elif kind == 'unet3d':
-        sd, c1 = UNet3D(n_filter=n_filter).state_dict(), n_filter // 2
-    else:
-        cfg = {'a': {'channels': 1, 'activation': 'sigmoid'}}
-        sd, c1, heads = MultiOutputUnet3D(1, cfg, n_filter, True).state_dict(), n_filter // 2, [('a', 1, 'sigmoid')]
-    g = torch.Generator().manual_seed(6)
-    x = torch.rand((batch, 1, *tile), generator=g) if in_float else torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
-    if kind == 'unet2d':                 # logits rescaled to unit variance (see TOL_STRESS)
-        sd = unit_logit_state_dict(n_filter, 13, x)
-    spec = dict(n_filter=n_filter, in_channels=1, heads=heads)
-    if kind == 'mo3d':
-        spec['use_interpolation'] = True
-    eng = Engine(kind, sd, precision='bf16', device='cuda:0', **spec)
-    eng.plan(batch, tile)
-    c1p = (c1 + 15) // 16 * 16
-    eng.set_first_tc(1)                 # experimental path, off by default
-    v_tc, _ = eng.forward(x.cuda(), want_val=True, want_u8=False)
-    e1_tc = eng.debug_activation('e1', c1p, 0).copy()
-    eng.set_first_tc(0)
-    v_cc, _ = eng.forward(x.cuda(), want_val=True, want_u8=False)
-    e1_cc = eng.debug_activation('e1', c1p, 0).copy()
-    scale = max(np.abs(e1_cc).max(), 1.0)
-    assert np.abs(e1_tc - e1_cc).max() <= 2 ** -6 * scale, np.abs(e1_tc - e1_cc).max()
-    assert c1 == c1p or np.abs(e1_tc[..., c1:]).max() == 0           # padded channels stay zero
-    assert (v_tc - v_cc).abs().max().item() < TOL_STRESS['bf16']
-    eng.close()
-
-
 @pytest.mark.parametrize('name', ['unet_f32_single', 'unet_f32_first_invert', 'unet_f32_all'])
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
 def test_predict_float32_stack_matches_reference_golden(name, precision, tmp_path):
