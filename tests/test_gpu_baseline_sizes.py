@@ -1,0 +1,239 @@
+"""Parity at the sizes the benchmark runs (BASELINE.json configs) - the kernel variants that large
+tiles and large batches select (both pipelines of the row kernel, the wide halo tiles, the 3D row kernel) are the ones
+compared with the CPU oracle here, on nets whose output spreads over the whole range:
+
+* cfg 1 in full through unet.Predict: 1024^2 uint16, 256^2 tiles, add_tile=1, Unet(32); fp32 / tf32 / bf16
+* cfg 2's tiles: 512^2, Unet(32), batch 150 (6 frames of 2048^2 through Session.predict_device) in bf16 and tf32
+* cfg 3: Siam_UNet(32, 'concat') 256^2 pairs (and one 512^2 pair inside a batch of 72)
+* cfg 4: UNet3D(16) 64x128x128 patches, batch 32
+* cfg 5: MultiOutputUnet3D(16, 3 sigmoid heads, interpolation) 64x256x256 patches, batch 8
+
+Reduced-precision gates: 1.5 x the error of the reference's own arithmetic at that precision (tests/_parity.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models as omodels
+from oracle import pipeline as opipe
+from tests import _parity
+from tests.test_gpu_unet import stress_state_dict, unit_logit_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(n, shape, seed0=0):
+    return np.stack([np.random.default_rng(seed0 + i).integers(0, 4096, shape).astype('uint16') for i in range(n)])
+
+
+def _blobs(shape, seed):
+    """Structured input: a few Gaussian blobs + noise, so that percentiles / clipping are non-degenerate."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:shape[0], 0:shape[1]].astype(np.float32)
+    img = rng.normal(300, 30, shape).astype(np.float32)
+    for _ in range(12):
+        cy, cx, s, a = rng.uniform(0, shape[0]), rng.uniform(0, shape[1]), rng.uniform(20, 90), rng.uniform(500, 3000)
+        img += a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
+    return img.clip(0, 65535).astype('uint16')
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# cfg 1
+# -------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def cfg1():
+    img = _blobs((1024, 1024), 1)
+    stages = {}
+    probe = opipe.split_2d(opipe.preprocess_stack(img[None].copy(), 'single', (0., 99.8), False), (256, 256), 1)[0]
+    sd = unit_logit_state_dict(32, 301, torch.from_numpy(probe[:4].copy()))
+    ref = opipe.unet_predict(img.copy(), sd, (256, 256), False, 'single', (0., 99.8), 1, stages)
+    return img, sd, ref, stages
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+def test_cfg1_full_predict_matches_oracle(cfg1, precision, tmp_path):
+    from bio_image_unet_b200 import tiff
+    from bio_image_unet_b200.unet import Predict
+    img, sd, ref, stages = cfg1
+    ckpt = str(tmp_path / 'm.pt')
+    torch.save({'state_dict': sd, 'n_filter': 32, 'in_channels': 1, 'out_channels': 1}, ckpt)
+    res = str(tmp_path / 'r.tif')
+    p = Predict(img.copy(), res, ckpt, resize_dim=(256, 256), add_tile=1, show_progress=False, device='cuda:0',
+                precision=precision, keep_intermediates=True)
+    assert (p.N_x, p.N_y) == (5, 5) and list(p.X_start) == [0, 192, 384, 576, 768]
+    assert np.array_equal(p.patches, stages['patches'])                      # normalisation + split: bit-exact
+    assert stages['result_patches'].std() > 40                               # the net is decisive, not 134..136
+    x = torch.from_numpy(stages['patches']).float() / 255
+    lsb = _parity.lsb_bound(omodels.unet_forward, precision, sd, x)
+    d = np.abs(p.result_patches.astype(np.int16) - stages['result_patches'].astype(np.int16))
+    assert d.max() <= lsb, (precision, d.max(), lsb)
+    out = tiff.imread(res)
+    st = opipe.stitch_mean_2d(p.result_patches, 1, (1024, 1024), (256, 256), stages['grid'])
+    assert np.array_equal(out, np.squeeze(st).astype('float16'))             # stitch: bit-exact
+    assert np.abs(out.astype(np.float32) - ref.astype(np.float32)).max() <= lsb
+    assert p.fallback_ops == 0 or precision == 'fp32'
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# cfg 2: the benched kernel variants (512^2 tiles, batch >= 148)
+# -------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['bf16', 'tf32'])
+def test_cfg2_tiles_in_a_full_batch_match_oracle(precision):
+    from bio_image_unet_b200.unet import Session
+    frames = _frames(6, (2048, 2048))
+    frames[0] = _blobs((2048, 2048), 2)
+    probe = torch.randint(0, 256, (1, 1, 512, 512), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
+    sd = unit_logit_state_dict(32, 302, probe)
+    ses = Session({'state_dict': sd, 'n_filter': 32, 'in_channels': 1, 'out_channels': 1}, resize_dim=(512, 512),
+                  add_tile=1, device='cuda:0', precision=precision, workspace_gb=40.0)
+    out = ses.predict_device(torch.from_numpy(frames).cuda(), keep=True)
+    assert ses.tile_batch == 150 and ses.engine.fallback_ops == 0
+    tiles, res = ses.last['tiles'].cpu(), ses.last['result_tiles'].cpu()
+    # normalised tiles of two frames against the oracle (bit-exact), four tiles of the batch through the oracle net
+    for f in (0, 5):
+        want = opipe.split_2d(opipe.preprocess_stack(frames[f:f + 1].copy(), 'single', (0., 99.8), False), (512, 512), 1)[0]
+        assert np.array_equal(tiles[25 * f:25 * (f + 1)].numpy(), want)
+    pick = [0, 12, 77, 149]
+    x = tiles[pick].float() / 255
+    with torch.no_grad():
+        ref = omodels.unet_forward(sd, x)[0]
+    ref_u8 = (ref.numpy() * 255).astype('uint8')
+    lsb = _parity.lsb_bound(omodels.unet_forward, precision, sd, x, ref=ref)
+    d = np.abs(res[pick].numpy().astype(np.int16) - ref_u8.astype(np.int16))
+    assert ref_u8.std() > 40 and d.max() <= lsb, (precision, d.max(), lsb)
+    _, mean_b = _parity.bound(omodels.unet_forward, precision, sd, x, ref=ref)
+    assert d.mean() <= 255 * mean_b + 0.5, (d.mean(), mean_b)
+    # stitch of the whole chunk: bit-exact from the engine's own tiles
+    grid = opipe.grid_2d((2048, 2048), (512, 512), 1)
+    st = opipe.stitch_mean_2d(res[:25].numpy(), 1, (2048, 2048), (512, 512), grid)
+    assert np.array_equal(out[0, 0].cpu().numpy(), np.squeeze(st))
+    ses.close()
+
+
+def test_session_multi_chunk_first_and_all_use_stack_wide_statistics():
+    """a movie longer than one chunk must be normalised with the statistics of the whole stack
+    (unet/predict.py:132-147), not of each chunk."""
+    from bio_image_unet_b200.unet import Session
+    rng = np.random.default_rng(3)
+    movie = np.stack([rng.integers(0, 600 + 500 * i, (96, 128)).astype('uint16') for i in range(5)])
+    sd = stress_state_dict(4, 3)
+    for mode in ('first', 'all'):
+        stages = {}
+        ref = opipe.unet_predict(movie.copy(), sd, (64, 64), False, mode, (1., 99.), 1, stages)
+        ses = Session({'state_dict': sd, 'n_filter': 4, 'in_channels': 1, 'out_channels': 1}, resize_dim=(64, 64),
+                      add_tile=1, normalization_mode=mode, clip_threshold=(1., 99.), device='cuda:0', precision='fp32')
+        out, norm = ses.predict_movie(movie.copy(), chunk_frames=2, want_norm=True)
+        want_norm = opipe.preprocess_stack(movie.copy(), mode, (1., 99.), False).astype('uint8')
+        assert np.array_equal(norm, want_norm), mode
+        assert np.abs(out[:, 0].astype(np.int16) - ref.astype(np.int16)).max() <= 1, mode
+        ses.close()
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# cfg 3: Siam
+# -------------------------------------------------------------------------------------------------------------------
+def _stress_module_sd(module, seed, head_keys=('final.0',)):
+    """Kaiming conv weights + randomised BN statistics on any of the product's module classes."""
+    g = torch.Generator().manual_seed(seed)
+    sd = module.state_dict()
+    for k, v in sd.items():
+        if k.endswith('num_batches_tracked') or not v.is_floating_point():
+            continue
+        if v.dim() >= 4:
+            fan_in = v[0].numel() if not k.startswith('up') or k.count('.') > 1 else v.shape[0]
+            sd[k] = torch.randn(v.shape, generator=g) * (2.0 / 1.01 / fan_in) ** 0.5
+        elif k.endswith('running_var') or k.endswith('.1.weight'):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith('.bias') and v.dim() == 1 and not k.endswith('.1.bias'):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.05
+        else:
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+    return sd
+
+
+def _unit_logits(sd, logits, w_key, b_key):
+    sd[w_key] = sd[w_key] / logits.std()
+    sd[b_key] = (sd[b_key] - logits.mean()) / logits.std()
+    return sd
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('tile,batch,pick', [((256, 256), 4, [0, 3]), ((512, 512), 72, [71])])
+def test_cfg3_siam_pairs_match_oracle(precision, tile, batch, pick):
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.siam_unet import Siam_UNet
+    if precision == 'fp32' and batch > 4:
+        pytest.skip('the exact-fp32 CUDA-core mode is covered at 256^2')
+    g = torch.Generator().manual_seed(21)
+    cur = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
+    prev = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
+    torch.manual_seed(1)
+    sd = _stress_module_sd(Siam_UNet(n_filter=32, mode='concat'), 31)
+    xc, xp = cur[pick].float() / 255, prev[pick].float() / 255
+    with torch.no_grad():
+        _, lg = omodels.siam_forward(sd, xc[:1, :, :128, :128], xp[:1, :, :128, :128], 'concat')
+        sd = _unit_logits(sd, lg, 'final.0.weight', 'final.0.bias')
+        ref = omodels.siam_forward(sd, xc, xp, 'concat')[0]
+    eng = Engine('siam2d', sd, 32, 1, [('', 1, 'sigmoid')], siam_mode='concat', precision=precision, device='cuda:0')
+    eng.plan(batch, tile)
+    val, _ = eng.forward(cur.cuda(), prev.cuda(), want_val=True)
+    fwd = lambda sd_, c_, p_: omodels.siam_forward(sd_, c_, p_, 'concat')                  # noqa: E731
+    assert ref.std() > 0.15
+    _parity.check(val[pick], ref, fwd, precision, sd, xc, xp, what=f'siam {tile}')
+    assert eng.fallback_ops == 0 or precision == 'fp32'
+    eng.close()
+
+
+# -------------------------------------------------------------------------------------------------------------------
+# cfg 4 / cfg 5: 3D patches at the benched sizes
+# -------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+def test_cfg4_unet3d_patch_matches_oracle(precision):
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.unet3d import UNet3D
+    batch, tile, pick = 32, (64, 128, 128), [0, 31]
+    g = torch.Generator().manual_seed(41)
+    x_u8 = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
+    torch.manual_seed(2)
+    sd = _stress_module_sd(UNet3D(n_filter=16), 41)
+    x = x_u8[pick].float() / 255
+    with torch.no_grad():
+        _, lg = omodels.unet3d_forward(sd, x[:1, :, :16, :32, :32])
+        sd = _unit_logits(sd, lg, 'final.weight', 'final.bias')
+        ref = omodels.unet3d_forward(sd, x)[0]
+    eng = Engine('unet3d', sd, 16, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
+    eng.plan(batch, tile)
+    val, u8 = eng.forward(x_u8.cuda(), want_val=True, want_u8=True)
+    fwd = lambda sd_, x_: omodels.unet3d_forward(sd_, x_)                                  # noqa: E731
+    assert ref.std() > 0.15
+    _, _, tol = _parity.check(val[pick], ref, fwd, precision, sd, x, what='unet3d 64x128x128')
+    d = np.abs(u8[pick].cpu().numpy().astype(np.int16) - (ref.numpy() * 255).astype('uint8').astype(np.int16))
+    assert d.max() <= 1 + int(np.ceil(tol * 255))
+    assert eng.fallback_ops == 0
+    eng.close()
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'bf16'])
+def test_cfg5_mo3d_patch_matches_oracle(precision):
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
+    heads = {f'h{i}': {'channels': 1, 'activation': 'sigmoid'} for i in range(3)}
+    batch, tile, pick = 8, (64, 256, 256), [7]
+    g = torch.Generator().manual_seed(51)
+    xs = torch.rand((batch, 1, *tile), generator=g)
+    torch.manual_seed(3)
+    sd = _stress_module_sd(MultiOutputUnet3D(1, heads, 16, True), 51)
+    x = xs[pick]
+
+    def fwd(sd_, x_):
+        o = omodels.mo3d_forward(sd_, x_, heads, True)
+        return torch.cat([o[k].float() for k in heads], 1)
+    with torch.no_grad():
+        ref = fwd(sd, x)
+    eng = Engine('mo3d', sd, 16, 1, [(k, 1, 'sigmoid') for k in heads], use_interpolation=True, precision=precision,
+                 device='cuda:0')
+    eng.plan(batch, tile)
+    val, _ = eng.forward(xs.cuda(), want_val=True, want_u8=False)
+    _parity.check(val[pick], ref, fwd, precision, sd, x, what='mo3d 64x256x256')
+    assert eng.fallback_ops == 0
+    eng.close()

@@ -2,21 +2,24 @@
 unmodified reference, plus bit-exactness of the 3D / ramp stitch kernels against the CPU oracle.
 
 Integer stages (tile indices, uint8 / float32 tiles, stitches) are bit-exact. The network forward is compared in
-the exact-fp32 mode at +-1 LSB of the reference's uint8 quantisation (float heads: 2e-4), and in the tf32 / bf16
-tensor-core modes within the bounds their arithmetic allows on these stress-initialised nets (see test_gpu_unet).
+the exact-fp32 mode at +-1 LSB of the reference's uint8 quantisation (float heads: 1e-4 of the head's range), and in
+the tf32 / bf16 tensor-core modes against 1.5x the error of the reference's own arithmetic at that precision on the
+fixture's weights and tiles (tests/_parity.py: torch.autocast(bfloat16) / operand-rounded TF32) - no constants.
 """
 import numpy as np
 import pytest
 import torch
 
+from oracle import models as omodels
 from oracle import pipeline as opipe
-from tests import _golden
+from tests import _golden, _parity
 
 pytestmark = pytest.mark.gpu
 
-LSB = {'fp32': 1, 'tf32': 4, 'bf16': 25}
-LSB_SIAM = {'fp32': 1, 'tf32': 10, 'bf16': 70}     # measured 7 / 61 on the siam_concat net (23 + 9 layers, logit sigma ~ 8)
-FLOAT_TOL = {'fp32': 2e-4, 'tf32': 2e-2, 'bf16': 1.5e-1}
+
+
+def _u8(t):
+    return torch.from_numpy(np.ascontiguousarray(t)).float() / 255
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
@@ -36,11 +39,17 @@ def test_siam_predict_matches_reference_golden(name, precision, tmp_path):
     assert (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
     assert np.array_equal(p.X_start, g['X_start']) and np.array_equal(p.Y_start, g['Y_start'])
     assert np.array_equal(p.patches, g['patches'])                    # (T, N, 2, th, tw): ch0 current, ch1 previous
-    # 'corr' sums h*w products of two bf16-rounded embeddings on top of the usual chain: a little more headroom
-    lsb = LSB_SIAM[precision] + (10 if (name == 'siam_corr' and precision == 'bf16') else 0)
+    mode = str(g['siam_mode'])
+    th, tw = (int(v) for v in g['resize_dim'])
+    cur, prev = _u8(g['patches'][:, :, 0]).reshape(-1, 1, th, tw), _u8(g['patches'][:, :, 1]).reshape(-1, 1, th, tw)
+    fwd = lambda sd_, c_, p_: omodels.siam_forward(sd_, c_, p_, mode)                     # noqa: E731
+    sd = _golden.state_dict(g)
+    lsb = _parity.lsb_bound(fwd, precision, sd, cur, prev)
     d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
-    assert d.max() <= lsb, d.max()
-    assert (d > 1).mean() < {'fp32': 1e-9, 'tf32': 0.02, 'bf16': 0.3}[precision]
+    assert d.max() <= lsb, (d.max(), lsb)
+    if precision != 'fp32':       # the error distribution, not only its tail, has to look like the reference arithmetic's
+        _, mean_b = _parity.bound(fwd, precision, sd, cur, prev)
+        assert d.mean() <= 255 * mean_b + 0.5, (d.mean(), mean_b)
     out = tiff.imread(res_file)
     assert out.dtype == np.uint8 and out.shape == g['result'].shape
     assert np.abs(out.astype(np.int16) - g['result'].astype(np.int16)).max() <= lsb
@@ -71,13 +80,16 @@ def test_unet3d_predict_matches_reference_golden(name, precision, tmp_path):
     for a, b in ((p.Z_start, g['Z_start']), (p.X_start, g['X_start']), (p.Y_start, g['Y_start'])):
         assert np.array_equal(a, b) and a.dtype == np.uint16
     assert np.array_equal(p.patches, g['patches'])
+    interp = bool('interp' in g and int(g['interp']))
+    fwd = lambda sd_, x_: omodels.unet3d_forward(sd_, x_, interp)                          # noqa: E731
+    lsb = _parity.lsb_bound(fwd, precision, _golden.state_dict(g), _u8(g['patches'])[:, None])
     d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
-    assert d.max() <= LSB[precision], d.max()
+    assert d.max() <= lsb, (d.max(), lsb)
     out = tiff.imread(res_file)
     assert out.dtype == np.float16
     grid = (p.N_z, p.N_x, p.N_y, p.Z_start, p.X_start, p.Y_start)
     assert np.array_equal(out, opipe.stitch_mod3(p.result_patches, g['vol'].shape, rd, grid).astype('float16'))
-    assert np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= LSB[precision]
+    assert np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= lsb
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32', 'bf16'])
@@ -97,10 +109,17 @@ def test_mo3d_predict_matches_reference_golden(name, precision, tmp_path):
     assert np.array_equal(p.patches, g['patches'])          # float32 normalisation + patch gather: bit-exact
     ref = _golden.sub(g, 'result')
     assert list(p.result.keys()) == list(_golden.MO3D_HEADS.keys())
-    for k in ref:
+    interp = bool(g['interp'])
+    fwd = lambda sd_, x_: omodels.mo3d_forward(sd_, x_, _golden.MO3D_HEADS, interp)        # noqa: E731
+    x = torch.from_numpy(g['patches']).reshape(-1, 1, *p.patch_size)
+    cb = _parity.per_channel_bound(fwd, precision, _golden.state_dict(g), x)               # heads of different scale
+    c0 = 0
+    for k, cfg in _golden.MO3D_HEADS.items():
         assert p.result[k].shape == ref[k].shape
-        err = np.abs(p.result[k] - ref[k]).max()
-        assert err <= FLOAT_TOL[precision], (k, err)
+        err = np.abs(p.result[k] - ref[k]).max()          # the blend is a convex combination: patch bounds carry over
+        bound = float(cb[c0:c0 + cfg['channels']].max()) + 2e-4
+        assert err <= bound, (k, err, bound)
+        c0 += cfg['channels']
 
 
 def test_norm_f32_single_mode_bit_exact():
@@ -199,7 +218,8 @@ def test_mo2d_predict_matches_reference_golden(name, precision, tmp_path):
     assert np.array_equal(p.X_start, g['X_start']) and np.array_equal(p.Y_start, g['Y_start'])
     assert np.array_equal(p.norm, g['norm'])
     assert np.array_equal(p.patches, g['patches'])
-    tol = {'fp32': 2e-3, 'tf32': 1e-2, 'bf16': 8e-2}[precision]       # stress net, outputs of magnitude ~1-10
+    fwd = lambda sd_, x_: omodels.mo2d_forward(sd_, x_, MO2D_HEADS)                        # noqa: E731
+    cb = _parity.per_channel_bound(fwd, precision, _golden.state_dict(g), torch.from_numpy(g['patches']).float()[:, None])
     c0 = 0
     info = opipe.mo2d_grid(g['imgs'].shape, tuple(int(v) for v in g['max_patch']), int(g['add_tile']))
     for k, cfg in MO2D_HEADS.items():
@@ -209,13 +229,9 @@ def test_mo2d_predict_matches_reference_golden(name, precision, tmp_path):
         got_rp = p.result_patches[:, c0:c0 + c]
 
         def close(a, b):
-            # linear heads: max-abs relative to the head's range. Sigmoid head of a stress net: the logit sigma is 3 to
-            # >100 here (mo2d_all_pad: the linear heads reach 259), so the few pixels on the decision boundary amplify
-            # any operand rounding (see test_gpu_unet.py) - 90 % of the pixels within tolerance, all of them in fp32
-            err = np.abs(a - b)
-            if cfg['activation'] == 'sigmoid' and precision != 'fp32':
-                return np.quantile(err, 0.9) <= tol
-            return err.max() <= tol * scale
+            # per head: 1.5 x what the reference's arithmetic at this precision does to that head on these weights
+            # (linear heads of the stress nets reach the hundreds; the sigmoid head stays in [0, 1])
+            return np.abs(a - b).max() <= float(cb[c0:c0 + c].max()) + 2e-3 * scale
         assert close(got_rp, ref_rp), (k, np.abs(got_rp - ref_rp).max(), scale)
         # stitch: the device kernel against the oracle's stitch of the engine's own (float16-rounded) patches
         st = opipe.mo2d_stitch(got_rp.astype(np.float16), c, g['imgs'].shape, info)
@@ -243,7 +259,10 @@ def test_nested_predict_matches_reference_golden(name, precision, tmp_path):
                    keep_intermediates=True)
     assert tuple(p.patch_size) == tuple(g['patch_size']) and (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
     assert np.array_equal(p.norm, g['norm']) and np.array_equal(p.patches, g['patches'])
-    tol = {'fp32': 2e-3, 'tf32': 1e-2, 'bf16': 8e-2}[precision]
+    depth = 3 if '3' in str(g['network']) else 4
+    ds = bool(int(g['deep_supervision']))
+    fwd = lambda sd_, x_: omodels.nested_forward(sd_, x_, MO2D_HEADS, depth, deep_supervision=ds)   # noqa: E731
+    cb = _parity.per_channel_bound(fwd, precision, _golden.state_dict(g), torch.from_numpy(g['patches']).float()[:, None])
     info = opipe.mo2d_grid(g['imgs'].shape, tuple(int(v) for v in g['max_patch']), int(g['add_tile']))
     c0 = 0
     for k, cfg in MO2D_HEADS.items():
@@ -252,11 +271,8 @@ def test_nested_predict_matches_reference_golden(name, precision, tmp_path):
         scale = max(1.0, np.abs(ref_rp).max())
         got_rp = p.result_patches[:, c0:c0 + c]
 
-        def close(a, b):      # same criteria as test_mo2d_predict_matches_reference_golden
-            err = np.abs(a - b)
-            if cfg['activation'] == 'sigmoid' and precision != 'fp32':
-                return np.quantile(err, 0.9) <= tol
-            return err.max() <= tol * scale
+        def close(a, b):      # same criterion as test_mo2d_predict_matches_reference_golden
+            return np.abs(a - b).max() <= float(cb[c0:c0 + c].max()) + 2e-3 * scale
         assert close(got_rp, ref_rp), (k, np.abs(got_rp - ref_rp).max(), scale)
         st = opipe.mo2d_stitch(got_rp.astype(np.float16), c, g['imgs'].shape, info)
         assert np.abs(p.result[k] - st).max() <= 1e-3 * scale, k

@@ -1,8 +1,10 @@
 """Parity of the 2D U-Net path on the GPU: engine forward vs the CPU oracle, and the whole Predict pipeline vs
 the golden fixtures produced by the unmodified reference.
 
-Tolerances (BASELINE.json north_star): fp32/TF32 mode max-abs 1e-3 on the sigmoid output, bf16 mode 1e-2;
-tile indices, uint8 tiles and the stitch are bit-exact.
+Tolerances (BASELINE.json north_star): fp32/TF32 mode max-abs 1e-3 on the sigmoid output, bf16 mode 1e-2 - asserted on
+PyTorch's default random init; on stress-initialised nets the reduced-precision modes are held to 1.5x the error of
+the reference's own arithmetic at that precision on the same weights and input (tests/_parity.py, oracle/yardstick.py).
+Tile indices, uint8 tiles and the stitch are bit-exact.
 """
 import os
 
@@ -12,20 +14,23 @@ import torch
 
 from oracle import models as omodels
 from oracle import pipeline as opipe
-from tests import _golden
+from tests import _golden, _parity
 
 pytestmark = pytest.mark.gpu
 
-# Stated tolerances (max-abs on the sigmoid output) — gate on PyTorch's default random init:
-TOL = {'fp32': 1e-3, 'tf32': 1e-3, 'bf16': 1e-2}
+# Stated tolerances (max-abs on the sigmoid output) - gate on PyTorch's default random init:
+TOL = _parity.NORTH_STAR
 # "Stress" regime (Kaiming weights, randomised BN statistics, logits rescaled to unit variance: every pixel sits on
-# the steep part of the sigmoid). Single-pass tf32 / bf16 operand rounding through 23 layers gives a logit error
-# of ~1 % / ~8 % of the logit sigma here (measured; the reference's own torch.autocast(bfloat16) shows the same
-# 7.7e-2) — the fp32 mode keeps the stated 1e-3, the reduced-precision modes get the bounds
-# their arithmetic allows.
-TOL_STRESS = {'fp32': 1e-3, 'tf32': 6e-3, 'bf16': 4e-2}
-# golden fixtures (nf=4 stress nets with logit sigma up to 3): allowance on the uint8-quantised tiles, in LSB
-LSB_GOLDEN = {'fp32': 1, 'tf32': 1 + 3, 'bf16': 1 + 24}
+# the steep part of the sigmoid): no constants - _parity.check / _parity.bound compare with the reference's own
+# reduced-precision arithmetic on the same weights (measured there: TF32 operand rounding 1.3e-3 .. 3.1e-3, bf16
+# autocast 1.3e-2 .. 2.7e-2 on these nets, growing with the number of pixels the maximum is taken over).
+
+
+def golden_lsb(forward, precision, sd, patches):
+    """Allowance on the uint8-quantised result tiles of a golden fixture, in LSB: 1 (truncation) + 1.5 x what the
+    reference's arithmetic at that precision moves the sigmoid on the fixture's own weights and tiles."""
+    x = torch.from_numpy(np.ascontiguousarray(patches)).float() / 255
+    return _parity.lsb_bound(forward, precision, sd, x)
 
 
 def stress_state_dict(n_filter, seed, head_gain=4.0):
@@ -75,17 +80,19 @@ def test_engine_forward_matches_oracle(precision, regime, n_filter, tile, batch)
     g = torch.Generator().manual_seed(7)
     tiles = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
     if regime == 'default':
-        sd, tol = default_state_dict(n_filter, seed=100 + n_filter), TOL[precision]
+        sd = default_state_dict(n_filter, seed=100 + n_filter)
     else:
-        sd, tol = unit_logit_state_dict(n_filter, 100 + n_filter, tiles), TOL_STRESS[precision]
+        sd = unit_logit_state_dict(n_filter, 100 + n_filter, tiles)
+    x = tiles.float() / 255
     with torch.no_grad():
-        ref, _ = omodels.unet_forward(sd, tiles.float() / 255)
+        ref, _ = omodels.unet_forward(sd, x)
     eng = Engine('unet2d', sd, n_filter, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
     eng.plan(batch, tile)
     val, u8 = eng.forward(tiles.cuda(), want_val=True, want_u8=True)
     torch.cuda.synchronize()
-    err = (val.cpu() - ref).abs().max().item()
-    assert err < tol, (precision, regime, err)
+    err, _, tol = _parity.check(val, ref, omodels.unet_forward, precision, sd, x, what=f'unet nf={n_filter} {regime}')
+    if regime == 'default':
+        assert err < TOL[precision], (precision, regime, err)
     # quantised output: trunc(sigmoid*255) within 1 LSB of the oracle's (+ the float tolerance in LSBs)
     ref_u8 = (ref.numpy() * 255).astype('uint8')
     d = np.abs(u8.cpu().numpy().astype(np.int16) - ref_u8.astype(np.int16))
@@ -171,8 +178,8 @@ def test_predict_matches_reference_golden(name, precision, tmp_path):
     assert np.array_equal(p.patches, g['patches'])
     if str(g['mode']) == 'single':
         assert np.array_equal(imgs, g['imgs_after'])
-    # forward: quantised result tiles within 1 LSB (+ float tolerance)
-    lsb = LSB_GOLDEN[precision]
+    # forward: quantised result tiles within 1 LSB (+ 1.5 x the reference's own reduced-precision error)
+    lsb = golden_lsb(omodels.unet_forward, precision, _golden.state_dict(g), g['patches'])
     d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
     assert d.max() <= lsb, d.max()
     # stitch: bit-exact given the engine's own tiles
@@ -285,14 +292,14 @@ def test_variant_forward_matches_oracle(precision, regime, network, n_filter, ti
             sd['final.0.weight'] = sd['final.0.weight'] / logits.std()
             sd['final.0.bias'] = (sd['final.0.bias'] - logits.mean()) / logits.std()
             ref, logits = forward(sd, tiles.float() / 255)
-    tol = TOL[precision] if regime == 'default' else TOL_STRESS[precision]
     kind = 'attunet2d' if network == 'AttentionUnet' else 'unet2d_v0'
     eng = Engine(kind, sd, n_filter, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
     eng.plan(batch, tile)
     val, u8 = eng.forward(tiles.cuda(), want_val=True, want_u8=True)
     torch.cuda.synchronize()
-    err = (val.cpu() - ref).abs().max().item()
-    assert err < tol, (network, precision, regime, err)
+    err, _, tol = _parity.check(val, ref, forward, precision, sd, tiles.float() / 255, what=f'{network} nf={n_filter} {regime}')
+    if regime == 'default':
+        assert err < TOL[precision], (network, precision, regime, err)
     ref_u8 = (ref.numpy() * 255).astype('uint8')
     d = np.abs(u8.cpu().numpy().astype(np.int16) - ref_u8.astype(np.int16))
     assert d.max() <= 1 + int(np.ceil(tol * 255)), d.max()
@@ -342,9 +349,9 @@ def test_variant_predict_matches_reference_golden(name, precision, as_class, tmp
     assert (p.N_x, p.N_y) == (int(g['N_x']), int(g['N_y']))
     assert np.array_equal(p.X_start, g['X_start']) and np.array_equal(p.Y_start, g['Y_start'])
     assert np.array_equal(p.patches, g['patches'])
-    lsb = LSB_GOLDEN[precision]
+    lsb = golden_lsb(omodels.FORWARD_2D[network], precision, _golden.state_dict(g), g['patches'])
     d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
-    assert d.max() <= lsb, d.max()
+    assert d.max() <= lsb, (d.max(), lsb)
     out = tiff.imread(res_file)
     assert out.dtype == np.float16 and out.shape == g['result_file'].shape
     assert np.abs(out.astype(np.float32) - g['result_file'].astype(np.float32)).max() <= lsb
@@ -397,10 +404,12 @@ def test_rows_kernel_matches_halo_kernel_2d(precision, n_filter, tile, batch, ro
         # encode2 / m1 come straight out of the first narrow block; d7 has the whole network in between
         assert np.abs(a - b).max() <= (8 if n == 'd7' else 1) * rel * max(np.abs(b).max(), 1.0), \
             (n, np.abs(a - b).max(), np.abs(b).max())
-    assert (got[1][0] - got[0][0]).abs().max().item() < 0.5 * TOL_STRESS[precision]
-    assert (got[1][0] - ref).abs().max().item() < TOL_STRESS[precision]
+    x = tiles.float() / 255
+    _, _, tol = _parity.check(got[1][0], ref, omodels.unet_forward, precision, sd, x, what='row kernel')
+    _parity.check(got[0][0], ref, omodels.unet_forward, precision, sd, x, what='halo kernel')
+    assert (got[1][0] - got[0][0]).abs().max().item() < 0.5 * tol
     assert np.abs(got[1][1].numpy().astype(np.int16) - got[0][1].numpy().astype(np.int16)).max() <= \
-        1 + int(np.ceil(0.5 * TOL_STRESS[precision] * 255))
+        1 + int(np.ceil(0.5 * tol * 255))
 
 
 @pytest.mark.parametrize('precision', ['tf32', 'bf16'])
@@ -426,12 +435,14 @@ def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, bat
         elif k.endswith('running_mean') or k.endswith('.1.bias'):
             sd[k] = torch.randn(v.shape, generator=g) * 0.1
     x = torch.rand((batch, 1, *tile), generator=g)
+    if kind == 'unet3d':
+        fwd = lambda sd_, x_: omodels.unet3d_forward(sd_, x_)[0]                       # noqa: E731
+    else:
+        def fwd(sd_, x_):
+            o = omodels.mo3d_forward(sd_, x_, cfg, True)
+            return torch.cat([o['seg'].float(), o['flow'].float()], 1)
     with torch.no_grad():
-        if kind == 'unet3d':
-            ref = omodels.unet3d_forward(sd, x)[0]
-        else:
-            o = omodels.mo3d_forward(sd, x, cfg, True)
-            ref = torch.cat([o['seg'], o['flow']], 1)
+        ref = fwd(sd, x)
     got = {}
     for on in (2, 1, 0):                  # 2: both pipelines of the row kernel forced on
         rows_kernel_toggle(on)
@@ -441,9 +452,9 @@ def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, bat
         got[on] = val.cpu()
         eng.close()
     assert torch.equal(got[2], got[1])    # one or two pipelines: bit-identical
-    tol = 2e-3 if precision == 'tf32' else 2e-2
+    _, _, tol = _parity.check(got[1], ref, fwd, precision, sd, x, what=f'{kind} row kernel')
+    _parity.check(got[0], ref, fwd, precision, sd, x, what=f'{kind} halo kernel')
     assert (got[1] - got[0]).abs().max().item() < 0.5 * tol
-    assert (got[1] - ref).abs().max().item() < tol, (got[1] - ref).abs().max().item()
 
 
 @pytest.mark.parametrize('name', ['unet_f32_single', 'unet_f32_first_invert', 'unet_f32_all'])
@@ -470,10 +481,8 @@ def test_predict_float32_stack_matches_reference_golden(name, precision, tmp_pat
     else:
         assert np.array_equal(imgs, g['imgs'])
     d = np.abs(p.result_patches.astype(np.int16) - g['result_patches'].astype(np.int16))
-    if precision == 'fp32':
-        assert d.max() <= LSB_GOLDEN[precision], d.max()
-    else:      # stress net: a few pixels on the steep part of the sigmoid move far under bf16 operand rounding
-        assert (d > LSB_GOLDEN[precision]).mean() < 5e-3 and np.median(d) <= 2, (d.max(), (d > LSB_GOLDEN[precision]).mean())
+    lsb = golden_lsb(omodels.unet_forward, precision, _golden.state_dict(g), g['patches'])
+    assert d.max() <= lsb, (d.max(), lsb)
     out = tiff.imread(res_file)
     assert out.shape == g['result_file'].shape and out.dtype == np.float16
 
