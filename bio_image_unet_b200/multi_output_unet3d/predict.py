@@ -35,19 +35,13 @@ class Session:
                               for k in self.target_keys],
                              use_interpolation=params.get('use_interpolation', True), precision=precision,
                              device=self.device)
-        self.tile_batch, self._budget_batch, self._plan_key = None, None, None
+        self.tile_batch = None
+        self._planner = P.BatchPlanner(self.engine, self.workspace_bytes)
         self._out = P.PinnedOut()
         self._host_out, self._s_out = None, None
 
     def _plan(self, tile, n_tiles):
-        if self._plan_key != tuple(tile):
-            per_tile = self.engine.plan(1, tile)
-            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
-            self._plan_key, self.tile_batch = tuple(tile), None
-        target = min(max(1, n_tiles), self._budget_batch)
-        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
-            self.engine.plan(target, tile)
-            self.tile_batch = target
+        self.tile_batch = self._planner.ensure(tile, n_tiles)
         return self.tile_batch
 
     def close(self):
@@ -75,7 +69,7 @@ class Session:
         return P.E.apply_lut_f32(vols_dev.reshape(n, -1), lut).reshape(vols_dev.shape) if n else \
             torch.zeros(vols_dev.shape, dtype=torch.float32, device=self.device)
 
-    def predict(self, imgs, keep=False, progress_notifier=None, show_progress=False):
+    def predict(self, imgs, keep=False, progress_notifier=None, show_progress=False, to_host=True):
         """imgs: (N, D, H, W) (or (D, H, W)) uint8 / uint16 host stack -> {head: float32 array} on rank 0 (None
         elsewhere). Results are views of a pinned buffer that the next call reuses."""
         if imgs.ndim == 3:
@@ -98,7 +92,7 @@ class Session:
         vols = P.to_device_stack(imgs[lo:hi].reshape(hi - lo, d_img * h_img, w_img), dev).reshape(hi - lo, d_img, h_img, w_img)
         norm = self._normalise(vols, lo)
         # multi-GPU: the stitched float32 volumes stay in HBM until the NCCL gather on rank 0
-        on_device = self.dist.multi
+        on_device = self.dist.multi or not to_host
         shape = (hi - lo, head_total, d_img, h_img, w_img)
         if on_device:
             out_local = torch.zeros(shape, dtype=torch.float32, device=dev)
@@ -151,6 +145,8 @@ class Session:
                 self.result_patches = np.concatenate(kept_r)
         if on_device:
             full = self.dist.gather_slabs(out_local, self.dist.shards(n_vol))
+            if not to_host:
+                return full                  # (N, head_total, D, H, W) float32 device tensor (rank 0)
             full = None if full is None else self._out.fetch(full)
         else:
             if self._s_out is not None:

@@ -94,6 +94,36 @@ def run_tiles(eng, tiles, tile_batch, prev_tiles=None, want_val=False):
     return u8, val
 
 
+def even_batch(total_tiles, budget_batch):
+    """Tile batch for a job of `total_tiles`: as few forwards as the workspace budget allows, all of (almost) the same
+    size - 288 tiles with room for 160 run as 2 x 144, not 160 + 128 padded to 160."""
+    total_tiles, budget_batch = max(1, int(total_tiles)), max(1, int(budget_batch))
+    n_fwd = -(-total_tiles // budget_batch)
+    return -(-total_tiles // n_fwd)
+
+
+class BatchPlanner:
+    """Plan policy shared by the Session classes: the plan grows on demand, shrinks only when a job is at most half
+    the planned batch (padding a 25-tile image to a 200-tile batch would cost 8x), and is never re-made for the
+    shorter tail chunk of a movie (run_tiles pads that one)."""
+
+    def __init__(self, engine, workspace_bytes):
+        self.engine, self.workspace_bytes = engine, workspace_bytes
+        self.tile, self.budget_batch, self.tile_batch = None, None, None
+
+    def ensure(self, tile, total_tiles):
+        tile = tuple(int(v) for v in tile)
+        if self.tile != tile:
+            per_tile = self.engine.plan(1, tile)
+            self.budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
+            self.tile, self.tile_batch = tile, None
+        target = even_batch(total_tiles, self.budget_batch)
+        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
+            self.engine.plan(target, tile)
+            self.tile_batch = target
+        return self.tile_batch
+
+
 def pick_tile_batch(eng, tile, total_tiles, budget_bytes):
     per_tile = eng.plan(1, tile)
     batch = int(max(1, min(total_tiles, budget_bytes // max(per_tile, 1))))

@@ -70,7 +70,7 @@ class Session:
         self.engine = Engine('siam2d', params['state_dict'], params['n_filter'], 1, [('', 1, 'sigmoid')],
                              siam_mode=params['mode'], precision=precision, device=self.device)
         self.tile_batch = None
-        self._plan_key = None
+        self._planner = P.BatchPlanner(self.engine, self.workspace_bytes)
         self._pin, self._streams, self._dev_in = {}, None, None
         self.last = {}
 
@@ -80,15 +80,7 @@ class Session:
         return (rd, *P.tiling.grid_2d(h, w, rd, self.add_tile))
 
     def _ensure_plan(self, rd, total_tiles):
-        total_tiles = max(1, int(total_tiles))
-        if self._plan_key != tuple(rd):
-            per_tile = self.engine.plan(1, rd)
-            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
-            self._plan_key, self.tile_batch = tuple(rd), None
-        target = min(total_tiles, self._budget_batch)
-        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
-            self.engine.plan(target, rd)
-            self.tile_batch = target
+        self.tile_batch = self._planner.ensure(rd, total_tiles)
 
     @staticmethod
     def pair_indices(n_frames, lo, hi):
@@ -143,9 +135,10 @@ class Session:
         n_per = n_x * n_y
         if hi <= lo:
             return
-        self._ensure_plan(rd, (hi - lo) * n_per)
         if chunk_pairs is None:
-            chunk_pairs = max(1, min(hi - lo, max(1, (2 * self.tile_batch) // n_per)))
+            self._ensure_plan(rd, (hi - lo) * n_per)
+            chunk_pairs = max(1, min(hi - lo, max(1, self.tile_batch // n_per)))
+        self._ensure_plan(rd, min(hi - lo, chunk_pairs) * n_per)
         tdtype = {np.dtype('uint8'): torch.uint8, np.dtype('uint16'): torch.uint16}.get(np.dtype(source.dtype))
         if tdtype is None:
             raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 movies on the device; got {source.dtype}')

@@ -39,25 +39,16 @@ class Session:
         self.engine = Engine(self.KINDS[network], params['state_dict'], params['n_filter'], params['in_channels'],
                              [('', self.out_channels, 'sigmoid')], precision=precision, device=self.device)
         self.tile_batch = None
-        self._budget_batch = None
-        self._graphs = {}
+        self._planner = P.BatchPlanner(self.engine, self.workspace_bytes)
         self.fixed_lut = None          # set by Predict for 'first' / 'all' (stack-wide statistics incl. other ranks)
         self.last = {}
         self._pin, self._streams, self._dev_in = {}, None, None
+        self._comm_stream, self._d2h_stream, self._slab, self._full, self.comm = None, None, None, None, {}
 
     def _ensure_plan(self, total_tiles):
-        """Tile batch of the engine plan: min(tiles of the job, what the workspace budget holds). The plan only grows
-        between calls; it shrinks when a later job is at most half the planned batch (padding a 25-tile image to a
-        200-tile batch would cost 8x), never for the shorter tail chunk of a movie (run_tiles pads that one)."""
-        total_tiles = max(1, int(total_tiles))
-        if self._budget_batch is None:
-            per_tile = self.engine.plan(1, self.resize_dim)
-            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
-        target = min(total_tiles, self._budget_batch)
-        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
-            self.engine.plan(target, self.resize_dim)
-            self.tile_batch = target
-            self._graphs = {}
+        """Tile batch of the engine plan (pipeline2d.BatchPlanner: grows on demand, even split of the job over the
+        forwards, no re-plan for the tail chunk of a movie)."""
+        self.tile_batch = self._planner.ensure(self.resize_dim, total_tiles)
 
     def stack_lut(self, frames, chunk_frames, reduce=None, first_frame=None):
         """LUT of the 'first' / 'all' modes for a WHOLE integer stack (host or device, any length): bounds from frame 0
@@ -143,14 +134,16 @@ class Session:
             if frames.dtype not in (torch.uint8, torch.uint16, torch.float32):
                 raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 / float32 stacks on the device; got {frames.dtype}')
             host = frames.contiguous()
+        resident = host.is_cuda             # the stack already lives in HBM: no H2D stage
         f, h, w = host.shape
         n_x, n_y, _, _ = P.tiling.grid_2d(h, w, self.resize_dim, self.add_tile)
-        self._ensure_plan(f * n_x * n_y)
         is_float = host.dtype == torch.float32
         if chunk_frames is None:
+            self._ensure_plan(f * n_x * n_y)
             chunk_frames = max(1, min(f, self.tile_batch // (n_x * n_y)))
         if is_float and self.normalization_mode != 'single':
             chunk_frames = f               # stack-wide float statistics are taken in one pass over the whole stack
+        self._ensure_plan(min(f, chunk_frames) * n_x * n_y)      # one chunk = a whole number of equal forwards
         dev = self.device
         lut = self.fixed_lut
         if lut is None and not is_float and self.normalization_mode != 'single' and f > chunk_frames:
@@ -165,11 +158,11 @@ class Session:
                 st.wait_stream(cur)
             out_host = self._pinned('out', (f, self.out_channels, h, w), torch.uint8) if out_dev is None else None
             norm_host = self._pinned('norm', (f, h, w), torch.float32 if is_float else torch.uint8) if want_norm else None
-            pinned_in = host.is_pinned()
+            pinned_in = resident or host.is_pinned()
             key = (chunk_frames, h, w, host.dtype)
-            if self._dev_in is None or self._dev_in[0] != key:
+            if not resident and (self._dev_in is None or self._dev_in[0] != key):
                 self._dev_in = (key, [torch.empty((chunk_frames, h, w), dtype=host.dtype, device=dev) for _ in range(2)])
-            dev_in = self._dev_in[1]
+            dev_in = None if resident else self._dev_in[1]
             stage = None if pinned_in else [self._pinned(f'stage{b}', (chunk_frames, h, w), host.dtype) for b in range(2)]
             ev_in = [torch.cuda.Event() for _ in range(2)]
             ev_done = [torch.cuda.Event() for _ in range(2)]
@@ -181,13 +174,15 @@ class Session:
                     ev_in[b].synchronize()                      # the copy that last read this staging buffer is done
                     stage[b][:n].copy_(src)
                     src = stage[b][:n]
-                with torch.cuda.stream(s_in):
-                    s_in.wait_event(ev_done[b])                 # the compute that last read dev_in[b] is done
-                    dev_in[b][:n].copy_(src, non_blocking=True)
-                    ev_in[b].record(s_in)
+                if not resident:
+                    with torch.cuda.stream(s_in):
+                        s_in.wait_event(ev_done[b])             # the compute that last read dev_in[b] is done
+                        dev_in[b][:n].copy_(src, non_blocking=True)
+                        ev_in[b].record(s_in)
                 with torch.cuda.stream(s_comp):
-                    s_comp.wait_event(ev_in[b])
-                    res = self.predict_device(dev_in[b][:n], lut=lut, planned=True)
+                    if not resident:
+                        s_comp.wait_event(ev_in[b])
+                    res = self.predict_device(src if resident else dev_in[b][:n], lut=lut, planned=True)
                     norm = self.last['norm'] if want_norm else None
                     if out_dev is not None:
                         out_dev[s0:s0 + n].copy_(res)
@@ -204,11 +199,102 @@ class Session:
             cur.wait_stream(s_comp)
         return (out_host.numpy() if out_dev is None else out_dev), (norm_host.numpy() if want_norm else None)
 
+    def predict_movie_sharded(self, frames_local, ctx, n_total, chunk_frames=None, segments=4, to_host=True):
+        """Multi-GPU prediction of a movie whose frames are sharded contiguously over the ranks of `ctx`
+        (tiling.shard_range): `frames_local` is THIS rank's slice - a host stack (pinned ideally; H2D pipelined as in
+        predict_movie) or a device tensor already in HBM. Frames are independent, so there is no data-path collective;
+        the stitched uint8 slabs are gathered on rank 0 with NCCL send / recv over NVLink straight into a full-movie
+        device buffer. The local slice is processed in `segments` parts: the gather of part j (communication stream)
+        and, on rank 0, its D2H copy (copy stream) overlap the compute of part j + 1.
+
+        Returns on rank 0 the (n_total, C, H, W) result - a numpy array backed by a pinned buffer (to_host) or the
+        device tensor - and None elsewhere. ``self.comm`` holds {'bytes': received on rank 0, 'ms': NCCL time}."""
+        dev = self.device
+        f = int(frames_local.shape[0])
+        lo, hi = ctx.shard(n_total)
+        assert hi - lo == f, (lo, hi, f)
+        h, w = int(frames_local.shape[1]), int(frames_local.shape[2])
+        c = self.out_channels
+        shards = ctx.shards(n_total)
+        segments = max(1, min(segments, max(1, min(b - a for a, b in shards))))
+        if self.normalization_mode != 'single' and self.fixed_lut is None:
+            is_dev = torch.is_tensor(frames_local) and frames_local.is_cuda
+            first = frames_local[0:1] if lo == 0 else None
+            f0 = torch.zeros((1, h, w), dtype=torch.uint16, device=dev) if first is None else \
+                (first if is_dev else P.to_device_stack(first, dev))
+            if self.normalization_mode == 'first':      # frame 0 lives on rank 0
+                f0 = ctx.broadcast(f0.view(torch.int16) if f0.dtype == torch.uint16 else f0, 0)
+                f0 = f0.view(torch.uint16) if f0.dtype == torch.int16 else f0
+            self.fixed_lut = self.stack_lut(frames_local, max(1, chunk_frames or 8), reduce=ctx.all_reduce_sum,
+                                            first_frame=f0)
+            clear_lut = True
+        else:
+            clear_lut = False
+        with torch.cuda.device(dev):
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(dev)
+            s_comm = self._comm_stream
+            if self._d2h_stream is None:
+                self._d2h_stream = torch.cuda.Stream(dev)
+            s_out = self._d2h_stream           # not predict_movie's copy stream: that one is synchronised per segment
+            cur = torch.cuda.current_stream(dev)
+            s_comm.wait_stream(cur)
+            key = (f, c, h, w)
+            if self._slab is None or self._slab[0] != key:
+                self._slab = (key, torch.empty((f, c, h, w), dtype=torch.uint8, device=dev))
+            slab = self._slab[1]
+            full = None
+            if ctx.rank == 0:
+                if self._full is None or tuple(self._full.shape) != (n_total, c, h, w):
+                    self._full = torch.empty((n_total, c, h, w), dtype=torch.uint8, device=dev) if ctx.multi else None
+                full = self._full if ctx.multi else slab
+            out_host = self._pinned('out_full', (n_total, c, h, w), torch.uint8) if (to_host and ctx.rank == 0) else None
+            t_ev = []
+            for j in range(segments):
+                a, b = P.tiling.shard_range(f, j, segments)
+                if b > a:
+                    self.predict_movie(frames_local[a:b], chunk_frames=chunk_frames, out_dev=slab[a:b])
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                bounds = []
+                for r, (r_lo, r_hi) in enumerate(shards):
+                    ra, rb = P.tiling.shard_range(r_hi - r_lo, j, segments)
+                    bounds.append((r_lo + ra, r_lo + rb))
+                with torch.cuda.stream(s_comm):
+                    s_comm.wait_event(done)
+                    if ctx.multi:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(s_comm)
+                        ctx.gather_slabs(slab[a:b], bounds, out=full, n_total=n_total)
+                        e1.record(s_comm)
+                        t_ev.append((e0, e1))
+                    got = torch.cuda.Event()
+                    got.record(s_comm)
+                if out_host is not None:
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(got)
+                        for ga, gb in bounds:
+                            if gb > ga:
+                                out_host[ga:gb].copy_(full[ga:gb], non_blocking=True)
+            s_comm.synchronize()
+            if out_host is not None:
+                s_out.synchronize()
+            cur.wait_stream(s_comm)
+            self.comm = {'bytes': int((n_total - f) * c * h * w) if (ctx.multi and ctx.rank == 0) else 0,
+                         'ms': float(sum(a.elapsed_time(b) for a, b in t_ev)) if t_ev else 0.0,
+                         'collective': 'ncclSend/ncclRecv gather of the stitched uint8 slabs to rank 0 '
+                                       f'({segments} segments, overlapped with compute)'}
+        if clear_lut:
+            self.fixed_lut = None
+        if ctx.rank != 0:
+            return None
+        return out_host.numpy() if to_host else full
+
     def close(self):
         if self.engine is not None:
             self.engine.close()
             self.engine = None
-        self._pin, self._dev_in = {}, None
+        self._pin, self._dev_in, self._slab, self._full = {}, None, None, None
 
 
 class Predict:

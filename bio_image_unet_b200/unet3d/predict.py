@@ -31,18 +31,13 @@ class Session:
                              [('', params['out_channels'], 'sigmoid')],
                              use_interpolation=params.get('use_interpolation', False), precision=precision,
                              device=self.device)
-        self.tile_batch, self._budget_batch = None, None
+        self.tile_batch = None
+        self._planner = P.BatchPlanner(self.engine, self.workspace_bytes)
         self.exchanged_bytes = 0
         self._out = P.PinnedOut()
 
     def _plan(self, tile, n_tiles):
-        if self._budget_batch is None:
-            per_tile = self.engine.plan(1, tile)
-            self._budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
-        target = min(max(1, n_tiles), self._budget_batch)
-        if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
-            self.engine.plan(target, tile)
-            self.tile_batch = target
+        self.tile_batch = self._planner.ensure(tile, n_tiles)
         return self.tile_batch
 
     def close(self):
@@ -50,7 +45,7 @@ class Session:
             self.engine.close()
             self.engine = None
 
-    def predict(self, vol, keep=False):
+    def predict(self, vol, keep=False, to_host=True):
         """Single process: the whole volume. Multi-GPU: the z-rows of the patch grid (the outermost loop of
         unet3d/predict.py:146,180) are sharded contiguously; a rank uploads and normalises only the z-slab its rows
         touch, predicts its patches, receives from the ranks above it the uint8 result patches of the z-rows that
@@ -134,7 +129,9 @@ class Session:
             if allp is not None:
                 self.patches, self.result_patches = allp.cpu().numpy(), allr.cpu().numpy()
         full = ctx.gather_slabs(st, [p['own'] for p in plans], n_total=z) if ctx.multi else st
-        return None if full is None else self._out.fetch(full)
+        if full is None or not to_host:
+            return full
+        return self._out.fetch(full)      # view of a pinned buffer that the next call reuses
 
 
 class Predict:
