@@ -193,10 +193,10 @@ class Session:
                     if out_dev is not None:
                         out_dev[s - lo:e - lo].copy_(st[:, 0])
                     ev_done[b].record(s_comp)
-                if keep is not None:
-                    both = torch.stack((self.last['tiles_cur'][:, 0], self.last['tiles_prev'][:, 0]), dim=1)
-                    keep['patches'].append(both.cpu().numpy().reshape(e - s, n_per, 2, *rd))
-                    keep['result_patches'].append(self.last['result_tiles'].cpu().numpy().reshape(e - s, n_per, 1, *rd))
+                    if keep is not None:              # test hook (on the compute stream: .cpu() waits for the kernels)
+                        both = torch.stack((self.last['tiles_cur'][:, 0], self.last['tiles_prev'][:, 0]), dim=1)
+                        keep['patches'].append(both.cpu().numpy().reshape(e - s, n_per, 2, *rd))
+                        keep['result_patches'].append(self.last['result_tiles'].cpu().numpy().reshape(e - s, n_per, 1, *rd))
                 if out_dev is None:
                     with torch.cuda.stream(s_out):
                         s_out.wait_event(ev_done[b])

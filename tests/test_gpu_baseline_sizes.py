@@ -85,7 +85,7 @@ def test_cfg2_tiles_in_a_full_batch_match_oracle(precision):
     probe = torch.randint(0, 256, (1, 1, 512, 512), dtype=torch.uint8, generator=torch.Generator().manual_seed(5))
     sd = unit_logit_state_dict(32, 302, probe)
     ses = Session({'state_dict': sd, 'n_filter': 32, 'in_channels': 1, 'out_channels': 1}, resize_dim=(512, 512),
-                  add_tile=1, device='cuda:0', precision=precision, workspace_gb=40.0)
+                  add_tile=1, device='cuda:0', precision=precision, workspace_gb=64.0)
     out = ses.predict_device(torch.from_numpy(frames).cuda(), keep=True)
     assert ses.tile_batch == 150 and ses.engine.fallback_ops == 0
     tiles, res = ses.last['tiles'].cpu(), ses.last['result_tiles'].cpu()

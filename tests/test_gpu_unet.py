@@ -407,9 +407,10 @@ def test_rows_kernel_matches_halo_kernel_2d(precision, n_filter, tile, batch, ro
     x = tiles.float() / 255
     _, _, tol = _parity.check(got[1][0], ref, omodels.unet_forward, precision, sd, x, what='row kernel')
     _parity.check(got[0][0], ref, omodels.unet_forward, precision, sd, x, what='halo kernel')
-    assert (got[1][0] - got[0][0]).abs().max().item() < 0.5 * tol
+    # the two kernels round every stored activation independently: their difference is of the size of the error itself
+    assert (got[1][0] - got[0][0]).abs().max().item() < tol
     assert np.abs(got[1][1].numpy().astype(np.int16) - got[0][1].numpy().astype(np.int16)).max() <= \
-        1 + int(np.ceil(0.5 * tol * 255))
+        1 + int(np.ceil(tol * 255))
 
 
 @pytest.mark.parametrize('precision', ['tf32', 'bf16'])
@@ -454,7 +455,7 @@ def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, bat
     assert torch.equal(got[2], got[1])    # one or two pipelines: bit-identical
     _, _, tol = _parity.check(got[1], ref, fwd, precision, sd, x, what=f'{kind} row kernel')
     _parity.check(got[0], ref, fwd, precision, sd, x, what=f'{kind} halo kernel')
-    assert (got[1] - got[0]).abs().max().item() < 0.5 * tol
+    assert (got[1] - got[0]).abs().max().item() < tol
 
 
 @pytest.mark.parametrize('name', ['unet_f32_single', 'unet_f32_first_invert', 'unet_f32_all'])
