@@ -24,6 +24,7 @@ SIGNATURES = {
     'biu_net_set_force_direct': (c_int, [_P, c_int]),
     'biu_net_set_fuse_pool': (c_int, [_P, c_int]),
     'biu_set_rows_kernel': (c_int, [c_int]),
+    'biu_set_halo_cta2': (c_int, [c_int]),
     'biu_net_fallback_ops': (c_int, [_P]),
     'biu_net_destroy': (None, [_P]),
     'biu_histogram': (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),

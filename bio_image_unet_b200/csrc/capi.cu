@@ -90,6 +90,11 @@ int biu_net_fallback_ops(biu_net* net) {
   return cnt;
 }
 
+int biu_set_halo_cta2(int on) {
+  conv_halo_set_cta2(on);
+  return 0;
+}
+
 int biu_set_rows_kernel(int on) {
   conv_rows_set_enabled(on);
   return 0;

@@ -220,10 +220,49 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
   return d;
 }
 
-// Instruction descriptor, kind::f16 / kind::tf32, K-major A and B, fp32 accumulate, M = 128.
+// Instruction descriptor, kind::f16 / kind::tf32, K-major A and B, fp32 accumulate, M = 128 (256 for a CTA pair).
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32
-__device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t n) {
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t n, uint32_t m = 128u) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ------------------------------------ CTA pairs (cta_group::2) ------------------------------------
+// Two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma of M = 256: each CTA contributes the 128 rows of
+// A in its own shared memory and HALF of the N rows of B, and receives its 128 accumulator rows in its own TMEM.
+// The leader (cluster rank 0) issues the MMAs. A shared::cluster address of a CTA's own shared memory carries the
+// CTA's rank within the pair in bit 24: clearing it addresses the same offset in the leader's shared memory.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same offset in the LEADER CTA's shared memory (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// completion of all earlier MMAs of this thread -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
 }
 
 #endif  // __CUDACC__

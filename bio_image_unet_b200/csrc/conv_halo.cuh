@@ -41,6 +41,8 @@ struct ConvHaloParams {
   int n_blk, n_total;
   int a_bufs, b_stages;
   int b_resident;                  // all (chunk, tap) weight tiles of the single n-block fit the ring: loaded once
+  int cta2;                        // CTA pairs: tiles t, t+1 of a pair share one tcgen05.mma.cta_group::2 of M = 256; every
+                                   // CTA stages only n_blk / 2 rows of each weight tile (b_stage_bytes counts those)
   int stage_bytes;                 // shared memory reserved for the epilogue's transposed-store tiles (0 or 16 KB)
   uint32_t a_buf_bytes, b_stage_bytes;
   int mode;
@@ -91,9 +93,29 @@ __device__ __forceinline__ HaloTile halo_decode(const ConvHaloParams& p, int t) 
 }
 
 // tcgen05.mma with a compile-time accumulate flag (no predicate register to materialise per instruction)
-template <int ESZ, int ACC>
+template <int ESZ, int ACC, bool CTA2 = false>
 __device__ __forceinline__ void tc_mma_imm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  if (ESZ == 2) {
+  if (CTA2) {                           // one MMA of M = 256 over the CTA pair (issued by the leader CTA only)
+    if (ESZ == 2) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "setp.ne.b32 p, %4, 0;\n"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+          "}\n" ::"r"(tmem_d),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "setp.ne.b32 p, %4, 0;\n"
+          "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+          "}\n" ::"r"(tmem_d),
+          "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
+          : "memory");
+    }
+  } else if (ESZ == 2) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -359,7 +381,7 @@ __device__ __forceinline__ void halo_epi_chunk(const ConvHaloParams& p, const ui
   }
 }
 
-template <int ESZ, int CW, int MODE, bool POOL>
+template <int ESZ, int CW, int MODE, bool POOL, bool CTA2>
 __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t tmem_base, uint32_t acc_cols,
                                               uint64_t* acc_full, uint64_t* acc_empty, const float* s_scale,
                                               const float* s_shift, const float* s_headw, uint32_t stage_base,
@@ -503,15 +525,15 @@ __device__ __forceinline__ void halo_epilogue(const ConvHaloParams& p, uint32_t 
       u = un;
     }
     PROF_ADD(10);
-    // this warp is done reading the accumulator stage: hand it back to the MMA issuer
+    // this warp is done reading the accumulator stage: hand it back to the MMA issuer (CTA pairs: the leader's)
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&acc_empty[as]);
+    if (lane == 0) { if (CTA2) mbar_arrive_leader(&acc_empty[as]); else mbar_arrive(&acc_empty[as]); }
     PROF_ADD(11);
   }
 }
 
-template <int ESZ, int KS, int MT>
+template <int ESZ, int KS, int MT, bool CTA2>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const ConvHaloParams p) {
@@ -549,20 +571,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (p.mode == EPI_HEAD)
     for (int i = threadIdx.x; i < p.head_n * p.n_blk; i += kHaloThreads) s_headw[i] = p.head_w[i];
 
+  // CTA pairs: rank 0 of the cluster is the leader - it owns the "full" barriers both CTAs' TMA loads complete on and
+  // the "accumulator drained" barrier both epilogues arrive on, and it issues the MMAs; the MMA completions are
+  // multicast to the "empty" / "accumulator full" barriers of both CTAs.
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < p.a_bufs; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], CTA2 ? 16 : 8); }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_slot, ncols);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc2(&tmem_slot, ncols); tmem_relinquish2(); }
+    else { tmem_alloc(&tmem_slot, ncols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();                   // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -580,19 +608,29 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           mbar_wait(&a_empty[ab], aph ^ 1, 0x400 + ab);
           PROF_ADD(0);
           if (BIU_DBG(p, 4)) { mbar_arrive(&a_full[ab]); if (++ab == p.a_bufs) { ab = 0; aph ^= 1; } continue; }
-          mbar_arrive_expect_tx(&a_full[ab], halo_tx);
+          if (!CTA2) mbar_arrive_expect_tx(&a_full[ab], halo_tx);
+          else if (leader) mbar_arrive_expect_tx(&a_full[ab], 2u * halo_tx);     // both CTAs' halo tiles land on this barrier
           // The tile is fetched as 2-row boxes issued back to back: one TMA operation keeps only a few dozen L2
           // requests in flight, many concurrent ones are needed to cover the L2 / HBM latency.
           const uint32_t box_bytes = 2u * (uint32_t)pw * rb;
           uint32_t dst = smem_base + ab * p.a_buf_bytes;
           for (int dz = 0; dz < p.kd; ++dz)
-            for (int r2 = 0; r2 < rows / 2; ++r2, dst += box_bytes)
-              asm volatile(
-                  "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-                  "%5, %6, %7}], [%2];" ::"r"(dst),
-                  "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[ab])), "r"(ch * p.ck),
-                  "r"(tl.x0 - p.halo), "r"(tl.y0 - p.halo + 2 * r2), "r"(tl.z0 - (p.kd >> 1) + dz), "r"(tl.b0)
-                  : "memory");
+            for (int r2 = 0; r2 < rows / 2; ++r2, dst += box_bytes) {
+              if (CTA2)
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+                    "{%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+                    "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[ab]) & kPeerBitMask), "r"(ch * p.ck),
+                    "r"(tl.x0 - p.halo), "r"(tl.y0 - p.halo + 2 * r2), "r"(tl.z0 - (p.kd >> 1) + dz), "r"(tl.b0)
+                    : "memory");
+              else
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+                    "%5, %6, %7}], [%2];" ::"r"(dst),
+                    "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[ab])), "r"(ch * p.ck),
+                    "r"(tl.x0 - p.halo), "r"(tl.y0 - p.halo + 2 * r2), "r"(tl.z0 - (p.kd >> 1) + dz), "r"(tl.b0)
+                    : "memory");
+            }
           PROF_ADD(1);
           if (++ab == p.a_bufs) { ab = 0; aph ^= 1; }
         }
@@ -601,7 +639,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   } else if (warp == 2) {
     // ================================= weight (B) producer ==================================
     if (elect_one()) {
-      const uint32_t b_tx = (uint32_t)p.n_blk * rb;
+      const uint32_t b_tx = (uint32_t)(CTA2 ? p.n_blk / 2 : p.n_blk) * rb;      // CTA pairs: every CTA stages half of the rows
+      const int n_half = CTA2 ? (int)cta_rank * (p.n_blk / 2) : 0;
       const int taps = taps_r * taps_x;
       int s = 0;
       uint32_t bph = 0;
@@ -615,24 +654,34 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             mbar_wait(&b_empty[s], bph ^ 1, 0x500 + s);
             PROF_ADD(2);
             if (BIU_DBG(p, 16)) { mbar_arrive(&b_full[s]); if (++s == p.b_stages) { s = 0; bph ^= 1; } continue; }
-            mbar_arrive_expect_tx(&b_full[s], b_tx);
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
-                "%5}], [%2];" ::"r"(b_base + s * p.b_stage_bytes),
-                "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&b_full[s])), "r"(ch * p.ck), "r"(tl.n0),
-                "r"(tap)
-                : "memory");
+            if (CTA2) {
+              if (leader) mbar_arrive_expect_tx(&b_full[s], 2u * b_tx);
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+                  "{%3, %4, %5}], [%2];" ::"r"(b_base + s * p.b_stage_bytes),
+                  "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&b_full[s]) & kPeerBitMask), "r"(ch * p.ck),
+                  "r"(tl.n0 + n_half), "r"(tap)
+                  : "memory");
+            } else {
+              mbar_arrive_expect_tx(&b_full[s], b_tx);
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+                  "%5}], [%2];" ::"r"(b_base + s * p.b_stage_bytes),
+                  "l"(reinterpret_cast<uint64_t>(&tmB)), "r"(smem_u32(&b_full[s])), "r"(ch * p.ck), "r"(tl.n0),
+                  "r"(tap)
+                  : "memory");
+            }
             if (++s == p.b_stages) { s = 0; bph ^= 1; }
           }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && leader) {
     // ====================================== MMA issuer ======================================
     // All 32 lanes run the loops (warp-uniform control flow and addresses); the elected lane issues. MT and KS are
     // compile-time so the MT*KS MMAs of a tap are straight-line code with immediate descriptor offsets.
     const bool issue = !BIU_DBG(p, 2);
     const uint32_t layout = rb == 128 ? 2u : (rb == 64 ? 4u : 6u);
-    const uint32_t idesc = make_idesc(ESZ == 2 ? 1u : 2u, (uint32_t)p.n_blk);
+    const uint32_t idesc = make_idesc(ESZ == 2 ? 1u : 2u, (uint32_t)p.n_blk, CTA2 ? 256u : 128u);
     // Descriptors: only the 14-bit start-address field (address >> 4) changes between MMAs and it never carries
     // out of the field (shared memory < 256 KB).
     const uint64_t a_desc0 = make_smem_desc(smem_base, (uint32_t)pw * rb, layout);
@@ -676,32 +725,32 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 for (int j = 0; j < MT; ++j)
 #pragma unroll
                   for (int k = 0; k < KS; ++k) {
-                    if (k == 0) tc_mma_imm<ESZ, 0>(tacc + j * n_blk, ad0 + (j * j_step + 2 * k), bd0 + 2 * k, idesc);
-                    else tc_mma_imm<ESZ, 1>(tacc + j * n_blk, ad0 + (j * j_step + 2 * k), bd0 + 2 * k, idesc);
+                    if (k == 0) tc_mma_imm<ESZ, 0, CTA2>(tacc + j * n_blk, ad0 + (j * j_step + 2 * k), bd0 + 2 * k, idesc);
+                    else tc_mma_imm<ESZ, 1, CTA2>(tacc + j * n_blk, ad0 + (j * j_step + 2 * k), bd0 + 2 * k, idesc);
                   }
               } else {
 #pragma unroll
                 for (int j = 0; j < MT; ++j)
 #pragma unroll
                   for (int k = 0; k < KS; ++k)
-                    tc_mma_imm<ESZ, 1>(tacc + j * n_blk, ad0 + (j * j_step + 2 * k), bd0 + 2 * k, idesc);
+                    tc_mma_imm<ESZ, 1, CTA2>(tacc + j * n_blk, ad0 + (j * j_step + 2 * k), bd0 + 2 * k, idesc);
               }
             }
-            if (!p.b_resident && elect_one()) tc_commit(&b_empty[bs]);
+            if (!p.b_resident && elect_one()) { if (CTA2) tc_commit2(&b_empty[bs]); else tc_commit(&b_empty[bs]); }
             first = false;
             PROF_ADD(6);
             if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
           }
         }
-        if (elect_one()) tc_commit(&a_empty[ab]);
+        if (elect_one()) { if (CTA2) tc_commit2(&a_empty[ab]); else tc_commit(&a_empty[ab]); }
         if (++ab == p.a_bufs) { ab = 0; aph ^= 1; }
       }
-      if (elect_one()) tc_commit(&acc_full[as]);
+      if (elect_one()) { if (CTA2) tc_commit2(&acc_full[as]); else tc_commit(&acc_full[as]); }
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================
 #define BIU_EPI(CW, MODE, POOL) \
-    halo_epilogue<ESZ, CW, MODE, POOL>(p, tmem_base, acc_cols, acc_full, acc_empty, s_scale, s_shift, s_headw, stage_base, warp, lane)
+    halo_epilogue<ESZ, CW, MODE, POOL, CTA2>(p, tmem_base, acc_cols, acc_full, acc_empty, s_scale, s_shift, s_headw, stage_base, warp, lane)
     if (p.n_blk % 32 == 0) {
       if (p.mode == EPI_CONV) { if (p.pool_out != nullptr) BIU_EPI(32, EPI_CONV, true); else BIU_EPI(32, EPI_CONV, false); }
       else if (p.mode == EPI_UP) BIU_EPI(32, EPI_UP, false);
@@ -716,7 +765,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (CTA2) cluster_sync_all();       // the peer may still read this CTA's shared memory / signal its barriers
+  if (warp == 1) { if (CTA2) tmem_dealloc2(tmem_base, ncols); else tmem_dealloc(tmem_base, ncols); }
 }
 
 // Host-side dispatch over the (k-steps per chunk, MMA tiles per work item) instantiations of one element size;
@@ -728,13 +778,30 @@ int halo_dispatch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 
 #define BIU_HALO_LAUNCH(E, K, M)                                                                                  \
   do {                                                                                                             \
-    static int max_set = 0;                                                                                        \
-    if (smem > max_set) {                                                                                          \
-      BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<E, K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                          smem));                                                                  \
-      max_set = smem;                                                                                              \
+    if (p.cta2) {                                                                                                  \
+      static int max_set2 = 0;                                                                                     \
+      if (smem > max_set2) {                                                                                       \
+        BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<E, K, M, true>,                                       \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+        max_set2 = smem;                                                                                           \
+      }                                                                                                            \
+      cudaLaunchConfig_t cfg;                                                                                      \
+      memset(&cfg, 0, sizeof(cfg));                                                                                \
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream; \
+      cudaLaunchAttribute at[1];                                                                                   \
+      at[0].id = cudaLaunchAttributeClusterDimension;                                                              \
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                          \
+      cfg.attrs = at; cfg.numAttrs = 1;                                                                            \
+      BIU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<E, K, M, true>, tmA, tmB, p));                      \
+    } else {                                                                                                       \
+      static int max_set = 0;                                                                                      \
+      if (smem > max_set) {                                                                                        \
+        BIU_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<E, K, M, false>,                                      \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                   \
+        max_set = smem;                                                                                            \
+      }                                                                                                            \
+      conv_halo_kernel<E, K, M, false><<<grid, kHaloThreads, smem, stream>>>(tmA, tmB, p);                         \
     }                                                                                                              \
-    conv_halo_kernel<E, K, M><<<grid, kHaloThreads, smem, stream>>>(tmA, tmB, p);                                  \
   } while (0)
 #define BIU_HALO_LAUNCH_M(E, K)                                                                                    \
   do {                                                                                                             \
@@ -746,6 +813,40 @@ int halo_dispatch_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
            cudaStream_t stream) {                                                                                  \
     const int ks = p.row_bytes / 32;                                                                               \
     if (ks == 4) BIU_HALO_LAUNCH_M(E, 4); else if (ks == 2) BIU_HALO_LAUNCH_M(E, 2); else BIU_HALO_LAUNCH_M(E, 1); \
+    return 0;                                                                                                      \
+  }
+
+// Co-resident CTA pairs of the 2-CTA kernel with `smem` bytes of dynamic shared memory (0: no cluster launch possible).
+// The kernel is persistent with a static tile stride, so its grid must not exceed what is resident at once.
+int halo_max_pairs_bf16(int ks, int mt, int smem);
+int halo_max_pairs_tf32(int ks, int mt, int smem);
+
+#define BIU_HALO_PAIRS(E, K, M)                                                                                    \
+  do {                                                                                                             \
+    if (cudaFuncSetAttribute(conv_halo_kernel<E, K, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != \
+        cudaSuccess) { cudaGetLastError(); return 0; }                                                             \
+    cudaLaunchConfig_t cfg;                                                                                        \
+    memset(&cfg, 0, sizeof(cfg));                                                                                  \
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(kHaloThreads); cfg.dynamicSmemBytes = smem;                         \
+    cudaLaunchAttribute at[1];                                                                                     \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                \
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                            \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                              \
+    int n = 0;                                                                                                     \
+    if (cudaOccupancyMaxActiveClusters(&n, conv_halo_kernel<E, K, M, true>, &cfg) != cudaSuccess) {                \
+      cudaGetLastError();                                                                                          \
+      return 0;                                                                                                    \
+    }                                                                                                              \
+    return n;                                                                                                      \
+  } while (0)
+#define BIU_HALO_PAIRS_M(E, K)                                                                                     \
+  do {                                                                                                             \
+    if (mt == 8) BIU_HALO_PAIRS(E, K, 8); else if (mt == 4) BIU_HALO_PAIRS(E, K, 4);                                \
+    else if (mt == 2) BIU_HALO_PAIRS(E, K, 2); else BIU_HALO_PAIRS(E, K, 1);                                        \
+  } while (0)
+#define BIU_DEFINE_HALO_PAIRS(NAME, E)                                                                             \
+  int NAME(int ks, int mt, int smem) {                                                                             \
+    if (ks == 4) BIU_HALO_PAIRS_M(E, 4); else if (ks == 2) BIU_HALO_PAIRS_M(E, 2); else BIU_HALO_PAIRS_M(E, 1);     \
     return 0;                                                                                                      \
   }
 

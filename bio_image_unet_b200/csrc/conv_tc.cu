@@ -130,7 +130,15 @@ static int sm_count_cached() {
   return n;
 }
 
-struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident, stage_bytes; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
+struct HaloPlan { int mt, a_bufs, b_stages, ck, b_resident, stage_bytes, cta2; uint32_t a_buf_bytes, b_stage_bytes; int smem; bool ok; };
+
+// CTA pairs (tcgen05.mma.cta_group::2, conv_halo.cuh): -1 = from the environment (BIU_HALO_NO_CTA2=1 disables)
+static int g_halo_cta2 = -1;
+void conv_halo_set_cta2(int on) { g_halo_cta2 = on ? 1 : 0; }
+static bool halo_cta2_enabled() {
+  if (g_halo_cta2 < 0) { const char* e = getenv("BIU_HALO_NO_CTA2"); g_halo_cta2 = (e && e[0] == '1') ? 0 : 1; }
+  return g_halo_cta2 == 1;
+}
 
 // can the halo kernel take this layer? (3x3(x3) blocks, and transposed convolutions as a 1-tap GEMM)
 static bool halo_shape_ok(const ConvTcArgs& a) {
@@ -142,10 +150,11 @@ static bool halo_shape_ok(const ConvTcArgs& a) {
   return true;
 }
 
-static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
+static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk, bool cta2 = false) {
   HaloPlan pl{};
   pl.ok = false;
   if (!halo_shape_ok(a) || n_blk > 256) return pl;
+  if (cta2 && (n_blk % 32 != 0)) return pl;                // every CTA of a pair stages n_blk / 2 weight rows
   const int halo = a.kw == 3 ? 1 : 0;
   const int rows = 16 + 2 * halo;
   const int taps = halo ? 9 * a.kd : 1;
@@ -176,14 +185,14 @@ static HaloPlan plan_halo(const ConvTcArgs& a, int n_blk) {
         const int rb = ck * a.esz;
         const int chunks = a.cin / ck;
         const uint32_t tile = ((uint32_t)(a.kd * rows * (8 * mt + 2 * halo) * rb) + 1023u) & ~1023u;
-        const uint32_t bst = ((uint32_t)(n_blk * rb) + 1023u) & ~1023u;
+        const uint32_t bst = ((uint32_t)((cta2 ? n_blk / 2 : n_blk) * rb) + 1023u) & ~1023u;
         int stages = (budget - (int)(abufs * tile) - 2048) / (int)bst;
         if (stages > kMaxBStages) stages = kMaxBStages;
         const bool resident = stages >= taps * chunks && a.n_total == n_blk;
         if (stages > taps * chunks) stages = taps * chunks;
         if (stages >= (abufs == 2 ? 3 : 2) || stages == taps * chunks) {
           pl.mt = mt; pl.a_bufs = abufs; pl.b_stages = stages; pl.ck = ck; pl.b_resident = resident ? 1 : 0;
-          pl.stage_bytes = stage_bytes;
+          pl.stage_bytes = stage_bytes; pl.cta2 = cta2 ? 1 : 0;
           pl.a_buf_bytes = tile; pl.b_stage_bytes = bst;
           pl.smem = (int)(abufs * tile + stages * bst) + 1024 + extra;
           pl.ok = true;
@@ -205,7 +214,33 @@ static int sm_count() {
   return n;
 }
 
-static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, cudaStream_t stream) {
+// CTA pairs pay off where a single CTA cannot fetch the weight tile fast enough (N >= 64 columns per MMA: an MMA of N
+// columns and K = 16 reads 4096 + 32 N operand bytes at ~85 B/clk for N / 2 cycles of math; a pair halves the weight
+// part). Tiles t, t + 1 of a pair must share their weight block (even tile count per block), and the whole grid of pairs
+// has to be resident at once (persistent kernel with a static tile stride).
+static bool halo_try_cta2(const ConvTcArgs& a, int n_blk, HaloPlan* out, int* pairs_out) {
+  if (!halo_cta2_enabled() || n_blk < 64) return false;
+  HaloPlan pl = plan_halo(a, n_blk, true);
+  if (!pl.ok) return false;
+  const long long per_block = (long long)ceil_div(a.W, 8 * pl.mt) * ceil_div(a.H, 16) * a.D * a.B;
+  if (per_block < 2 || (per_block & 1)) return false;
+  static int cache[2][3][4];                               // [esz][ks index][mt index] -> pairs + 1 for the largest smem seen
+  static int cache_smem[2][3][4];
+  const int ks = pl.ck * a.esz / 32, ki = ks == 4 ? 2 : (ks == 2 ? 1 : 0), mi = pl.mt == 8 ? 3 : (pl.mt == 4 ? 2 : (pl.mt == 2 ? 1 : 0));
+  const int ei = a.esz == 2 ? 0 : 1;
+  if (cache[ei][ki][mi] == 0 || cache_smem[ei][ki][mi] < pl.smem) {
+    const int n = a.esz == 2 ? halo_max_pairs_bf16(ks, pl.mt, pl.smem) : halo_max_pairs_tf32(ks, pl.mt, pl.smem);
+    cache[ei][ki][mi] = n + 1;
+    cache_smem[ei][ki][mi] = pl.smem;
+  }
+  const int pairs = cache[ei][ki][mi] - 1;
+  if (pairs < 1) return false;
+  *out = pl;
+  *pairs_out = pairs;
+  return true;
+}
+
+static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, cudaStream_t stream, int max_pairs = 0) {
   ConvHaloParams p;
   memset(&p, 0, sizeof(p));
   p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
@@ -220,6 +255,7 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   p.n_blk = n_blk; p.n_total = a.n_total;
   p.a_bufs = pl.a_bufs; p.b_stages = pl.b_stages; p.a_buf_bytes = pl.a_buf_bytes; p.b_stage_bytes = pl.b_stage_bytes;
   p.b_resident = pl.b_resident;
+  p.cta2 = pl.cta2;
   p.stage_bytes = pl.stage_bytes;
   p.up_cout = a.up_cout; p.up_dims = a.up_dims;
   p.pool_out = a.pool_out; p.pool_ctot = a.pool_ctot; p.pool_coff = a.pool_coff;
@@ -236,8 +272,15 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   const char* in_base = reinterpret_cast<const char*>(a.in) + (size_t)a.in_coff * a.esz;
   if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, 8 * pl.mt + 2 * p.halo, 2, 1, 1))
     return rc;
-  if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, p.halo ? 9 * a.kd : 1, pl.ck, n_blk)) return rc;
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  if (int rc = encode_wgt_map(&tmB, a.wgt, a.esz, a.cin, a.n_total, p.halo ? 9 * a.kd : 1, pl.ck, pl.cta2 ? n_blk / 2 : n_blk))
+    return rc;
+  int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  if (pl.cta2) {                                           // whole pairs, all of them resident at once
+    int pairs = sm_count() / 2;
+    if (max_pairs > 0 && pairs > max_pairs) pairs = max_pairs;
+    if (pairs > p.total_tiles / 2) pairs = p.total_tiles / 2;
+    grid = 2 * pairs;
+  }
   BIU_REQUIRE(pl.mt == 1 || pl.mt == 2 || pl.mt == 4 || pl.mt == 8, "halo kernel: mt must be 1, 2, 4 or 8 (got %d)", pl.mt);
   // the kernel instantiations live in their own translation units (conv_halo_bf16.cu / conv_halo_tf32.cu)
   if (int rc = a.esz == 2 ? halo_dispatch_bf16(tmA, tmB, p, grid, pl.smem, stream)
@@ -398,6 +441,9 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
   }
   const int n_blk = choose_n_blk(a);
   {
+    HaloPlan pl2;
+    int pairs = 0;
+    if (halo_try_cta2(a, n_blk, &pl2, &pairs)) return launch_conv_halo(a, n_blk, pl2, stream, pairs);
     const HaloPlan pl = plan_halo(a, n_blk);
     if (pl.ok) return launch_conv_halo(a, n_blk, pl, stream);
   }

@@ -39,6 +39,7 @@ struct ConvTcArgs {
 };
 bool conv_tc_supported(const ConvTcArgs& a);
 bool conv_tc_can_fuse_pool(const ConvTcArgs& a);
+void conv_halo_set_cta2(int on);      // test hook: CTA pairs (tcgen05.mma.cta_group::2) in the halo-tile kernel (default on)
 void conv_rows_set_enabled(int on);   // test hook: route narrow 3x3 blocks through the row-streaming kernel (default on)
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 int read_device_fault(unsigned int* out);

@@ -81,6 +81,11 @@ int biu_net_set_fuse_pool(biu_net* net, int on);
  * take (planes narrower than 8 px, ...). 0 in the exact-fp32 mode's sense of "as requested"; the Python Predict
  * classes turn a non-zero count into a RuntimeWarning (the result is the same, the speed is not). */
 int biu_net_fallback_ops(biu_net* net);
+/* Test hook (process-wide): 0 = run every halo-tile convolution on single CTAs instead of CTA pairs (default 1: layers
+ * with at least 64 output channels per block run tcgen05.mma.cta_group::2, M = 256 over the two SMs of a TPC, each CTA
+ * staging half of every weight tile; the MMAs and their order per output tile are the same, so results are
+ * bit-identical). */
+int biu_set_halo_cta2(int on);
 /* Test hook (process-wide): 0 = run the narrow (Cout <= 32) 3x3 blocks on the halo-tile kernel instead of the
  * row-streaming folded-tap kernel (default 1; results agree to fp32 summation order); 2 = row kernel with its two
  * pipelines per CTA forced on even for workloads with few work items (they are only chosen for large batches). */

@@ -503,3 +503,53 @@ def test_float32_normalisation_kernel_bit_exact():
             assert np.array_equal(f32.cpu().numpy(), ref.astype(np.float32), equal_nan=True), (mode, invert)
             ok = ~np.isnan(ref)
             assert np.array_equal(u8.cpu().numpy()[ok], ref.astype(np.float32)[ok].astype(np.uint8)), (mode, invert)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CTA pairs in the halo-tile kernel (tcgen05.mma.cta_group::2, conv_halo.cuh)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def cta2_toggle():
+    from bio_image_unet_b200 import _lib
+    lib = _lib.load()
+    yield lambda on: lib.biu_set_halo_cta2(int(on))
+    lib.biu_set_halo_cta2(1)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'tf32'])
+@pytest.mark.parametrize('kind,n_filter,tile,batch', [('unet2d', 32, (128, 128), 6), ('unet2d', 32, (64, 96), 2), ('unet2d', 16, (256, 64), 3),
+                                                      ('unet3d', 32, (16, 32, 32), 2)])
+def test_cta_pairs_match_single_cta(precision, kind, n_filter, tile, batch, cta2_toggle):
+    """Same network with the wide layers (>= 64 output channels per block) on CTA pairs (one MMA of M = 256 over two
+    SMs, each CTA staging half of every weight tile) and on single CTAs: per output tile the same MMAs in the same
+    order, so activations and outputs are bit-identical; and the paired run matches the oracle."""
+    from bio_image_unet_b200.engine import Engine
+    from bio_image_unet_b200.unet3d import UNet3D
+    g = torch.Generator().manual_seed(12)
+    x = torch.randint(0, 256, (batch, 1, *tile), dtype=torch.uint8, generator=g)
+    if kind == 'unet2d':
+        sd = unit_logit_state_dict(n_filter, 55, x)
+        names = [('mid2', 16 * n_filter, 4), ('d2', 8 * n_filter, 3), ('d4', 4 * n_filter, 2), ('cat3', 4 * n_filter, 1)]
+        fwd = omodels.unet_forward
+    else:
+        torch.manual_seed(7)
+        sd = UNet3D(n_filter=n_filter).state_dict()
+        names = []
+        fwd = lambda sd_, x_: omodels.unet3d_forward(sd_, x_)                              # noqa: E731
+    got = {}
+    for on in (1, 0):
+        cta2_toggle(on)
+        eng = Engine(kind, sd, n_filter, 1, [('', 1, 'sigmoid')], precision=precision, device='cuda:0')
+        eng.plan(batch, tile)
+        val, u8 = eng.forward(x.cuda(), want_val=True, want_u8=True)
+        torch.cuda.synchronize()
+        got[on] = (val.cpu(), u8.cpu(), {n: eng.debug_activation(n, c, l).copy() for n, c, l in names})
+        assert eng.fallback_ops == 0
+        eng.close()
+    for n, _, _ in names:
+        assert np.array_equal(got[1][2][n], got[0][2][n]), n
+    assert torch.equal(got[1][0], got[0][0]) and torch.equal(got[1][1], got[0][1])
+    xf = x.float() / 255
+    with torch.no_grad():
+        ref = fwd(sd, xf)[0]
+    _parity.check(got[1][0], ref, fwd, precision, sd, xf, what=f'{kind} CTA pairs')
