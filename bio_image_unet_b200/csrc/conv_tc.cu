@@ -220,6 +220,7 @@ static int sm_count() {
 // has to be resident at once (persistent kernel with a static tile stride).
 static bool halo_try_cta2(const ConvTcArgs& a, int n_blk, HaloPlan* out, int* pairs_out) {
   if (!halo_cta2_enabled() || n_blk < 64) return false;
+  if (a.mode == EPI_UP) return false;                     // transposed convolutions are bound by their stores: measured slower in pairs
   HaloPlan pl = plan_halo(a, n_blk, true);
   if (!pl.ok) return false;
   const long long per_block = (long long)ceil_div(a.W, 8 * pl.mt) * ceil_div(a.H, 16) * a.D * a.B;

@@ -135,69 +135,157 @@ __device__ double percentile_from_hist(const unsigned long long* cum_sh, const u
   return r;
 }
 
-__global__ void __launch_bounds__(256) norm_lut_kernel(const unsigned int* __restrict__ hist_bounds,
-                                                        const unsigned int* __restrict__ hist_range,
-                                                        long long bounds_stride, long long range_stride, double q_lo,
-                                                        double q_hi, int invert, uint8_t* __restrict__ lut,
-                                                        double* __restrict__ params) {
-  __shared__ unsigned long long cum[256];
-  __shared__ double sp[4];
+// One order statistic per call site would walk a 256-bin group of the GLOBAL histogram serially (a dependent L2 load per
+// step: ~100 us per frame with one block per frame - most of a small job's run time). Here the block scans the
+// histogram cooperatively (coalesced), finds the coarse groups of the four order statistics in parallel, stages those
+// groups in shared memory for the fine search, and `kLutSplit` blocks per frame each fill one slice of the table
+// (every block repeats the cheap parameter computation). The float64 arithmetic and its order are unchanged.
+constexpr int kLutSplit = 8;
+constexpr int kLutThreads = 1024;
+
+struct OrderStat { long long k; int group; };
+
+__device__ __forceinline__ void percentile_indices(long long n, double q, long long* prev, long long* next, double* gamma) {
+  const double quant = __ddiv_rn(q, 100.0);
+  const double vi = __dmul_rn((double)(n - 1), quant);
+  *prev = (long long)floor(vi);
+  *next = *prev + 1;
+  if (vi >= (double)(n - 1)) {
+    *prev = n - 1; *next = n - 1;
+    *gamma = __dsub_rn(vi, -1.0);  // numpy subtracts the (already replaced) index -1; the lerp is between equal values
+  } else if (vi < 0.0) {
+    *prev = 0; *next = 0;
+    *gamma = vi;
+  } else {
+    *gamma = __dsub_rn(vi, (double)*prev);
+  }
+}
+__device__ __forceinline__ double percentile_lerp(double a, double b, double gamma) {
+  const double diff = __dsub_rn(b, a);
+  double r = __dadd_rn(a, __dmul_rn(diff, gamma));
+  if (gamma >= 0.5) r = __dsub_rn(b, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+  return r;
+}
+
+__global__ void __launch_bounds__(kLutThreads) norm_lut_kernel(const unsigned int* __restrict__ hist_bounds,
+                                                               const unsigned int* __restrict__ hist_range,
+                                                               long long bounds_stride, long long range_stride, double q_lo,
+                                                               double q_hi, int invert, uint8_t* __restrict__ lut,
+                                                               double* __restrict__ params) {
+  __shared__ unsigned long long cum[256];              // inclusive prefix counts over 256 groups of 256 bins
+  __shared__ unsigned int fine[4][256];                // the groups holding the four order statistics
+  __shared__ long long s_k[4];
+  __shared__ int s_g[4], s_val[4];
+  __shared__ double s_gamma[2], sp[4];
   __shared__ int s_vmin, s_vmax;
-  const int f = blockIdx.x;
+  const int f = blockIdx.x / kLutSplit, part = blockIdx.x % kLutSplit;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned int* hb = hist_bounds + (long long)f * bounds_stride;
   const unsigned int* hr = hist_range + (long long)f * range_stride;
-  // coarse counts: thread t sums bins [256 t, 256 t + 256)
-  {
-    unsigned long long s = 0;
-    for (int i = 0; i < 256; ++i) s += hb[threadIdx.x * 256 + i];
-    cum[threadIdx.x] = s;
-  }
   if (threadIdx.x == 0) { s_vmin = kHistBins; s_vmax = -1; }
   __syncthreads();
-  // value range of the data that will be normalised
-  {
-    int lo_b = kHistBins, hi_b = -1;
-    for (int i = 0; i < 256; ++i) {
-      const int b = threadIdx.x * 256 + i;
-      if (hr[b]) { if (b < lo_b) lo_b = b; if (b > hi_b) hi_b = b; }
-    }
-    if (hi_b >= 0) { atomicMin(&s_vmin, lo_b); atomicMax(&s_vmax, hi_b); }
+  // group sums (warp w: groups w, w + 32, ...; a lane reads 8 consecutive bins) and the value range of the data
+  int lo_b = kHistBins, hi_b = -1;
+  for (int g = warp; g < 256; g += kLutThreads / 32) {
+    const uint4* pb = reinterpret_cast<const uint4*>(hb + g * 256 + lane * 8);
+    const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1);
+    unsigned long long sum = (unsigned long long)b0.x + b0.y + b0.z + b0.w + b1.x + b1.y + b1.z + b1.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) cum[g] = sum;
+    const uint4* pr = reinterpret_cast<const uint4*>(hr + g * 256 + lane * 8);
+    const uint4 r0 = __ldg(pr), r1 = __ldg(pr + 1);
+    const unsigned int rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (rv[i]) { const int bin = g * 256 + lane * 8 + i; lo_b = min(lo_b, bin); hi_b = max(hi_b, bin); }
   }
-  if (threadIdx.x == 0) {
-    for (int g = 1; g < 256; ++g) cum[g] += cum[g - 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo_b = min(lo_b, __shfl_xor_sync(0xffffffffu, lo_b, o));
+    hi_b = max(hi_b, __shfl_xor_sync(0xffffffffu, hi_b, o));
+  }
+  if (lane == 0 && hi_b >= 0) { atomicMin(&s_vmin, lo_b); atomicMax(&s_vmax, hi_b); }
+  __syncthreads();
+  if (warp == 0) {                                     // inclusive scan of the 256 group sums: 8 per lane + warp scan
+    unsigned long long v[8], run = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { run += cum[lane * 8 + i]; v[i] = run; }
+    unsigned long long incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const unsigned long long excl = incl - run;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cum[lane * 8 + i] = v[i] + excl;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     const long long n = (long long)cum[255];
-    const double lo = percentile_from_hist(cum, hb, n, q_lo);
-    const double hi = percentile_from_hist(cum, hb, n, q_hi);
+    percentile_indices(n, q_lo, &s_k[0], &s_k[1], &s_gamma[0]);
+    percentile_indices(n, q_hi, &s_k[2], &s_k[3], &s_gamma[1]);
+    for (int i = 0; i < 4; ++i) s_g[i] = 255;          // k beyond the data (empty histogram): last group, like the serial walk
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {                             // the group of order statistic k: first g with cum[g] > k
+    const int g = threadIdx.x;
+    const long long below = g == 0 ? 0 : (long long)cum[g - 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if ((long long)cum[g] > s_k[i] && below <= s_k[i]) s_g[i] = g;
+  }
+  __syncthreads();
+  fine[threadIdx.x >> 8][threadIdx.x & 255] = __ldg(hb + s_g[threadIdx.x >> 8] * 256 + (threadIdx.x & 255));
+  __syncthreads();
+  if (threadIdx.x < 4) {                               // smallest bin whose cumulative count exceeds k
+    const int i = threadIdx.x, g = s_g[i];
+    long long c = g == 0 ? 0 : (long long)cum[g - 1];
+    int b = 0;
+    for (; b < 255; ++b) {
+      c += fine[i][b];
+      if (c > s_k[i]) break;
+    }
+    s_val[i] = g * 256 + b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double lo = percentile_lerp((double)s_val[0], (double)s_val[1], s_gamma[0]);
+    const double hi = percentile_lerp((double)s_val[2], (double)s_val[3], s_gamma[1]);
     // np.clip = minimum(maximum(x, lo), hi)
     const double cmin = fmin(fmax((double)s_vmin, lo), hi);
     const double cmax = fmin(fmax((double)s_vmax, lo), hi);
     const double mn = cmin;
     const double mx = __dsub_rn(cmax, mn);
     sp[0] = lo; sp[1] = hi; sp[2] = mn; sp[3] = mx;
-    if (params) { params[f * 4 + 0] = lo; params[f * 4 + 1] = hi; params[f * 4 + 2] = mn; params[f * 4 + 3] = mx; }
+    if (params && part == 0) { params[f * 4 + 0] = lo; params[f * 4 + 1] = hi; params[f * 4 + 2] = mn; params[f * 4 + 3] = mx; }
   }
   __syncthreads();
   const double lo = sp[0], hi = sp[1], mn = sp[2], mx = sp[3];
   uint8_t* out = lut + (long long)f * kHistBins;
-  for (int v = threadIdx.x; v < kHistBins; v += blockDim.x) {
-    double x = fmin(fmax((double)v, lo), hi);
-    x = __dsub_rn(x, mn);
-    x = __dmul_rn(__ddiv_rn(x, mx), 255.0);
-    if (invert) x = __dsub_rn(255.0, x);
-    // truncating float64 -> integer cast; NaN (constant image) -> 0 like the x86 cast numpy performs
-    int q = (x == x) ? (int)x : 0;
-    out[v] = (uint8_t)q;
+  constexpr int kSlice = kHistBins / kLutSplit;
+  for (int v4 = part * kSlice + 4 * threadIdx.x; v4 < (part + 1) * kSlice; v4 += 4 * kLutThreads) {
+    uint8_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double x = fmin(fmax((double)(v4 + i), lo), hi);
+      x = __dsub_rn(x, mn);
+      x = __dmul_rn(__ddiv_rn(x, mx), 255.0);
+      if (invert) x = __dsub_rn(255.0, x);
+      // truncating float64 -> integer cast; NaN (constant image) -> 0 like the x86 cast numpy performs
+      const int q = (x == x) ? (int)x : 0;
+      r[i] = (uint8_t)q;
+    }
+    *reinterpret_cast<uchar4*>(out + v4) = make_uchar4(r[0], r[1], r[2], r[3]);
   }
 }
 
 int launch_norm_lut(const unsigned int* hist_bounds, const unsigned int* hist_range, long long bounds_stride,
                     long long range_stride, int frames, double q_lo, double q_hi, int invert, uint8_t* lut,
                     double* params, cudaStream_t stream) {
-  norm_lut_kernel<<<frames, 256, 0, stream>>>(hist_bounds, hist_range, bounds_stride, range_stride, q_lo, q_hi,
-                                              invert, lut, params);
+  norm_lut_kernel<<<frames * kLutSplit, kLutThreads, 0, stream>>>(hist_bounds, hist_range, bounds_stride, range_stride,
+                                                                  q_lo, q_hi, invert, lut, params);
   BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
