@@ -35,6 +35,8 @@ SIGNATURES = {
     'biu_apply_lut_f32': (c_int, [_P, c_int, c_longlong, c_int, _P, c_longlong, _P, _P]),
     'biu_gather_tiles_f32': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                      c_int, _P, _P]),
+    'biu_gather_tiles_lut': (c_int, [_P, c_int, _P, c_longlong, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, _P, _P]),
     'biu_gather_tiles': (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                  c_int, _P, _P]),
     'biu_stitch_mean_u8': (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),

@@ -143,7 +143,14 @@ int biu_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int
 }
 int biu_gather_tiles(const uint8_t* src, int F, int Z, int H, int W, int pad_mode, const int* zs, const int* ys,
                      const int* xs, int nz, int ny, int nx, int pd, int ph, int pw, uint8_t* dst, void* stream) {
-  GatherArgs a{src, F, Z, H, W, pad_mode, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst};
+  GatherArgs a{src, 1, nullptr, 0, F, Z, H, W, pad_mode, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst};
+  return launch_gather_tiles(a, (cudaStream_t)stream);
+}
+int biu_gather_tiles_lut(const void* src, int dtype_bytes, const uint8_t* lut, long long lut_stride, int F, int Z, int H,
+                         int W, int pad_mode, const int* zs, const int* ys, const int* xs, int nz, int ny, int nx, int pd,
+                         int ph, int pw, uint8_t* dst, void* stream) {
+  BIU_REQUIRE(lut != nullptr && (dtype_bytes == 1 || dtype_bytes == 2), "gather_tiles_lut: uint8 / uint16 source and a table");
+  GatherArgs a{src, dtype_bytes, lut, lut_stride, F, Z, H, W, pad_mode, zs, ys, xs, nz, ny, nx, pd, ph, pw, dst};
   return launch_gather_tiles(a, (cudaStream_t)stream);
 }
 int biu_stitch_mean_u8(const uint8_t* tiles, int F, int C, int H, int W, const int* ys, const int* xs, int ny, int nx,

@@ -144,7 +144,10 @@ int launch_norm_lut(const unsigned int* hist_bounds, const unsigned int* hist_ra
 int launch_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
                      long long lut_stride, uint8_t* out, cudaStream_t stream);
 struct GatherArgs {
-  const uint8_t* src;           // [F][Z][H][W]
+  const void* src;              // [F][Z][H][W] uint8, or the raw uint8 / uint16 stack when `lut` is set
+  int src_bytes;                // 1 or 2
+  const uint8_t* lut;           // optional: fused normalisation, dst = lut[f * lut_stride + src] (unet/predict.py:122-131)
+  long long lut_stride;         // 65536 (one table per frame) or 0 (one table for the stack)
   int F, Z, H, W;
   int pad_mode;                 // 0 = reflect, 1 = constant zero
   const int* zs; const int* ys; const int* xs;   // device arrays of tile starts

@@ -298,32 +298,40 @@ template <typename T>
 __global__ void __launch_bounds__(256) apply_lut_kernel(const T* __restrict__ img, long long n_per_frame,
                                                          const uint8_t* __restrict__ lut, long long lut_stride,
                                                          uint8_t* __restrict__ out, int blocks_per_frame) {
+  // 16 pixels per thread: one (uint8) or two (uint16) 16-byte loads, 16 table look-ups (the table of a frame is 64 KB
+  // and stays in L1 / L2), one 16-byte store
   const int frame = blockIdx.x / blocks_per_frame;
   const int blk = blockIdx.x % blocks_per_frame;
   const T* src = img + (long long)frame * n_per_frame;
   uint8_t* dst = out + (long long)frame * n_per_frame;
   const uint8_t* l = lut + (long long)frame * lut_stride;
-  constexpr int VEC = 16 / sizeof(T);
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-  const long long nvec = aligned ? n_per_frame / VEC : 0;
+  const long long nvec = aligned ? n_per_frame / 16 : 0;
   const long long stride = (long long)blocks_per_frame * blockDim.x;
   for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
-    const T* e = reinterpret_cast<const T*>(&q);
-    uint8_t r[VEC];
+    uint8_t r[16];
+    if (sizeof(T) == 2) {
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(src) + 2 * i), q1 = __ldg(reinterpret_cast<const uint4*>(src) + 2 * i + 1);
+      const unsigned short* e0 = reinterpret_cast<const unsigned short*>(&q0);
+      const unsigned short* e1 = reinterpret_cast<const unsigned short*>(&q1);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r[k] = __ldg(l + e[k]);
-    if (VEC == 8) *reinterpret_cast<uint2*>(dst + i * VEC) = *reinterpret_cast<uint2*>(r);
-    else *reinterpret_cast<uint4*>(dst + i * VEC) = *reinterpret_cast<uint4*>(r);
+      for (int k = 0; k < 8; ++k) { r[k] = __ldg(l + e0[k]); r[8 + k] = __ldg(l + e1[k]); }
+    } else {
+      const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      const uint8_t* e0 = reinterpret_cast<const uint8_t*>(&q0);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) r[k] = __ldg(l + e0[k]);
+    }
+    *reinterpret_cast<uint4*>(dst + i * 16) = *reinterpret_cast<uint4*>(r);
   }
-  for (long long i = nvec * VEC + (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame; i += stride)
+  for (long long i = nvec * 16 + (long long)blk * blockDim.x + threadIdx.x; i < n_per_frame; i += stride)
     dst[i] = __ldg(l + src[i]);
 }
 
 int launch_apply_lut(const void* img, int dtype_bytes, long long n_per_frame, int frames, const uint8_t* lut,
                      long long lut_stride, uint8_t* out, cudaStream_t stream) {
   BIU_REQUIRE(dtype_bytes == 1 || dtype_bytes == 2, "apply_lut: only uint8/uint16 input");
-  long long work = ceil_div_ll(n_per_frame, 256LL * 16 * 4);
+  long long work = ceil_div_ll(n_per_frame, 256LL * 16 * 2);
   int bpf = (int)(work < 1 ? 1 : (work > 1184 ? 1184 : work));
   if (dtype_bytes == 2)
     apply_lut_kernel<uint16_t><<<frames * bpf, 256, 0, stream>>>((const uint16_t*)img, n_per_frame, lut, lut_stride, out, bpf);
@@ -347,12 +355,17 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
   return i < n ? i : period - i;
 }
 
+// TSRC = uint8_t: plain copy of an already normalised stack. With a.lut the normalisation is fused in: the source is
+// the raw uint8 / uint16 stack and every value goes through the frame's look-up table on its way into the tile (the
+// normalised frame is then never written). V pixels per thread (16 when the tile width allows it): runs that lie inside
+// the source row and are 16-byte aligned move as whole vectors.
+template <typename TSRC, int V>
 __global__ void __launch_bounds__(256) gather_tiles_kernel(GatherArgs a) {
   const long long tile_elems = (long long)a.pd * a.ph * a.pw;
   const long long total = (long long)a.F * a.nz * a.ny * a.nx * tile_elems;
-  for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; idx < total;
-       idx += (long long)gridDim.x * blockDim.x * 4) {
-    // 4 consecutive x (pw is a multiple of 4 for every supported tile size)
+  const TSRC* srcb = reinterpret_cast<const TSRC*>(a.src);
+  for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V; idx < total;
+       idx += (long long)gridDim.x * blockDim.x * V) {
     long long r = idx;
     const int x = (int)(r % a.pw); r /= a.pw;
     const int y = (int)(r % a.ph); r /= a.ph;
@@ -365,26 +378,50 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(GatherArgs a) {
     bool zero = false;
     if (sz >= a.Z) { if (a.pad_mode == 0) sz = reflect_index(sz, a.Z); else zero = true; }
     if (sy >= a.H) { if (a.pad_mode == 0) sy = reflect_index(sy, a.H); else zero = true; }
-    const uint8_t* row = a.src + (((long long)f * a.Z + sz) * a.H + sy) * a.W;
-    uint8_t v[4];
+    const TSRC* row = srcb + (((long long)f * a.Z + sz) * a.H + sy) * a.W;
+    const uint8_t* l = a.lut ? a.lut + (long long)f * a.lut_stride : nullptr;
+    const int sx0 = a.xs[ix] + x;
+    TSRC raw[V];
+    bool zk[V];
+    if (!zero && sx0 + V <= a.W && ((reinterpret_cast<uintptr_t>(row + sx0) & 15) == 0)) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int sx = a.xs[ix] + x + k;
-      bool zk = zero;
-      if (sx >= a.W) { if (a.pad_mode == 0) sx = reflect_index(sx, a.W); else zk = true; }
-      v[k] = zk ? 0 : __ldg(row + sx);
+      for (int q = 0; q < (int)(V * sizeof(TSRC)) / 16; ++q)
+        reinterpret_cast<uint4*>(raw)[q] = __ldg(reinterpret_cast<const uint4*>(row + sx0) + q);
+#pragma unroll
+      for (int k = 0; k < V; ++k) zk[k] = false;
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        int sx = sx0 + k;
+        zk[k] = zero;
+        if (sx >= a.W) { if (a.pad_mode == 0) sx = reflect_index(sx, a.W); else zk[k] = true; }
+        raw[k] = zk[k] ? (TSRC)0 : __ldg(row + sx);
+      }
     }
-    *reinterpret_cast<uchar4*>(a.dst + idx) = make_uchar4(v[0], v[1], v[2], v[3]);
+    uint8_t v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = zk[k] ? (uint8_t)0 : (l ? __ldg(l + raw[k]) : (uint8_t)raw[k]);
+    if (V == 16) *reinterpret_cast<uint4*>(a.dst + idx) = *reinterpret_cast<uint4*>(v);
+    else *reinterpret_cast<uchar4*>(a.dst + idx) = *reinterpret_cast<uchar4*>(v);
   }
 }
 
 int launch_gather_tiles(const GatherArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(a.pw % 4 == 0, "gather_tiles: tile width must be a multiple of 4 (got %d)", a.pw);
-  const long long total = (long long)a.F * a.nz * a.ny * a.nx * a.pd * a.ph * a.pw / 4;
+  BIU_REQUIRE(a.src_bytes == 1 || (a.src_bytes == 2 && a.lut != nullptr),
+              "gather_tiles: a uint16 source needs the look-up table of the fused normalisation");
+  const int v = (a.pw % 16 == 0) ? 16 : 4;
+  const long long total = (long long)a.F * a.nz * a.ny * a.nx * a.pd * a.ph * a.pw / v;
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (blocks < 1) blocks = 1;
-  gather_tiles_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  if (a.src_bytes == 2) {
+    if (v == 16) gather_tiles_kernel<uint16_t, 16><<<(int)blocks, 256, 0, stream>>>(a);
+    else gather_tiles_kernel<uint16_t, 4><<<(int)blocks, 256, 0, stream>>>(a);
+  } else {
+    if (v == 16) gather_tiles_kernel<uint8_t, 16><<<(int)blocks, 256, 0, stream>>>(a);
+    else gather_tiles_kernel<uint8_t, 4><<<(int)blocks, 256, 0, stream>>>(a);
+  }
   BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -396,38 +433,57 @@ int launch_gather_tiles(const GatherArgs& a, cudaStream_t stream) {
 // in tests). Gather formulation: one thread per 4 output pixels, no atomics, deterministic.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stitch_mean_kernel(StitchMeanArgs a) {
-  const int W4 = (a.W + 3) / 4;
-  const long long total = (long long)a.F * a.C * a.H * W4;
+  // 16 output pixels per thread; a covering tile contributes a run of up to 16 bytes, loaded as one vector when it
+  // lies inside the tile row and is 16-byte aligned (tile starts that are multiples of 16: every default grid)
+  const int W16 = (a.W + 15) / 16;
+  const long long total = (long long)a.F * a.C * a.H * W16;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx;
-    const int x4 = (int)(r % W4) * 4; r /= W4;
+    const int x16 = (int)(r % W16) * 16; r /= W16;
     const int y = (int)(r % a.H); r /= a.H;
     const int c = (int)(r % a.C); r /= a.C;
     const int f = (int)r;
-    unsigned int sum[4] = {0, 0, 0, 0}, cnt[4] = {0, 0, 0, 0};
+    unsigned int sum[16], cnt[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { sum[q] = 0; cnt[q] = 0; }
     for (int j = 0; j < a.ny; ++j) {
       const int ty = y - a.ys[j];
       if (ty < 0 || ty >= a.ph) continue;
       for (int k = 0; k < a.nx; ++k) {
-        const int tx0 = x4 - a.xs[k];
-        if (tx0 <= -4 || tx0 >= a.pw) continue;
+        const int tx0 = x16 - a.xs[k];
+        if (tx0 <= -16 || tx0 >= a.pw) continue;
         const uint8_t* t = a.tiles + ((((long long)f * a.ny + j) * a.nx + k) * a.C + c) * a.ph * a.pw + (long long)ty * a.pw;
+        if (tx0 >= 0 && tx0 + 16 <= a.pw && ((reinterpret_cast<uintptr_t>(t + tx0) & 15) == 0)) {
+          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(t + tx0));
+          const uint8_t* e = reinterpret_cast<const uint8_t*>(&v4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int tx = tx0 + q;
-          if (tx >= 0 && tx < a.pw) { sum[q] += __ldg(t + tx); cnt[q] += 1; }
+          for (int q = 0; q < 16; ++q) { sum[q] += e[q]; cnt[q] += 1; }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int tx = tx0 + q;
+            if (tx >= 0 && tx < a.pw) { sum[q] += __ldg(t + tx); cnt[q] += 1; }
+          }
         }
       }
     }
-    uint8_t* o = a.out + (((long long)f * a.C + c) * a.H + y) * a.W + x4;
+    uint8_t o16[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (x4 + q < a.W) o[q] = cnt[q] ? (uint8_t)(sum[q] / cnt[q]) : 0;  // uncovered -> nanmean of nothing = nan -> 0
+    for (int q = 0; q < 16; ++q)                       // uncovered -> nanmean of nothing = nan -> 0
+      o16[q] = cnt[q] ? (uint8_t)(sum[q] / cnt[q]) : (uint8_t)0;
+    uint8_t* o = a.out + (((long long)f * a.C + c) * a.H + y) * a.W + x16;
+    if (x16 + 16 <= a.W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(o16);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (x16 + q < a.W) o[q] = o16[q];
+    }
   }
 }
 int launch_stitch_mean(const StitchMeanArgs& a, cudaStream_t stream) {
-  const long long total = (long long)a.F * a.C * a.H * ((a.W + 3) / 4);
+  const long long total = (long long)a.F * a.C * a.H * ((a.W + 15) / 16);
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (blocks < 1) blocks = 1;

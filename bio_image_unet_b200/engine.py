@@ -265,6 +265,25 @@ def gather_tiles(src, zs, ys, xs, tile, pad_mode):
     return out
 
 
+def gather_tiles_lut(raw, lut, zs, ys, xs, tile, pad_mode):
+    """Normalisation fused into the tile gather: raw (F, Z, H, W) uint8 / uint16 device stack, lut (F | 1, 65536)
+    uint8 tables of norm_lut(); returns the (F*nz*ny*nx, pd, ph, pw) uint8 tiles of the normalised stack without ever
+    writing that stack."""
+    lib = _lib.load()
+    f, z, h, w = raw.shape
+    pd, ph, pw = tile
+    dev = raw.device
+    assert raw.is_contiguous() and raw.dtype in (torch.uint8, torch.uint16)
+    dzs, dys, dxs = _dev_i32(zs, dev), _dev_i32(ys, dev), _dev_i32(xs, dev)
+    out = torch.empty((f * len(zs) * len(ys) * len(xs), pd, ph, pw), dtype=torch.uint8, device=dev)
+    stride = HIST_BINS if lut.shape[0] > 1 else 0
+    with torch.cuda.device(dev):
+        _lib.check(lib.biu_gather_tiles_lut(_lib.ptr(raw), raw.element_size(), _lib.ptr(lut), stride, f, z, h, w,
+                                            int(pad_mode), _lib.ptr(dzs), _lib.ptr(dys), _lib.ptr(dxs), len(zs), len(ys),
+                                            len(xs), pd, ph, pw, _lib.ptr(out), _lib.stream_ptr()), 'biu_gather_tiles_lut')
+    return out
+
+
 def stitch_mean_u8(tiles, frames, channels, out_hw, ys, xs, tile_hw):
     """tiles (F*ny*nx, C, ph, pw) uint8 -> (F, C, H, W) uint8, sum // count over covering tiles."""
     lib = _lib.load()

@@ -135,6 +135,13 @@ int biu_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int
  * src [F][Z][H][W] uint8 -> dst [F*nz*ny*nx][pd][ph][pw]; starts are device int32 arrays. */
 int biu_gather_tiles(const uint8_t* src, int F, int Z, int H, int W, int pad_mode, const int* zs, const int* ys,
                      const int* xs, int nz, int ny, int nx, int pd, int ph, int pw, uint8_t* dst, void* stream);
+/* Same with the intensity normalisation fused in (unet/predict.py:122-131 + :152-182 in one pass): src is the RAW
+ * uint8 / uint16 stack and every value goes through lut[f * lut_stride + value] (tables of biu_norm_lut; lut_stride
+ * 65536 = one table per frame, 0 = one for the stack) on its way into the tile - the normalised stack is never written.
+ * Padding of undersized sources applies to the normalised values (zeros stay zeros, reflection commutes with the table). */
+int biu_gather_tiles_lut(const void* src, int dtype_bytes, const uint8_t* lut, long long lut_stride, int F, int Z, int H,
+                         int W, int pad_mode, const int* zs, const int* ys, const int* xs, int nz, int ny, int nx, int pd,
+                         int ph, int pw, uint8_t* dst, void* stream);
 
 /* ---- stitching: replaces Predict.__stitch -------------------------------------------------------------------*/
 /* unet/predict.py:204-229, siam_unet/predict.py:217-240: uint8(nanmean) == sum // count.
