@@ -26,6 +26,7 @@ SIGNATURES = {
     'biu_set_rows_kernel': (c_int, [c_int]),
     'biu_set_halo_cta2': (c_int, [c_int]),
     'biu_net_fallback_ops': (c_int, [_P]),
+    'biu_net_set_siam_shared': (c_int, [_P, c_int]),
     'biu_net_destroy': (None, [_P]),
     'biu_histogram': (c_int, [_P, c_int, c_longlong, c_int, _P, _P]),
     'biu_hist_sum': (c_int, [_P, c_int, _P, _P]),

@@ -83,6 +83,14 @@ int biu_net_set_force_direct(biu_net* net, int on) {
   return 0;
 }
 
+int biu_net_set_siam_shared(biu_net* net, int tiles_per_frame) {
+  BIU_REQUIRE(net && net->n, "null handle");
+  BIU_REQUIRE(tiles_per_frame >= 0, "tiles_per_frame must not be negative");
+  BIU_REQUIRE(tiles_per_frame == 0 || net->n->kind == NET_SIAM2D, "the shared twin encoder is a Siam_UNet mode");
+  net->n->siam_shared = tiles_per_frame;
+  net->n->B = 0;                            // buffer sizes change: biu_net_plan has to be called again
+  return 0;
+}
 int biu_net_fallback_ops(biu_net* net) {
   BIU_REQUIRE(net && net->n, "null handle");
   int cnt = 0;

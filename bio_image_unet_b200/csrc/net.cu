@@ -597,7 +597,8 @@ long long net_plan(Net* n, int B, int D, int H, int W) {
     int d, h, w;
     level_dims(n, b.level, &d, &h, &w);
     b.offset = off;
-    size_t bytes = (size_t)B * b.batch_mul * d * h * w * b.ctot * n->esz;
+    const size_t imgs = (b.batch_mul == 2 && n->siam_shared > 0) ? (size_t)B + n->siam_shared : (size_t)B * b.batch_mul;
+    size_t bytes = imgs * d * h * w * b.ctot * n->esz;
     off += (bytes + 1023) & ~(size_t)1023;
   }
   n->ws_bytes = off;
@@ -886,13 +887,22 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
     skip_pool = false;
     int d, h, w;
     level_dims(n, o.level, &d, &h, &w);
-    const int batch = n->B * o.batch_mul;
+    // twin-encoder buffers hold two image streams: [current (B) | previous (B)], or with the shared encoder the unique
+    // tiles, previous stream = images [0, B) and current stream = images [shared, shared + B)
+    const int shared = (n->kind == NET_SIAM2D && n->siam_mode != SIAM_CONTROL) ? n->siam_shared : 0;
+    auto stream_img0 = [&](const Buf* bf, int stream) -> size_t {
+      if (bf->batch_mul == 2 && shared > 0) return stream == 0 ? (size_t)shared : 0;
+      return (size_t)stream * n->B;
+    };
+    const int batch = (o.batch_mul == 2 && shared > 0) ? n->B + shared : n->B * o.batch_mul;
     const Buf* sb = o.src >= 0 ? &n->bufs[o.src] : nullptr;
     const Buf* db = o.dst >= 0 ? &n->bufs[o.dst] : nullptr;
     const size_t img_in = sb ? (size_t)d * h * w * sb->ctot * n->esz : 0;
-    const char* src = sb ? ws + sb->offset + (size_t)o.src_img0 * n->B * img_in : nullptr;
+    // an op that covers both streams (batch_mul 2) starts at image 0 of the buffer
+    const char* src = sb ? ws + sb->offset + (o.batch_mul == 2 ? 0 : stream_img0(sb, o.src_img0)) * img_in : nullptr;
     auto dst_ptr = [&](int dd, int hh, int ww) -> char* {
-      return db ? ws + db->offset + (size_t)o.dst_img0 * n->B * ((size_t)dd * hh * ww * db->ctot * n->esz) : nullptr;
+      return db ? ws + db->offset + (o.batch_mul == 2 ? 0 : stream_img0(db, o.dst_img0)) *
+                                        ((size_t)dd * hh * ww * db->ctot * n->esz) : nullptr;
     };
     switch (o.kind) {
       case OP_FIRST: {
@@ -901,10 +911,14 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         memset(&a, 0, sizeof(a));
         a.in_kind = in_kind;
         a.in = o.src == -1 ? in : in2;
+        if (shared > 0) {                    // one pass over the B + shared unique tiles, given as ONE array
+          if (o.src != -1) { n->op_kinds[op_index] += 32; break; }
+          BIU_REQUIRE(in2 == nullptr, "shared twin encoder: the unique tiles come as one array (no second input)");
+        }
         BIU_REQUIRE(a.in != nullptr, "network input pointer is null");
-        a.cin = n->in_ch; a.W = w; a.H = h; a.D = d; a.B = n->B; a.kd = L.kd;
+        a.cin = n->in_ch; a.W = w; a.H = h; a.D = d; a.B = shared > 0 ? n->B + shared : n->B; a.kd = L.kd;
         a.wgt = L.w_direct; a.cout = L.cout_pad; a.slope = L.slope; a.scale = L.scale; a.shift = L.shift;
-        a.esz = n->esz; a.out = dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
+        a.esz = n->esz; a.out = shared > 0 ? ws + db->offset : dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
         a.cout_pad = L.cout_pad; a.round_tf32 = round_tf32;
         if (int rc = launch_first_conv(a, stream)) return rc;
         break;
@@ -1071,8 +1085,8 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         const size_t smem = (size_t)2 * h * w * G * sizeof(float);
         BIU_REQUIRE(smem <= 200 * 1024, "Siam_UNet mode='corr': a %dx%d embedding does not fit shared memory", h, w);
         const int blocks = n->B * (sb->ctot / G);
-        const char* cur = ws + sb->offset;
-        const char* prv = ws + sb->offset + img * n->B;
+        const char* cur = ws + sb->offset + img * stream_img0(sb, 0);
+        const char* prv = ws + sb->offset + img * stream_img0(sb, 1);
         if (n->esz == 2) {
           if (smem > 48 * 1024)
             BIU_CHECK_CUDA(cudaFuncSetAttribute(xcorr_join_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1133,8 +1147,8 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         long long blocks = ceil_div_ll(nvec, 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         if (blocks < 1) blocks = 1;
-        max_join_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(ws + sb->offset),
-                                                         reinterpret_cast<const uint4*>(ws + sb->offset + img * n->B),
+        max_join_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(ws + sb->offset + img * stream_img0(sb, 0)),
+                                                         reinterpret_cast<const uint4*>(ws + sb->offset + img * stream_img0(sb, 1)),
                                                          reinterpret_cast<uint4*>(ws + db->offset), nvec, n->esz);
         BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -1163,7 +1177,8 @@ int net_debug_copy(Net* n, const char* buf_name, void* workspace, void* dst_host
     if (b.name == buf_name) {
       int d, h, w;
       level_dims(n, b.level, &d, &h, &w);
-      long long bytes = (long long)n->B * b.batch_mul * d * h * w * b.ctot * n->esz;
+      const long long imgs = (b.batch_mul == 2 && n->siam_shared > 0) ? (long long)n->B + n->siam_shared : (long long)n->B * b.batch_mul;
+      long long bytes = imgs * d * h * w * b.ctot * n->esz;
       if (bytes > max_bytes) bytes = max_bytes;
       BIU_CHECK_CUDA(cudaMemcpy(dst_host, reinterpret_cast<char*>(workspace) + b.offset, bytes, cudaMemcpyDeviceToHost));
       return 0;

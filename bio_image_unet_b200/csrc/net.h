@@ -82,6 +82,11 @@ struct Net {
   int gate_scratch = -1;            // AttentionUnet: buffer for the CUDA-core fallback of the gate GEMM
   std::vector<void*> dev_allocs;
 
+  // Siam_UNet, 'single' normalisation: frame t is the current frame of pair t and the previous frame of pair t + 1, and
+  // its encoder output is the same in both. siam_shared = tiles per frame (> 0) runs the twin encoder ONCE over the
+  // B + siam_shared unique tiles of a batch of B consecutive pairs [previous frame of the first pair | current frames]
+  // instead of over 2 B: the previous stream is images [0, B), the current stream images [siam_shared, siam_shared + B).
+  int siam_shared = 0;
   // plan
   int B = 0, D = 1, H = 0, W = 0;
   size_t ws_bytes = 0;

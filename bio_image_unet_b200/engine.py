@@ -72,9 +72,13 @@ class Engine:
         self.fallback_ops = 0
         self._fallback_checked = False
 
-    def plan(self, batch, tile):
-        """tile: (h, w) or (d, h, w)."""
+    def plan(self, batch, tile, siam_shared=0):
+        """tile: (h, w) or (d, h, w). siam_shared = tiles per frame: Siam_UNet in 'single' mode, the twin encoder runs
+        once over the batch + siam_shared unique tiles of `batch` consecutive pairs (see biu_net_set_siam_shared)."""
         d, h, w = (1, *tile) if len(tile) == 2 else tile
+        if self.kind == 'siam2d' or siam_shared:
+            _lib.check(self.lib.biu_net_set_siam_shared(self.handle, int(siam_shared)), 'biu_net_set_siam_shared')
+        self.siam_shared = int(siam_shared)
         with torch.cuda.device(self.device):
             nbytes = self.lib.biu_net_plan(self.handle, int(batch), int(d), int(h), int(w))
             if nbytes < 0:
@@ -100,7 +104,8 @@ class Engine:
         if in_kind == 1 and tiles.dtype != torch.float32:
             raise TypeError('tiles must be uint8 or float32')
         d, h, w = self.tile
-        assert tiles.numel() == self.batch * self.in_channels * d * h * w, (tiles.shape, self.batch, self.tile)
+        n_in = self.batch + getattr(self, 'siam_shared', 0)
+        assert tiles.numel() == n_in * self.in_channels * d * h * w, (tiles.shape, self.batch, self.tile)
         spatial = (h, w) if self.kind in KIND_2D else (d, h, w)
         shape = (self.batch, self.head_total, *spatial)
         val = torch.empty(shape, dtype=torch.float32, device=self.device) if want_val else None

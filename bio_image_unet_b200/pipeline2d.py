@@ -110,18 +110,36 @@ class BatchPlanner:
     def __init__(self, engine, workspace_bytes):
         self.engine, self.workspace_bytes = engine, workspace_bytes
         self.tile, self.budget_batch, self.tile_batch = None, None, None
+        self.plan_kwargs = {}                      # e.g. siam_shared=tiles per frame (Engine.plan)
 
     def ensure(self, tile, total_tiles):
         tile = tuple(int(v) for v in tile)
-        if self.tile != tile:
+        key = (tile, tuple(sorted(self.plan_kwargs.items())))
+        if self.tile != key:
             per_tile = self.engine.plan(1, tile)
             self.budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
-            self.tile, self.tile_batch = tile, None
+            self.tile, self.tile_batch = key, None
         target = even_batch(total_tiles, self.budget_batch)
         if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
-            self.engine.plan(target, tile)
+            self.engine.plan(target, tile, **self.plan_kwargs)
             self.tile_batch = target
         return self.tile_batch
+
+
+def run_tiles_shared(eng, tiles_u, tile_batch, n_per):
+    """Siam_UNet with the shared twin encoder: tiles_u = [tiles of the previous frame of the first pair | tiles of the
+    current frames] (n_pairs + n_per tiles); pair j = (previous tile j, current tile j + n_per). Batches of `tile_batch`
+    pairs take the contiguous slice of tile_batch + n_per unique tiles they need (the tail batch is zero-padded)."""
+    n_pairs = tiles_u.shape[0] - n_per
+    outs = []
+    for s in range(0, n_pairs, tile_batch):
+        cnt = min(tile_batch, n_pairs - s)
+        t = tiles_u[s:s + cnt + n_per]
+        if cnt < tile_batch:
+            t = torch.cat((t, torch.zeros((tile_batch - cnt, *t.shape[1:]), dtype=t.dtype, device=t.device)))
+        _, u8 = eng.forward(t.contiguous(), None, want_val=False, want_u8=True)
+        outs.append(u8[:cnt])
+    return outs[0] if len(outs) == 1 else torch.cat(outs)
 
 
 def pick_tile_batch(eng, tile, total_tiles, budget_bytes):
@@ -140,15 +158,19 @@ def check_starts(starts, tile, extent):
                              f'(image smaller than resize_dim with add_tile > 0)')
 
 
-def predict_frames_2d(eng, norm_u8, resize_dim, add_tile, out_channels, tile_batch, pad_mode=0):
-    """norm_u8: (F, H, W) uint8 device tensor (already normalised). Returns ((F, C, H, W) uint8 device tensor,
-    grid, tiles, result_tiles)."""
-    f, h, w = norm_u8.shape
+def predict_frames_2d(eng, norm_u8, resize_dim, add_tile, out_channels, tile_batch, pad_mode=0, raw=None, lut=None):
+    """norm_u8: (F, H, W) uint8 device tensor (already normalised) - or None with `raw` (the uint8 / uint16 stack) and
+    `lut` (its normalisation tables): the normalisation is then fused into the tile gather and the normalised stack
+    is never written. Returns ((F, C, H, W) uint8 device tensor, grid, tiles, result_tiles)."""
+    f, h, w = (norm_u8 if norm_u8 is not None else raw).shape
     th, tw = resize_dim
     n_x, n_y, xs, ys = tiling.grid_2d(h, w, resize_dim, add_tile)
     check_starts(xs, th, h)
     check_starts(ys, tw, w)
-    tiles = E.gather_tiles(norm_u8.view(f, 1, h, w), [0], xs, ys, (1, th, tw), pad_mode)      # (F*N, 1, th, tw)
+    if norm_u8 is not None:
+        tiles = E.gather_tiles(norm_u8.view(f, 1, h, w), [0], xs, ys, (1, th, tw), pad_mode)  # (F*N, 1, th, tw)
+    else:
+        tiles = E.gather_tiles_lut(raw.view(f, 1, h, w), lut, [0], xs, ys, (1, th, tw), pad_mode)
     res_u8, _ = run_tiles(eng, tiles, tile_batch)
     out = E.stitch_mean_u8(res_u8, f, out_channels, (h, w), xs, ys, (th, tw))
     return out, (n_x, n_y, xs, ys), tiles, res_u8

@@ -71,6 +71,10 @@ class Session:
                              siam_mode=params['mode'], precision=precision, device=self.device)
         self.tile_batch = None
         self._planner = P.BatchPlanner(self.engine, self.workspace_bytes)
+        # per-frame normalisation + a join that uses the previous frame: frame t's encoder pass serves pair t (as the
+        # current frame) and pair t + 1 (as the previous one) - it runs once (biu_net_set_siam_shared)
+        self.shared_encoder = normalization_mode == 'single' and params['mode'] != 'control'
+        self.siam_mode = params['mode']
         self._pin, self._streams, self._dev_in = {}, None, None
         self.last = {}
 
@@ -79,8 +83,20 @@ class Session:
         rd = self.resize_dim if self.resize_dim is not None else (h, w)
         return (rd, *P.tiling.grid_2d(h, w, rd, self.add_tile))
 
-    def _ensure_plan(self, rd, total_tiles):
+    def _ensure_plan(self, rd, total_tiles, n_per=0):
+        self._planner.plan_kwargs = {'siam_shared': n_per} if (self.shared_encoder and n_per) else {}
         self.tile_batch = self._planner.ensure(rd, total_tiles)
+
+    def chunk_frames(self, n_frames, s, e):
+        """Frames a chunk of pairs [s, e) needs, in upload order, and the (previous, current) position of every pair.
+        Shared encoder: [previous frame of pair s, frames s .. e-1] - pair j is (position j, position j + 1)."""
+        prev_idx, cur_idx = self.pair_indices(n_frames, s, e)
+        if self.shared_encoder:
+            needed = [prev_idx[0]] + cur_idx
+            return needed, list(range(e - s)), list(range(1, e - s + 1))
+        needed = sorted(set(prev_idx + cur_idx))
+        pos = {f: j for j, f in enumerate(needed)}
+        return needed, [pos[f] for f in prev_idx], [pos[f] for f in cur_idx]
 
     @staticmethod
     def pair_indices(n_frames, lo, hi):
@@ -98,6 +114,19 @@ class Session:
         n_pairs = int(c_sel.shape[0])
         q_lo, q_hi = self.clip_threshold
         hist = P.E.histogram(frames)
+        if self.shared_encoder:
+            # frames = [previous frame of the first pair | current frames] (chunk_frames): every frame is normalised on
+            # its own statistics (:128-136) inside the tile gather, and its tiles go through the encoder once
+            assert k == n_pairs + 1, 'shared encoder: the stack must hold the n_pairs + 1 frames of chunk_frames()'
+            P.check_starts(xs, th, h)
+            P.check_starts(ys, tw, w)
+            lut, _ = P.E.norm_lut(hist, hist, k, q_lo, q_hi, self.invert)
+            tiles_u = P.E.gather_tiles_lut(frames.contiguous().view(k, 1, h, w), lut, [0], xs, ys, (1, th, tw), 1)
+            n_per = n_x * n_y
+            res_u8 = P.run_tiles_shared(self.engine, tiles_u, self.tile_batch, n_per)
+            st = P.E.stitch_mean_u8(res_u8, n_pairs, 1, (h, w), xs, ys, (th, tw))
+            self.last = dict(tiles_cur=tiles_u[n_per:], tiles_prev=tiles_u[:n_pairs * n_per], result_tiles=res_u8) if keep else {}
+            return st
         if self.normalization_mode == 'single':       # each frame on its own statistics (:128-136)
             lut, _ = P.E.norm_lut(hist, hist, k, q_lo, q_hi, self.invert)
             norm = P.E.apply_lut(frames, lut)
@@ -136,9 +165,9 @@ class Session:
         if hi <= lo:
             return
         if chunk_pairs is None:
-            self._ensure_plan(rd, (hi - lo) * n_per)
+            self._ensure_plan(rd, (hi - lo) * n_per, n_per)
             chunk_pairs = max(1, min(hi - lo, max(1, self.tile_batch // n_per)))
-        self._ensure_plan(rd, min(hi - lo, chunk_pairs) * n_per)
+        self._ensure_plan(rd, min(hi - lo, chunk_pairs) * n_per, n_per)
         tdtype = {np.dtype('uint8'): torch.uint8, np.dtype('uint16'): torch.uint16}.get(np.dtype(source.dtype))
         if tdtype is None:
             raise TypeError(f'bio_image_unet_b200 normalises uint8 / uint16 movies on the device; got {source.dtype}')
@@ -174,14 +203,12 @@ class Session:
             for i, s in enumerate(it):
                 b = i & 1
                 e = min(s + chunk_pairs, hi)
-                prev_idx, cur_idx = self.pair_indices(source.n, s, e)
-                needed = sorted(set(prev_idx + cur_idx))
-                pos = {f: j for j, f in enumerate(needed)}
+                needed, p_pos, c_pos = self.chunk_frames(source.n, s, e)
                 k = len(needed)
                 ev_in[b].synchronize()                  # the H2D copy that last read this staging buffer is done
                 source.read_into(stage[b].numpy(), needed)      # host work overlaps the previous chunk's kernels
-                p_sel = P.E._dev_i64([pos[f] for f in prev_idx], dev)
-                c_sel = P.E._dev_i64([pos[f] for f in cur_idx], dev)
+                p_sel = P.E._dev_i64(p_pos, dev)
+                c_sel = P.E._dev_i64(c_pos, dev)
                 with torch.cuda.stream(s_in):
                     s_in.wait_event(ev_done[b])         # the compute that last read dev_in[b] is done
                     dev_in[b][:k].copy_(stage[b][:k], non_blocking=True)

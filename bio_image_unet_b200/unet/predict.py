@@ -76,6 +76,18 @@ class Session:
         lut, _ = P.E.norm_lut(bounds, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
         return lut
 
+    def lut_device(self, frames_dev, lut=None):
+        """uint8 normalisation tables of an integer device stack: (F, 65536) in 'single' mode (per-frame statistics,
+        unet/predict.py:123-131), (1, 65536) otherwise."""
+        lut = lut if lut is not None else self.fixed_lut
+        if lut is None and self.normalization_mode != 'single':     # the stack given here IS the whole stack
+            lut = self.stack_lut(frames_dev, max(1, frames_dev.shape[0]))
+        if lut is None:
+            hist = P.E.histogram(frames_dev)
+            lut, _ = P.E.norm_lut(hist, hist, frames_dev.shape[0], self.clip_threshold[0], self.clip_threshold[1],
+                                  self.invert)
+        return lut
+
     def normalise_device(self, frames_dev, lut=None):
         if frames_dev.dtype == torch.float32:
             # float stacks: exact float32 percentiles by radix select; 'first' / 'all' need the whole stack in one call
@@ -83,25 +95,29 @@ class Session:
                                            self.clip_threshold[1], self.invert, want_f32=True)
             self.last_norm_f32 = f32
             return u8
-        lut = lut if lut is not None else self.fixed_lut
-        if lut is None and self.normalization_mode != 'single':     # the stack given here IS the whole stack
-            lut = self.stack_lut(frames_dev, max(1, frames_dev.shape[0]))
-        if lut is not None:
-            return P.E.apply_lut(frames_dev, lut)
-        return P.Normalizer2D('single', self.clip_threshold, self.invert)(frames_dev)
+        return P.E.apply_lut(frames_dev, self.lut_device(frames_dev, lut))
 
-    def predict_device(self, frames_dev, keep=False, lut=None, planned=False):
+    def predict_device(self, frames_dev, keep=False, lut=None, planned=False, want_norm=None):
         """(F, H, W) uint8/uint16/float32 device tensor -> (F, C, H, W) uint8 device tensor. `lut`: stack-wide LUT when
-        the frames are one chunk of a longer stack ('first' / 'all'); `planned`: the caller already sized the plan."""
+        the frames are one chunk of a longer stack ('first' / 'all'); `planned`: the caller already sized the plan.
+        Unless the normalised frames are wanted (`want_norm`, default = keep) the normalisation of an integer stack
+        is fused into the tile gather and the normalised stack is never materialised."""
         f, h, w = frames_dev.shape
         if not planned:
             n_x, n_y, _, _ = P.tiling.grid_2d(h, w, self.resize_dim, self.add_tile)
             self._ensure_plan(f * n_x * n_y)
-        norm = self.normalise_device(frames_dev, lut)
-        out, grid, tiles, res_tiles = P.predict_frames_2d(self.engine, norm, self.resize_dim, self.add_tile,
-                                                          self.out_channels, self.tile_batch)
-        if frames_dev.dtype == torch.float32:      # what the reference stores back into a float stack (:131)
-            norm = self.last_norm_f32
+        want_norm = keep if want_norm is None else want_norm
+        if frames_dev.dtype == torch.float32 or want_norm:
+            norm = self.normalise_device(frames_dev, lut)
+            out, grid, tiles, res_tiles = P.predict_frames_2d(self.engine, norm, self.resize_dim, self.add_tile,
+                                                              self.out_channels, self.tile_batch)
+            if frames_dev.dtype == torch.float32:      # what the reference stores back into a float stack (:131)
+                norm = self.last_norm_f32
+        else:
+            norm = None
+            out, grid, tiles, res_tiles = P.predict_frames_2d(self.engine, None, self.resize_dim, self.add_tile,
+                                                              self.out_channels, self.tile_batch,
+                                                              raw=frames_dev.contiguous(), lut=self.lut_device(frames_dev, lut))
         self.last = dict(grid=grid, norm=norm, tiles=tiles if keep else None, result_tiles=res_tiles if keep else None)
         return out
 
@@ -182,7 +198,7 @@ class Session:
                 with torch.cuda.stream(s_comp):
                     if not resident:
                         s_comp.wait_event(ev_in[b])
-                    res = self.predict_device(src if resident else dev_in[b][:n], lut=lut, planned=True)
+                    res = self.predict_device(src if resident else dev_in[b][:n], lut=lut, planned=True, want_norm=want_norm)
                     norm = self.last['norm'] if want_norm else None
                     if out_dev is not None:
                         out_dev[s0:s0 + n].copy_(res)

@@ -86,10 +86,10 @@ class Session:
         lut, _ = P.E.norm_lut(total, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
         n_local = (r_hi - r_lo) * n_xy
         if n_local > 0:
-            norm = P.E.apply_lut(slab_dev, lut)                                  # (b - a, X, Y) uint8
+            # normalisation fused into the patch gather: the normalised (b - a, X, Y) slab is never written
+            patches = P.E.gather_tiles_lut(slab_dev.contiguous().view(1, b - a, x, y), lut, [v - a for v in zs[r_lo:r_hi]],
+                                           self.X_start, self.Y_start, (d, h, w), 0)
             del slab_dev
-            patches = P.E.gather_tiles(norm.view(1, b - a, x, y), [v - a for v in zs[r_lo:r_hi]], self.X_start,
-                                       self.Y_start, (d, h, w), 0)
             tile_batch = self._plan((d, h, w), n_local)
             res_local, _ = P.run_tiles(self.engine, patches.reshape(n_local, 1, d, h, w), tile_batch)
             res_local = res_local.reshape(n_local, d, h, w)

@@ -76,6 +76,14 @@ int biu_net_set_force_direct(biu_net* net, int on);
 /* Test hook: 0 = run MaxPool2d as its own kernel instead of fusing it into the preceding block's epilogue
  * (default 1; both give bit-identical activations). */
 int biu_net_set_fuse_pool(biu_net* net, int on);
+/* Siam_UNet with per-frame ('single') normalisation (siam_unet/predict.py:102-136, siam_unet/siam_unet.py:85-112): frame t
+ * is the current frame of pair t and the previous frame of pair t + 1 and its normalised tiles - hence its encoder
+ * output - are the same in both. tiles_per_frame > 0 makes the following biu_net_plan(batch B, ...) / biu_net_forward
+ * run the shared-weight encoder ONCE over the B + tiles_per_frame unique tiles of B consecutive tile pairs: `in` then
+ * holds [tiles of the previous frame of the first pair | tiles of the current frames] (B + tiles_per_frame tiles, `in2`
+ * null); pair j uses tile j as its previous and tile j + tiles_per_frame as its current frame. 0 restores the two-input
+ * form. Results are bit-identical; 21 % of the reference's FLOPs are not executed. */
+int biu_net_set_siam_shared(biu_net* net, int tiles_per_frame);
 /* Number of convolution / transposed-convolution / gate ops of the most recent biu_net_forward that a tensor-core
  * mode (bf16 / tf32) had to run on the CUDA-core kernels because the tile shape is outside what the tcgen05 kernels
  * take (planes narrower than 8 px, ...). 0 in the exact-fp32 mode's sense of "as requested"; the Python Predict

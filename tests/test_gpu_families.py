@@ -339,3 +339,40 @@ def test_nested_module_eval_forward_and_dilation():
     d = MultiOutputNestedUNet(1, heads, 8, dilation=(1, 2, 1, 1, 1)).eval().cuda()
     with pytest.raises(NotImplementedError):
         d(x.cuda())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('mode', ['concat', 'max', 'corr'])
+def test_siam_shared_encoder_is_bit_identical(mode, precision):
+    """'single' normalisation: frame t's encoder pass is the same in pair t (current) and pair t + 1 (previous), so the
+    Session runs the shared-weight encoder once per frame (biu_net_set_siam_shared). Against the two-pass form: the
+    same stitched pages, bit for bit - including frame 0, which is paired with frame 1 (siam_unet/predict.py:108-112),
+    chunk boundaries and a zero-padded tail batch."""
+    from bio_image_unet_b200.siam_unet import Session, Siam_UNet
+    from bio_image_unet_b200.siam_unet.predict import _ArraySource
+    torch.manual_seed(4)
+    sd = Siam_UNet(n_filter=16, mode=mode).state_dict()
+    g = torch.Generator().manual_seed(2)
+    for k, v in sd.items():
+        if k.endswith('running_var') or k.endswith('.1.weight'):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith('running_mean') or k.endswith('.1.bias'):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+    movie = np.random.default_rng(9).integers(0, 4096, (7, 96, 160)).astype('uint16')
+    outs = {}
+    for shared in (True, False):
+        ses = Session({'state_dict': sd, 'n_filter': 16, 'mode': mode}, resize_dim=(64, 64), add_tile=1, device='cuda:0',
+                      precision=precision, workspace_gb=4.0)
+        assert ses.shared_encoder
+        ses.shared_encoder = shared
+        out = np.zeros((7, 96, 160), dtype='uint8')
+
+        def sink(first, pages):
+            out[first:first + len(pages)] = pages
+        ses.predict_stream(_ArraySource(movie), 0, 7, sink, chunk_pairs=3)
+        outs[shared] = out.copy()
+        ses.close()
+    assert outs[True].std() > 0 and np.array_equal(outs[True], outs[False])
+    ref = opipe.siam_predict(movie.copy(), sd, mode, (64, 64), False, 'single', (0.0, 99.98), 1)
+    if precision == 'fp32':
+        assert np.abs(outs[True].astype(np.int16) - ref.astype(np.int16)).max() <= 1
