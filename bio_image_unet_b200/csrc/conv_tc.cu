@@ -328,7 +328,8 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   if (a.n_total != 16 && a.n_total != 32 && !wide) return pl;
   if (a.W < 128) return pl;                                  // one MMA tile = 128 consecutive pixels of a row
   if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
-  if (a.pool_out != nullptr && (a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1))) return pl;
+  // fused max-pool: every plane is pooled in (y, x); 3D callers reduce the z pairs afterwards (conv_tc_can_fuse_pool_xy)
+  if (a.pool_out != nullptr && ((a.H & 1) || (a.W & 1) || a.n_total > 32)) return pl;
   const int ck = pick_ck(a.cin, a.esz);
   if (ck == 0) return pl;
   const int rb = ck * a.esz, chunks = a.cin / ck, nfold = 3 * a.n_total;
@@ -416,6 +417,11 @@ static int choose_n_blk(const ConvTcArgs& a) {
   return n_blk;
 }
 
+bool conv_tc_can_fuse_pool_xy(const ConvTcArgs& a) {
+  // 3D blocks: only the row kernel pools (plane by plane, in y and x)
+  if (!conv_tc_supported(a) || a.mode != EPI_CONV || a.kd != 3 || (a.H & 1) || (a.W & 1) || (a.D & 1)) return false;
+  return plan_rows(a).ok;
+}
 bool conv_tc_can_fuse_pool(const ConvTcArgs& a) {
   if (!conv_tc_supported(a) || a.mode != EPI_CONV || a.kd != 1 || a.D != 1 || (a.H & 1) || (a.W & 1)) return false;
   return plan_rows(a).ok || plan_halo(a, choose_n_blk(a)).ok;

@@ -574,13 +574,15 @@ __global__ void __launch_bounds__(256) pool2_kernel(PoolArgs a) {
   // output rows flattened over the threads, one 64-bit division per thread and 32-bit arithmetic below it;
   // consecutive threads read consecutive vectors of
   // consecutive input voxels (x = 2 ox, 2 ox + 1 are adjacent), i.e. contiguous runs of the 2 (x 2) input rows
-  const int oW = a.W / 2, oH = a.H / 2, oD = a.dims == 3 ? a.D / 2 : a.D;
+  const bool zonly = a.mode == 2;                   // input already pooled in (y, x): reduce the z pairs
+  const int oW = zonly ? a.W : a.W / 2, oH = zonly ? a.H : a.H / 2, oD = a.dims == 3 ? a.D / 2 : a.D;
   const int cv = a.c / VEC;
   const int rows = a.B * oD * oH, per_row = oW * cv;
   const T* in = reinterpret_cast<const T*>(a.in);
   T* out = reinterpret_cast<T*>(a.out);
-  const int nz = (a.dims == 3 && a.mode == 0) ? 2 : 1;
+  const int nz = (a.dims == 3 && a.mode != 1) ? 2 : 1;
   const int nyx = a.mode == 0 ? 2 : 1;
+  const int xy = zonly ? 1 : 2;
   const int zs = a.dims == 3 ? 2 : 1;
   const long long i_y = (long long)a.W * a.in_ctot, i_z = (long long)a.H * a.W * a.in_ctot;
   const long long total = (long long)rows * per_row;
@@ -589,13 +591,13 @@ __global__ void __launch_bounds__(256) pool2_kernel(PoolArgs a) {
       const int row = (int)(idx / per_row), i = (int)(idx - (long long)row * per_row);
       const int y = row % oH, bz = row / oH;
       const int z = bz % oD, b = bz / oD;
-      const T* i00 = in + ((((long long)b * a.D + zs * z) * a.H + 2 * y) * a.W) * a.in_ctot + a.in_coff;
+      const T* i00 = in + ((((long long)b * a.D + zs * z) * a.H + xy * y) * a.W) * a.in_ctot + a.in_coff;
       T* orow = out + (long long)row * oW * a.out_ctot + a.out_coff;
       const int x = i / cv, c = (i - x * cv) * VEC;
       float m[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
-      const T* ip = i00 + (long long)(2 * x) * a.in_ctot + c;
+      const T* ip = i00 + (long long)(xy * x) * a.in_ctot + c;
       for (int dz = 0; dz < nz; ++dz)
         for (int dy = 0; dy < nyx; ++dy)
           for (int dx = 0; dx < nyx; ++dx) {
@@ -618,7 +620,8 @@ int launch_pool2(const PoolArgs& a, cudaStream_t stream) {
   BIU_REQUIRE(a.c % vec == 0 && a.in_ctot % vec == 0 && a.in_coff % vec == 0 && a.out_ctot % vec == 0 &&
                   a.out_coff % vec == 0,
               "pool2: channel counts must be multiples of %d", vec);
-  long long blocks = ceil_div_ll((long long)a.B * (a.dims == 3 ? a.D / 2 : a.D) * (a.H / 2) * (a.W / 2) * (a.c / vec), 256);
+  const int oh = a.mode == 2 ? a.H : a.H / 2, ow = a.mode == 2 ? a.W : a.W / 2;
+  long long blocks = ceil_div_ll((long long)a.B * (a.dims == 3 ? a.D / 2 : a.D) * oh * ow * (a.c / vec), 256);
   if (blocks > 148LL * 16) blocks = 148LL * 16;
   if (blocks < 1) blocks = 1;
   if (a.esz == 2) pool2_kernel<__nv_bfloat16, 8><<<(int)blocks, 256, 0, stream>>>(a);

@@ -39,6 +39,7 @@ struct ConvTcArgs {
 };
 bool conv_tc_supported(const ConvTcArgs& a);
 bool conv_tc_can_fuse_pool(const ConvTcArgs& a);
+bool conv_tc_can_fuse_pool_xy(const ConvTcArgs& a);   // 3D: the row kernel pools every plane in (y, x) only
 void conv_halo_set_cta2(int on);      // test hook: CTA pairs (tcgen05.mma.cta_group::2) in the halo-tile kernel (default on)
 void conv_rows_set_enabled(int on);   // test hook: route narrow 3x3 blocks through the row-streaming kernel (default on)
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
@@ -102,7 +103,8 @@ struct PoolArgs {
   int in_ctot, in_coff, c;
   int W, H, D, B;               // input extents
   int dims;                     // 2: pool (h,w); 3: pool (d,h,w)
-  int mode;                     // 0 = max, 1 = nearest (take the even-index sample)
+  int mode;                     // 0 = max, 1 = nearest (take the even-index sample), 2 = max over z pairs only (the
+                                // input is already pooled in y and x: extents W, H are those of the output)
   void* out;                    // [B][D'][H/2][W/2][out_ctot]
   int out_ctot, out_coff;
 };

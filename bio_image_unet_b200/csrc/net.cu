@@ -240,6 +240,7 @@ int net_build(Net* n) {
       d_b[l] = l > 0 ? b.buf("d" + std::to_string(2 * (2 - l) + 2), l, pad16(dec_out[l])) : -1;
       upt[l] = (interp && !tri) ? b.buf("upn" + std::to_string(3 - l), l, pad16(up_c[l])) : -1;
     }
+    if (pad16(dec_mid[0]) >= pad16(c_b[0])) n->pool_scratch = d_a[0];
     for (int l = 0; l < 3; ++l) {
       const std::string n1 = "encode" + std::to_string(2 * l + 1), n2 = "encode" + std::to_string(2 * l + 2);
       if (l == 0) {
@@ -955,7 +956,31 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
               else a.pool_out = nullptr;
             }
           }
+          // MaxPool3d(2) after a full-resolution block (unet3d/unet3d.py:66-73): the row kernel's epilogue pools every
+          // plane in (y, x) into an idle decoder buffer, a second pass over a quarter of the data reduces the z pairs
+          bool zpairs = false;
+          PoolArgs zp;
+          if (!head && n->dims == 3 && !n->no_fuse && o.level == 0 && n->pool_scratch >= 0 &&
+              op_index + 1 < (int)n->ops.size()) {
+            const Op& nx = n->ops[op_index + 1];
+            if (nx.kind == OP_POOL && nx.pool_mode == 0 && nx.src == o.dst && nx.src_coff == o.dst_coff &&
+                nx.c == L.cout_pad && nx.batch_mul == 1 && o.batch_mul == 1 && nx.level == 0) {
+              const Buf& sc = n->bufs[n->pool_scratch];
+              const Buf& pb = n->bufs[nx.dst];
+              a.pool_out = ws + sc.offset; a.pool_ctot = L.cout_pad; a.pool_coff = 0;
+              if (conv_tc_can_fuse_pool_xy(a)) {
+                zpairs = skip_pool = true;
+                memset(&zp, 0, sizeof(zp));
+                zp.esz = n->esz; zp.in = a.pool_out; zp.in_ctot = L.cout_pad; zp.in_coff = 0; zp.c = L.cout_pad;
+                zp.W = w / 2; zp.H = h / 2; zp.D = d; zp.B = batch; zp.dims = 3; zp.mode = 2;
+                zp.out = ws + pb.offset; zp.out_ctot = pb.ctot; zp.out_coff = nx.dst_coff;
+              } else {
+                a.pool_out = nullptr;
+              }
+            }
+          }
           if (int rc = launch_conv_tc(a, stream)) return rc;
+          if (zpairs) { if (int rc = launch_pool2(zp, stream)) return rc; }
         } else {
           n->op_kinds[op_index] += 16;
           DirectConvArgs da;

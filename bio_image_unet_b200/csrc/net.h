@@ -80,6 +80,8 @@ struct Net {
   float* head_w = nullptr;
   float* head_b = nullptr;
   int gate_scratch = -1;            // AttentionUnet: buffer for the CUDA-core fallback of the gate GEMM
+  int pool_scratch = -1;            // UNet3D: a level-0 decoder buffer, idle during the encoder, that takes the (y, x)-pooled
+                                    // planes the row kernel's epilogue writes before the z pairs are reduced
   std::vector<void*> dev_allocs;
 
   // Siam_UNet, 'single' normalisation: frame t is the current frame of pair t and the previous frame of pair t + 1, and

@@ -383,7 +383,8 @@ __global__ void __launch_bounds__(256) gather_tiles_kernel(GatherArgs a) {
     const int sx0 = a.xs[ix] + x;
     TSRC raw[V];
     bool zk[V];
-    if (!zero && sx0 + V <= a.W && ((reinterpret_cast<uintptr_t>(row + sx0) & 15) == 0)) {
+    constexpr bool kVec = (V * sizeof(TSRC)) % 16 == 0;       // whole 16-byte vectors only (V = 4 runs stay scalar)
+    if (kVec && !zero && sx0 + V <= a.W && ((reinterpret_cast<uintptr_t>(row + sx0) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < (int)(V * sizeof(TSRC)) / 16; ++q)
         reinterpret_cast<uint4*>(raw)[q] = __ldg(reinterpret_cast<const uint4*>(row + sx0) + q);
