@@ -457,12 +457,14 @@ class Cfg4(Workload):
         self.params = {'state_dict': sd, 'n_filter': 16, 'in_channels': 1, 'out_channels': 1}
         self.ses = Session(self.params, self.PATCH, add_patch=self.args.add_patch, device=self.device,
                            precision=self.precision, workspace_gb=60.0, dist=self.ctx)
+        if getattr(self.args, 'vol', None):          # profiling runs: a smaller volume (tools/profile_step.py --vol)
+            self.VOL = tuple(int(v) for v in self.args.vol.split(','))
         vol = np.random.default_rng(0).integers(0, 4096, self.VOL).astype('uint16')
         self.host = torch.from_numpy(vol).pin_memory()
         self.dev = self.host.to(self.device)
         nvox = float(np.prod(self.VOL))
         self.units_per_step = nvox / 1e6
-        n_patches = 256 if self.args.add_patch == 0 else 550
+        n_patches = int(np.prod([-(-v // p) for v, p in zip(self.VOL, self.PATCH)])) if self.args.add_patch == 0 else 550
         self.flop_per_step = n_patches * float(np.prod(self.PATCH)) * FLOP_UNET3D16_PER_VOXEL
         self.h2d_bytes, self.d2h_bytes = int(nvox) * 2, int(nvox)
         self.config = {'workload': self.name, 'patches_per_step': n_patches, 'add_patch': self.args.add_patch,
@@ -750,6 +752,7 @@ def main():
     ap.add_argument('--frames', type=int, default=None, help='frames (cfg 2/3) or volumes (cfg 5) per step')
     ap.add_argument('--chunk-frames', type=int, default=8)
     ap.add_argument('--add-patch', type=int, default=0)
+    ap.add_argument('--vol', default=None, help=argparse.SUPPRESS)
     ap.add_argument('--precision', default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true')
