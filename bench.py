@@ -385,7 +385,7 @@ class Cfg3(Workload):
         self.params = {'state_dict': sd, 'n_filter': 32, 'mode': 'concat'}
         self.ses = Session(self.params, resize_dim=(512, 512), add_tile=1, device=self.device, precision=self.precision,
                            workspace_gb=40.0)
-        self.n = self.args.frames or 32
+        self.n = self.args.frames or 64
         movie = synth_frames(self.n, (1024, 1024))
         self.host = torch.from_numpy(movie).pin_memory()
         self.source = _ArraySource(self.host.numpy())

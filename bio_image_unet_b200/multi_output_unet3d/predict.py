@@ -107,8 +107,10 @@ class Session:
                 self._s_out = torch.cuda.Stream(dev)
             self._s_out.wait_stream(torch.cuda.current_stream(dev))
         if hi > lo:
-            tile_batch = self._plan(self.patch_size, (hi - lo) * self.N_per_vol)
-            vols_per_chunk = max(1, (2 * tile_batch) // self.N_per_vol)
+            vols_per_chunk = max(1, min(hi - lo, self._planner.budget(self.patch_size) // self.N_per_vol))
+            if hi - lo > 1:          # at least four chunks, so that the D2H copy of a chunk's result overlaps the next one
+                vols_per_chunk = min(vols_per_chunk, max(1, -(-(hi - lo) // 4)))
+            tile_batch = self._plan(self.patch_size, vols_per_chunk * self.N_per_vol)
             it = range(0, hi - lo, vols_per_chunk)
             if show_progress and self.dist.rank == 0 and progress_notifier is not None:
                 it = progress_notifier.iterator(it)

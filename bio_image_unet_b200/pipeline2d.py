@@ -112,13 +112,19 @@ class BatchPlanner:
         self.tile, self.budget_batch, self.tile_batch = None, None, None
         self.plan_kwargs = {}                      # e.g. siam_shared=tiles per frame (Engine.plan)
 
-    def ensure(self, tile, total_tiles):
+    def budget(self, tile):
+        """Largest tile batch the workspace budget holds for this tile size."""
         tile = tuple(int(v) for v in tile)
         key = (tile, tuple(sorted(self.plan_kwargs.items())))
         if self.tile != key:
             per_tile = self.engine.plan(1, tile)
             self.budget_batch = int(max(1, self.workspace_bytes // max(per_tile, 1)))
             self.tile, self.tile_batch = key, None
+        return self.budget_batch
+
+    def ensure(self, tile, total_tiles):
+        tile = tuple(int(v) for v in tile)
+        self.budget(tile)
         target = even_batch(total_tiles, self.budget_batch)
         if self.tile_batch is None or target > self.tile_batch or 2 * target <= self.tile_batch:
             self.engine.plan(target, tile, **self.plan_kwargs)
