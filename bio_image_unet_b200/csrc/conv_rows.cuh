@@ -60,6 +60,13 @@ struct ConvRowsParams {
   uint32_t w_tile_bytes;         // one folded weight tile [(dy, co)][ck]; kd * 3 * cin_chunks of them
   int t_slots;                   // TMEM ring: 512 / cp slots of cp columns (one per output row)
   int pipes;                     // 1 or 2 independent pipelines (producer + MMA warp + epilogue groups) per CTA
+  // PLANE mode (3D blocks on planes narrower than 128 px): the M tile is a 16 x 8 pixel tile of one plane, a ring slot
+  // holds its 18 x 10 halo tile (all nine in-plane taps run out of it by row-shifted descriptors, as in conv_halo.cuh),
+  // the dz taps are folded into N and the "rows" that stream through the TMEM slot ring are the PLANES z of the tile:
+  // work item = tile x all D planes of one volume, weights packed [dy*3+dx][(2-dz)*cp + co][cin].
+  int plane;
+  int tiles_x, tiles_y;          // plane mode: 16 x 8 tiles per plane
+  int slot_px;                   // pixels (shared-memory rows) per channel chunk of a slot: 130, or 18 * 10 = 180
   int mode;                      // EPI_CONV or EPI_HEAD
   float slope;
   const float* scale;
@@ -210,6 +217,12 @@ struct RowsItem { int x0, y0, rows, z, b; };
 
 __device__ __forceinline__ RowsItem rows_decode(const ConvRowsParams& p, int t) {
   RowsItem r;
+  if (p.plane) {
+    const int tx = t % p.tiles_x; t /= p.tiles_x;
+    const int ty = t % p.tiles_y; t /= p.tiles_y;
+    r.b = t; r.z = 0; r.x0 = tx * 8; r.y0 = ty * 16; r.rows = p.D;
+    return r;
+  }
   const int sx = t % p.strips; t /= p.strips;
   const int rb = t % p.rblocks; t /= p.rblocks;
   r.z = t % p.D; t /= p.D;
@@ -264,20 +277,25 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
 
   for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += p.pipes * gridDim.x) {
     const RowsItem it = rows_decode(p, t);
-    const int px0 = it.x0 + q * 32;              // first pixel of this warp's quarter
+    // row mode: the quarter = 32 consecutive pixels of the strip; plane mode: rows 4q .. 4q+3 of the 16 x 8 tile
+    const bool plane = p.plane != 0;
+    const int px0 = plane ? it.x0 : it.x0 + q * 32;     // first pixel (column) of this warp's quarter
     const int px = px0 + lane;
 #ifdef BIU_DBG_KNOBS
     const int npix = (g_rows_dbg & 8) ? 0 : min(32, p.W - px0);
 #else
-    const int npix = min(32, p.W - px0);         // valid pixels of the quarter (<= 0: none)
+    const int npix = min(32, p.W - px0);         // row mode: valid pixels of the quarter (<= 0: none)
 #endif
-    const bool col_ok = lane < npix;
-    const long long plane_row0 = ((long long)it.b * p.D + it.z) * p.H + it.y0;
-    char* out_q = nullptr;                       // pixel px0 of the item's first output row
+    const int q_rows = plane ? min(4, p.H - (it.y0 + 4 * q)) : 0, q_cols = plane ? min(8, p.W - it.x0) : 0;
+    auto pix_ok = [&](int pxi) { return plane ? ((pxi >> 3) < q_rows && (pxi & 7) < q_cols) : pxi < npix; };
+    const bool col_ok = pix_ok(lane);
+    const long long plane_row0 = ((long long)it.b * p.D + it.z) * p.H + it.y0 + (plane ? 4 * q : 0);
+    char* out_q = nullptr;                       // first pixel of the quarter in the item's first output row / plane
     if (MODE == EPI_CONV)
       out_q = reinterpret_cast<char*>(p.out) + ((plane_row0 * p.W + px0) * p.out_ctot + p.out_coff) * ESZ;
-    const long long out_row_bytes = (long long)p.W * p.out_ctot * ESZ;
+    const long long out_row_bytes = (plane ? (long long)p.H * p.W : (long long)p.W) * p.out_ctot * ESZ;   // next output row / plane
     const int out_px_bytes = p.out_ctot * ESZ;
+    const long long out_q8_bytes = (plane ? (long long)p.W : 8LL) * out_px_bytes;      // 8 quarter-pixels further
     char* pool_px = nullptr;
     long long pool_row_bytes = 0;
     if (POOL) {
@@ -327,7 +345,7 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
           const int pxi = i * PPI + rd_px;
           const int swz = SV == 4 ? ((pxi >> 1) & 3) : ((pxi >> 2) & 1);
           const uint4 v4 = *reinterpret_cast<const uint4*>(tile + pxi * SB + ((rd_piece ^ swz) << 4));
-          if (pxi < npix) *reinterpret_cast<uint4*>(orow + (long long)pxi * out_px_bytes) = v4;
+          if (pix_ok(pxi)) *reinterpret_cast<uint4*>(orow + (pxi >> 3) * out_q8_bytes + (long long)(pxi & 7) * out_px_bytes) = v4;
         }
       }
     };
@@ -528,14 +546,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     const int pipe = warp >> 1;
     if (elect_one()) {
       const int cps = p.cps, groups = p.cin_chunks / cps;          // a slot holds cps channel chunks of one input row
-      const uint32_t slot_tx = (uint32_t)cps * (uint32_t)kRowsPx * rb;
+      const uint32_t slot_tx = (uint32_t)cps * (uint32_t)p.slot_px * rb;
+      const int kdl = p.plane ? 1 : p.kd;                          // plane mode: dz is folded, one slot per input plane
       const int a0 = pipe * asl;                                   // this pipeline's slots: [a0, a0 + asl)
       int as = 0;
       uint32_t aph = 0;
       for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += pipes * gridDim.x) {
         const RowsItem it = rows_decode(p, t);
         for (int i = 0; i < it.rows + 2; ++i)
-          for (int dz = 0; dz < p.kd; ++dz)
+          for (int dz = 0; dz < kdl; ++dz)
             for (int g = 0; g < groups; ++g) {
               mbar_wait(&a_empty[a0 + as], aph ^ 1, 0xB00 + as);
 #ifdef BIU_DBG_KNOBS
@@ -547,7 +566,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
                     "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
                     "%5, %6, %7}], [%2];" ::"r"(a_base + (a0 + as) * p.a_slot_bytes + c * p.a_chunk_bytes),
                     "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[a0 + as])), "r"((g * cps + c) * p.ck),
-                    "r"(it.x0 - 1), "r"(it.y0 - 1 + i), "r"(it.z - (p.kd >> 1) + dz), "r"(it.b)
+                    "r"(it.x0 - 1), "r"(p.plane ? it.y0 - 1 : it.y0 - 1 + i),
+                    "r"(p.plane ? i - 1 : it.z - (p.kd >> 1) + dz), "r"(it.b)
                     : "memory");
               if (++as == asl) { as = 0; aph ^= 1; }
             }
@@ -561,7 +581,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     const uint32_t idesc3 = make_idesc(fmt, (uint32_t)(3 * p.cp));      // whole folded tile
     const uint32_t idesc2 = make_idesc(fmt, (uint32_t)(2 * p.cp));      // split MMAs where the three slots wrap
     const uint32_t idesc1 = make_idesc(fmt, (uint32_t)p.cp);
-    const uint64_t a_desc0 = make_smem_desc(a_base + (uint32_t)(pipe * asl) * p.a_slot_bytes, 8u * rb, layout);
+    const uint64_t a_desc0 = make_smem_desc(a_base + (uint32_t)(pipe * asl) * p.a_slot_bytes, (p.plane ? 10u : 8u) * rb, layout);
     const uint64_t w_desc0 = make_smem_desc(smem_base, 8u * rb, layout);
     constexpr uint32_t px_step = 2u * KS;              // one pixel = row_bytes / 16
     const uint32_t aslot_step = p.a_slot_bytes >> 4, achunk_step = p.a_chunk_bytes >> 4, wtile_step = p.w_tile_bytes >> 4;
@@ -603,7 +623,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
     };
     const uint32_t t_mask = (uint32_t)tsl - 1u, t_lg = tsl == 32 ? 5u : (tsl == 16 ? 4u : 3u), t_wrap = 2u * (uint32_t)tsl - 1u;
-    const int kd = p.kd, chunks = p.cin_chunks, cps = p.cps;
+    const int kd = p.plane ? 1 : p.kd, chunks = p.cin_chunks, cps = p.cps;
+    const bool plane = p.plane != 0;
     const uint32_t cp = (uint32_t)p.cp;
     const uint32_t tmem_pipe = tmem_base + (uint32_t)(pipe * tsl) * cp;   // this pipeline's slot 0
     int as = 0;
@@ -615,8 +636,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
       er = (er + 1u) & t_wrap;
     };
     for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += pipes * gridDim.x) {
-      const int rblk = (t / p.strips) % p.rblocks;
-      const int rows = min(p.RB, p.H - rblk * p.RB);
+      const int rblk = plane ? 0 : (t / p.strips) % p.rblocks;
+      const int rows = plane ? p.D : min(p.RB, p.H - rblk * p.RB);
       wait_empty();                                    // dummy rows v = 0, 1 of this item
       wait_empty();
       for (int i = 0; i < rows + 2; ++i) {
@@ -634,7 +655,28 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
             const int ch = g0 + c;
             const uint64_t ad0 = a_desc0 + (uint64_t)(as * aslot_step + c * achunk_step);
             const uint64_t wd0 = w_desc0 + (uint64_t)((dz * 3 * chunks + ch) * wtile_step);
-            if (!dbg_nomma && elect_one()) {
+            if (plane) {
+              // nine in-plane taps out of the slot's 18 x 10 halo tile: pixel-row (dy * 10 + dx) further; N = (2-dz, co)
+              if (!dbg_nomma && elect_one()) {
+                const uint32_t n_lo = wrap == 1 ? idesc2 : idesc1, n_hi = wrap == 1 ? idesc1 : idesc2;
+                const uint32_t w_hi = (uint32_t)(3 - wrap) * wrow_step;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                  for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+                      const uint64_t ad = ad0 + ((dy * 10 + dx) * px_step + 2 * k);
+                      const uint64_t wd = wd0 + ((dy * 3 + dx) * wdx_step + 2 * k);
+                      if (wrap <= 0) {
+                        tc_mma_imm<ESZ, 1>(tcol, ad, wd, idesc3);
+                      } else {
+                        tc_mma_imm<ESZ, 1>(tcol, ad, wd, n_lo);
+                        tc_mma_imm<ESZ, 1>(tmem_pipe, ad, wd + w_hi, n_hi);
+                      }
+                    }
+              }
+            } else if (!dbg_nomma && elect_one()) {
               if (wrap <= 0) {
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx)

@@ -219,7 +219,7 @@ static int sm_count() {
 // part). Tiles t, t + 1 of a pair must share their weight block (even tile count per block), and the whole grid of pairs
 // has to be resident at once (persistent kernel with a static tile stride).
 static bool halo_try_cta2(const ConvTcArgs& a, int n_blk, HaloPlan* out, int* pairs_out) {
-  if (!halo_cta2_enabled() || n_blk < 64) return false;
+  if (!halo_cta2_enabled() || n_blk < (a.kd == 3 ? 32 : 64)) return false;   // 27-tap blocks: worth it from N = 32
   if (a.mode == EPI_UP) return false;                     // transposed convolutions are bound by their stores: measured slower in pairs
   HaloPlan pl = plan_halo(a, n_blk, true);
   if (!pl.ok) return false;
@@ -303,7 +303,7 @@ static bool rows_disabled() {
   return g_rows_enabled == 0;
 }
 
-struct RowsPlan { int ck, cps, stage_px, a_slots, t_slots, RB, smem; uint32_t a_slot_bytes, a_chunk_bytes, w_tile_bytes; bool ok; };
+struct RowsPlan { int ck, cps, stage_px, a_slots, t_slots, RB, smem, plane; uint32_t a_slot_bytes, a_chunk_bytes, w_tile_bytes; bool ok; };
 
 static bool rows_single_pipe() {
   static int v = -1;
@@ -376,6 +376,12 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
   p.strips = (a.W + 127) / 128; p.RB = pl.RB; p.rblocks = (a.H + pl.RB - 1) / pl.RB;
   p.total_items = p.strips * p.rblocks * a.D * a.B;
+  p.plane = pl.plane; p.slot_px = pl.plane ? 180 : kRowsPx;
+  if (pl.plane) {
+    p.tiles_x = (a.W + 7) / 8; p.tiles_y = (a.H + 15) / 16;
+    p.strips = 1; p.rblocks = 1;
+    p.total_items = p.tiles_x * p.tiles_y * a.B;
+  }
   p.kd = a.kd;
   p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
   p.cp = a.n_total;
@@ -395,8 +401,11 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   p.out_val = a.out_val; p.out_u8 = a.out_u8;
   CUtensorMap tmA, tmW;
   const char* in_base = reinterpret_cast<const char*>(a.in) + (size_t)a.in_coff * a.esz;
-  if (int rc = encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, kRowsPx, 1, 1, 1)) return rc;
-  if (int rc = encode_wgt_map(&tmW, a.wgt_fold, a.esz, a.cin, 3 * a.n_total, a.kd * 3, pl.ck, 3 * a.n_total)) return rc;
+  if (int rc = pl.plane ? encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, 10, 18, 1, 1)
+                        : encode_act_map(&tmA, in_base, a.esz, a.cin, a.W, a.H, a.D, a.B, a.in_ctot, pl.ck, kRowsPx, 1, 1, 1))
+    return rc;
+  if (int rc = encode_wgt_map(&tmW, pl.plane ? a.wgt_fold_z : a.wgt_fold, a.esz, a.cin, 3 * a.n_total, a.kd * 3, pl.ck, 3 * a.n_total))
+    return rc;
   const int grid = p.total_items < sm_count_cached() ? p.total_items : sm_count_cached();
   if (int rc = a.esz == 2 ? rows_dispatch_bf16(tmA, tmW, p, grid, pl.smem, stream)
                           : rows_dispatch_tf32(tmA, tmW, p, grid, pl.smem, stream))
@@ -415,6 +424,52 @@ static int choose_n_blk(const ConvTcArgs& a) {
   }
   if (a.mode == EPI_UP && n_blk > a.up_cout && n_blk % a.up_cout != 0) n_blk = a.up_cout;
   return n_blk;
+}
+
+// Plane mode of the row kernel (conv_rows.cuh): 3x3x3 blocks with Cout <= 32 on planes narrower than 128 px (the
+// level-1 layers of the 3D nets). The M tile is a 16 x 8 pixel tile, the dz taps are folded into N and the planes of
+// the tile stream through the TMEM slot ring: N = 3 * Cout per MMA instead of the halo-tile kernel's N = Cout.
+static bool rows_plane_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BIU_ROWS_NO_PLANE"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+static RowsPlan plan_rows_plane(const ConvTcArgs& a) {
+  RowsPlan pl{};
+  pl.ok = false;
+  if (rows_disabled() || halo_disabled() || !rows_plane_enabled() || a.wgt_fold_z == nullptr) return pl;
+  if (a.mode != EPI_CONV || a.pool_out != nullptr || a.out == nullptr) return pl;
+  if (a.kw != 3 || a.kh != 3 || a.kd != 3 || a.D < 2) return pl;
+  if (a.n_total != 16 && a.n_total != 32) return pl;
+  if (a.W < 8 || a.H < 16) return pl;                        // tiny planes: the halo / per-tap kernels (wide ones try the row mode first)
+  const int ck = pick_ck(a.cin, a.esz);
+  if (ck == 0) return pl;
+  const int rb = ck * a.esz, chunks = a.cin / ck, nfold = 3 * a.n_total;
+  pl.plane = 1;
+  pl.ck = ck;
+  pl.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
+  pl.a_chunk_bytes = ((uint32_t)(180 * rb) + 1023u) & ~1023u;      // 18 x 10 halo tile of one plane and channel chunk
+  const int px_bytes = a.n_total * a.esz;
+  pl.stage_px = px_bytes < 64 ? px_bytes : 64;
+  const int tail = (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * pl.stage_px + 64;
+  const int wbytes = (int)(9 * chunks * pl.w_tile_bytes);
+  const int budget = 225 * 1024 - tail - 1024 - wbytes;
+  pl.cps = chunks;
+  pl.a_slot_bytes = (uint32_t)chunks * pl.a_chunk_bytes;
+  int slots = budget / (int)pl.a_slot_bytes;
+  if (slots < 3 && chunks > 1) {                            // one channel chunk per slot
+    pl.cps = 1;
+    pl.a_slot_bytes = pl.a_chunk_bytes;
+    slots = budget / (int)pl.a_slot_bytes;
+  }
+  if (slots < 3) return pl;
+  if (slots > kRowsMaxASlots) slots = kRowsMaxASlots;
+  pl.a_slots = slots;
+  pl.t_slots = 512 / a.n_total;
+  pl.smem = wbytes + slots * (int)pl.a_slot_bytes + tail + 1024;
+  pl.RB = a.D;
+  pl.ok = true;
+  return pl;
 }
 
 bool conv_tc_can_fuse_pool_xy(const ConvTcArgs& a) {
@@ -445,6 +500,8 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
   {
     const RowsPlan rp = plan_rows(a);
     if (rp.ok) return launch_conv_rows(a, rp, stream);
+    const RowsPlan pp = plan_rows_plane(a);
+    if (pp.ok) return launch_conv_rows(a, pp, stream);
   }
   const int n_blk = choose_n_blk(a);
   {

@@ -34,6 +34,7 @@ struct ConvTcArgs {
   uint8_t* out_u8;
   int smem_budget;              // 0 = default
   const void* wgt_fold;         // optional: weights packed [kd*3 (dz,dx)][3*cout ((2-dy),co)][cin] for the row-streaming kernel
+  const void* wgt_fold_z;       // optional (3D): [9 (dy,dx)][3*cout ((2-dz),co)][cin] for the row kernel's plane mode
   void* pool_out;               // optional fused MaxPool2d(2) output (EPI_CONV, 2D, halo-tile / row kernels only)
   int pool_ctot, pool_coff;
 };

@@ -502,6 +502,32 @@ int net_finalize(Net* n) {
             if (upload(n, wf, &d)) return -1;
             L.w_fold = d;
           }
+          // 3D: third packing with the dz taps folded instead (planes narrower than 128 px: the row kernel's plane
+          // mode streams the planes of a 16 x 8 tile), order dz = 2, 1, 0 = output planes z-1, z, z+1 of input plane z
+          if (L.kd == 3 && L.cout_pad <= 32) {
+            std::vector<float> wz((size_t)9 * nfold * L.cin_phys, 0.f);
+            for (int dz = 0; dz < 3; ++dz)
+              for (int dy = 0; dy < 3; ++dy)
+                for (int dx = 0; dx < 3; ++dx) {
+                  const int t = (dz * 3 + dy) * 3 + dx;
+                  for (int co = 0; co < L.cout; ++co)
+                    for (int ci = 0; ci < L.cin_log; ++ci)
+                      wz[((size_t)(dy * 3 + dx) * nfold + (2 - dz) * L.cout_pad + co) * L.cin_phys + phys[ci]] =
+                          w->data[((size_t)co * L.cin_log + ci) * taps + t];
+                }
+            if (n->esz == 2) {
+              std::vector<uint16_t> wp(wz.size());
+              for (size_t i = 0; i < wz.size(); ++i) wp[i] = host_bf16(wz[i]);
+              uint16_t* d = nullptr;
+              if (upload(n, wp, &d)) return -1;
+              L.w_fold_z = d;
+            } else {
+              for (auto& v : wz) v = host_round_tf32(v);
+              float* d = nullptr;
+              if (upload(n, wz, &d)) return -1;
+              L.w_fold_z = d;
+            }
+          }
         }
       }
     } else {
@@ -932,7 +958,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         memset(&a, 0, sizeof(a));
         a.esz = n->esz; a.in = src; a.in_ctot = sb->ctot; a.in_coff = o.src_coff; a.cin = L.cin_phys;
         a.W = w; a.H = h; a.D = d; a.B = batch; a.kw = L.kw; a.kh = L.kh; a.kd = L.kd;
-        a.wgt = L.w_tc; a.wgt_fold = L.w_fold; a.n_total = L.cout_pad; a.mode = head ? EPI_HEAD : EPI_CONV; a.slope = L.slope;
+        a.wgt = L.w_tc; a.wgt_fold = L.w_fold; a.wgt_fold_z = L.w_fold_z; a.n_total = L.cout_pad; a.mode = head ? EPI_HEAD : EPI_CONV; a.slope = L.slope;
         a.scale = L.scale; a.shift = L.shift;
         a.out = head ? nullptr : dst_ptr(d, h, w);
         a.out_ctot = head ? 0 : db->ctot; a.out_coff = o.dst_coff;

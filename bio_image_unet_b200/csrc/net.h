@@ -38,6 +38,7 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   std::vector<Segment> segs;
   void* w_tc = nullptr;      // packed [tap][n][cin_phys] bf16 / tf32
   void* w_fold = nullptr;    // narrow 3x3 blocks: [dz*3+dx][(2-dy)*cout_pad + co][cin_phys] for the row-streaming kernel
+  void* w_fold_z = nullptr;  // narrow 3x3x3 blocks: [dy*3+dx][(2-dz)*cout_pad + co][cin_phys] for its plane mode (dz folded)
   float* w_direct = nullptr; // fp32 [tap or q][cin_phys][cout_pad]
   float* scale = nullptr;    // [n_total]
   float* shift = nullptr;

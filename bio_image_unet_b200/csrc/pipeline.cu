@@ -501,15 +501,20 @@ int launch_stitch_mean(const StitchMeanArgs& a, cudaStream_t stream) {
 // evaluated as float16(sum)/count in float16 then truncated (== numpy's float16 nanmean path).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stitch_mod3_kernel(StitchMod3Args a) {
-  const long long total = (long long)a.Z * a.H * a.W;
+  // 16 consecutive x voxels per thread. Patches are visited in increasing n (z -> y -> x order), so within a slot a
+  // later patch simply overwrites an earlier one - exactly the reference's assignment order.
+  const int W16 = (a.W + 15) / 16;
+  const long long total = (long long)a.Z * a.H * W16;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx;
-    const int x = (int)(r % a.W); r /= a.W;
+    const int x16 = (int)(r % W16) * 16; r /= W16;
     const int y = (int)(r % a.H); r /= a.H;
     const int z = (int)r;
-    int best_n[3] = {-1, -1, -1};
-    int best_v[3] = {0, 0, 0};
+    uint8_t v0[16], v1[16], v2[16];
+    unsigned int has0 = 0, has1 = 0, has2 = 0;           // bit q: slot holds a value for voxel q
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { v0[q] = 0; v1[q] = 0; v2[q] = 0; }
     for (int i = 0; i < a.nz; ++i) {
       const int tz = z - a.zs[i];
       if (tz < 0 || tz >= a.pd) continue;
@@ -517,26 +522,60 @@ __global__ void __launch_bounds__(256) stitch_mod3_kernel(StitchMod3Args a) {
         const int ty = y - a.ys[j];
         if (ty < 0 || ty >= a.ph) continue;
         for (int k = 0; k < a.nx; ++k) {
-          const int tx = x - a.xs[k];
-          if (tx < 0 || tx >= a.pw) continue;
+          const int tx0 = x16 - a.xs[k];
+          if (tx0 <= -16 || tx0 >= a.pw) continue;
           const int n = (i * a.ny + j) * a.nx + k;
-          const int s = n % 3;
-          if (n > best_n[s]) {
-            best_n[s] = n;
-            best_v[s] = __ldg(a.tiles + (((long long)n * a.pd + tz) * a.ph + ty) * a.pw + tx);
+          const uint8_t* t = a.tiles + (((long long)n * a.pd + tz) * a.ph + ty) * a.pw;
+          uint8_t e[16];
+          unsigned int m = 0;
+          if (tx0 >= 0 && tx0 + 16 <= a.pw && ((reinterpret_cast<uintptr_t>(t + tx0) & 15) == 0)) {
+            *reinterpret_cast<uint4*>(e) = __ldg(reinterpret_cast<const uint4*>(t + tx0));
+            m = 0xffffu;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int tx = tx0 + q;
+              e[q] = 0;
+              if (tx >= 0 && tx < a.pw) { e[q] = __ldg(t + tx); m |= 1u << q; }
+            }
+          }
+          const int sl = n % 3;
+          if (sl == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) if ((m >> q) & 1u) v0[q] = e[q];
+            has0 |= m;
+          } else if (sl == 1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) if ((m >> q) & 1u) v1[q] = e[q];
+            has1 |= m;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) if ((m >> q) & 1u) v2[q] = e[q];
+            has2 |= m;
           }
         }
       }
     }
-    int sum = 0, cnt = 0;
+    uint8_t o16[16];
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
-      if (best_n[s] >= 0) { sum += best_v[s]; cnt += 1; }
-    a.out[idx] = cnt ? (uint8_t)(sum / cnt) : 0;
+    for (int q = 0; q < 16; ++q) {
+      const int c0 = (has0 >> q) & 1, c1 = (has1 >> q) & 1, c2 = (has2 >> q) & 1;
+      const int cnt = c0 + c1 + c2;
+      const int sum = (c0 ? v0[q] : 0) + (c1 ? v1[q] : 0) + (c2 ? v2[q] : 0);
+      o16[q] = cnt ? (uint8_t)(sum / cnt) : (uint8_t)0;
+    }
+    uint8_t* o = a.out + ((long long)z * a.H + y) * a.W + x16;
+    if (x16 + 16 <= a.W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(o16);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (x16 + q < a.W) o[q] = o16[q];
+    }
   }
 }
 int launch_stitch_mod3(const StitchMod3Args& a, cudaStream_t stream) {
-  const long long total = (long long)a.Z * a.H * a.W;
+  const long long total = (long long)a.Z * a.H * ((a.W + 15) / 16);
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (blocks < 1) blocks = 1;
@@ -565,19 +604,21 @@ __device__ __forceinline__ float ramp_weight(int z, int y, int x, int iz, int iy
 }
 
 __global__ void __launch_bounds__(256) stitch_ramp_kernel(StitchRampArgs a) {
-  const long long vol = (long long)a.Z * a.H * a.W;
-  const long long total = (long long)a.V * a.C * vol;
+  // 4 consecutive x voxels per thread (one 16-byte load per covering patch when the run is inside the patch row and
+  // aligned); per voxel the accumulation order is the reference's patch order z -> y -> x
+  const int W4 = (a.W + 3) / 4;
+  const long long total = (long long)a.V * a.C * a.Z * a.H * W4;
   const long long pvol = (long long)a.pd * a.ph * a.pw;
   const int npv = a.nz * a.ny * a.nx;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx;
-    const int x = (int)(r % a.W); r /= a.W;
+    const int x4 = (int)(r % W4) * 4; r /= W4;
     const int y = (int)(r % a.H); r /= a.H;
     const int z = (int)(r % a.Z); r /= a.Z;
     const int c = (int)(r % a.C); r /= a.C;
     const int v = (int)r;
-    float acc = 0.f, wsum = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wsum[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < a.nz; ++i) {
       const int tz = z - a.zs[i];
       if (tz < 0 || tz >= a.pd) continue;
@@ -585,21 +626,47 @@ __global__ void __launch_bounds__(256) stitch_ramp_kernel(StitchRampArgs a) {
         const int ty = y - a.ys[j];
         if (ty < 0 || ty >= a.ph) continue;
         for (int k = 0; k < a.nx; ++k) {
-          const int tx = x - a.xs[k];
-          if (tx < 0 || tx >= a.pw) continue;
-          const float w = ramp_weight(tz, ty, tx, i, j, k, a.nz, a.ny, a.nx, a.margin);
+          const int tx0 = x4 - a.xs[k];
+          if (tx0 <= -4 || tx0 >= a.pw) continue;
           const long long n = (long long)v * npv + (i * a.ny + j) * a.nx + k;
-          const float p = __ldg(a.tiles + (n * a.C + c) * pvol + ((long long)tz * a.ph + ty) * a.pw + tx);
-          acc = __fadd_rn(acc, __fmul_rn(p, w));
-          wsum = __fadd_rn(wsum, w);
+          const float* t = a.tiles + (n * a.C + c) * pvol + ((long long)tz * a.ph + ty) * a.pw;
+          float pv[4];
+          const bool whole = tx0 >= 0 && tx0 + 4 <= a.pw;
+          if (whole && ((reinterpret_cast<uintptr_t>(t + tx0) & 15) == 0)) {
+            *reinterpret_cast<float4*>(pv) = __ldg(reinterpret_cast<const float4*>(t + tx0));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int tx = tx0 + q;
+              pv[q] = (tx >= 0 && tx < a.pw) ? __ldg(t + tx) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int tx = tx0 + q;
+            if (tx < 0 || tx >= a.pw) continue;
+            const float w = ramp_weight(tz, ty, tx, i, j, k, a.nz, a.ny, a.nx, a.margin);
+            acc[q] = __fadd_rn(acc[q], __fmul_rn(pv[q], w));
+            wsum[q] = __fadd_rn(wsum[q], w);
+          }
         }
       }
     }
-    a.out[idx] = wsum > 0.f ? __fdiv_rn(acc, wsum) : 0.f;
+    float o4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o4[q] = wsum[q] > 0.f ? __fdiv_rn(acc[q], wsum[q]) : 0.f;
+    float* o = a.out + ((((long long)v * a.C + c) * a.Z + z) * a.H + y) * a.W + x4;
+    if (x4 + 4 <= a.W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      *reinterpret_cast<float4*>(o) = *reinterpret_cast<float4*>(o4);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (x4 + q < a.W) o[q] = o4[q];
+    }
   }
 }
 int launch_stitch_ramp(const StitchRampArgs& a, cudaStream_t stream) {
-  const long long total = (long long)a.V * a.C * a.Z * a.H * a.W;
+  const long long total = (long long)a.V * a.C * a.Z * a.H * ((a.W + 3) / 4);
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (blocks < 1) blocks = 1;
@@ -774,9 +841,10 @@ __global__ void __launch_bounds__(256) gather_tiles_f32_kernel(const float* __re
                                                                const int* __restrict__ zs, const int* __restrict__ ys,
                                                                const int* __restrict__ xs, int nz, int ny, int nx, int pd,
                                                                int ph, int pw, float* __restrict__ dst) {
+  // 4 consecutive x per thread (pw is a multiple of 4: patch extents are multiples of 8 / 16)
   const long long total = (long long)F * nz * ny * nx * pd * ph * pw;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
+  for (long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; idx < total;
+       idx += (long long)gridDim.x * blockDim.x * 4) {
     long long r = idx;
     const int x = (int)(r % pw); r /= pw;
     const int y = (int)(r % ph); r /= ph;
@@ -785,15 +853,29 @@ __global__ void __launch_bounds__(256) gather_tiles_f32_kernel(const float* __re
     const int iy = (int)(r % ny); r /= ny;
     const int iz = (int)(r % nz); r /= nz;
     const int f = (int)r;
-    int yy = ys[iy] + y, xx = xs[ix] + x;
-    if (yy >= H) yy = 2 * (H - 1) - yy;          // np.pad(..., 'reflect') at the far end (multi_output_unet/predict.py:172)
-    if (xx >= W) xx = 2 * (W - 1) - xx;
-    dst[idx] = __ldg(src + (((long long)f * Z + zs[iz] + z) * H + yy) * W + xx);
+    int zz = zs[iz] + z, yy = ys[iy] + y;
+    if (zz >= Z) zz = reflect_index(zz, Z);      // np.pad(..., 'reflect') at the far end (multi_output_unet/predict.py:172),
+    if (yy >= H) yy = reflect_index(yy, H);      // periodic like numpy's when the pad exceeds the extent
+    const float* row = src + (((long long)f * Z + zz) * H + yy) * W;
+    const int sx0 = xs[ix] + x;
+    float v[4];
+    if (sx0 + 4 <= W && ((reinterpret_cast<uintptr_t>(row + sx0) & 15) == 0)) {
+      *reinterpret_cast<float4*>(v) = __ldg(reinterpret_cast<const float4*>(row + sx0));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int xx = sx0 + q;
+        if (xx >= W) xx = reflect_index(xx, W);
+        v[q] = __ldg(row + xx);
+      }
+    }
+    *reinterpret_cast<float4*>(dst + idx) = *reinterpret_cast<float4*>(v);
   }
 }
 int launch_gather_tiles_f32(const float* src, int F, int Z, int H, int W, const int* zs, const int* ys, const int* xs,
                             int nz, int ny, int nx, int pd, int ph, int pw, float* dst, cudaStream_t stream) {
-  const long long total = (long long)F * nz * ny * nx * pd * ph * pw;
+  BIU_REQUIRE(pw % 4 == 0, "gather_tiles_f32: patch width must be a multiple of 4 (got %d)", pw);
+  const long long total = (long long)F * nz * ny * nx * pd * ph * pw / 4;
   long long blocks = ceil_div_ll(total, 256);
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   if (blocks < 1) blocks = 1;

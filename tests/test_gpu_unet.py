@@ -415,7 +415,11 @@ def test_rows_kernel_matches_halo_kernel_2d(precision, n_filter, tile, batch, ro
 
 @pytest.mark.parametrize('precision', ['tf32', 'bf16'])
 @pytest.mark.parametrize('kind,n_filter,tile,batch', [('unet3d', 16, (8, 16, 128), 2), ('unet3d', 32, (16, 24, 128), 1),
-                                                      ('mo3d', 16, (8, 32, 256), 1)])
+                                                      ('mo3d', 16, (8, 32, 256), 1),
+                                                      # planes narrower than 128 px: the row kernel's PLANE mode (16 x 8 tiles,
+                                                      # dz folded into N, planes streamed); W = 40 / H = 48: ragged tiles
+                                                      ('unet3d', 16, (16, 32, 64), 2), ('unet3d', 32, (16, 48, 40), 1),
+                                                      ('mo3d', 16, (16, 32, 96), 1), ('unet3d', 16, (32, 64, 64), 3)])
 def test_rows_kernel_matches_halo_kernel_3d(precision, kind, n_filter, tile, batch, rows_kernel_toggle):
     from bio_image_unet_b200.engine import Engine
     from bio_image_unet_b200.multi_output_unet3d import MultiOutputUnet3D
