@@ -597,7 +597,10 @@ def measure(wl, steps, warmup, ctx, lib, local_rank, with_cpu, cpu, sample_clock
 
     # per-kernel timing of the dominant kernels (tcgen05 implicit-GEMM convs): CUDA events on the launching stream around
     # every op of every timed forward (set_profile above); the ones of the LAST forward of the timed loop are read here
-    kinds, ms = eng.read_profile()
+    try:
+        kinds, ms = eng.read_profile()
+    except Exception:  # noqa: BLE001  (a rank that owns no work - more ranks than z-rows of patches - ran no forward)
+        kinds, ms = [], []
     eng.set_profile(0)
     tc_ms = sum(m for k, m in zip(kinds, ms) if k in (1, 2, 3))
     tc_launches = sum(1 for k in kinds if k in (1, 2, 3))
@@ -612,7 +615,7 @@ def measure(wl, steps, warmup, ctx, lib, local_rank, with_cpu, cpu, sample_clock
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     step_tf = wl.flop_per_step / world * steps / (dev_ms / 1e3) / 1e12          # per GPU
     batch = eng.batch
-    d, h, w = eng.tile
+    d, h, w = eng.tile if eng.tile else (0, 0, 0)
     per_px = {'unet2d': FLOP_UNET32_PER_TILE_PX_TC, 'siam2d': FLOP_SIAM32_PER_TILE_PX - 2 * 2 * (9 * 32) - 2 * 32,
               'unet3d': FLOP_UNET3D16_PER_VOXEL - 2 * (27 * 8) - 2 * 8, 'mo3d': FLOP_MO3D16_PER_VOXEL - 2 * (27 * 8) - 2 * 8 * 3}[eng.kind]
     flops_last_fwd = per_px * batch * d * h * w                                  # padded tail batches compute full batches
