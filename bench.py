@@ -781,6 +781,8 @@ def main():
     with_cpu = not args.no_cpu_baseline
     cpu = CpuReference() if (rank == 0 and world == 1 and with_cpu) else None
 
+    if world > 1 and args.config in (1, 3):
+        raise SystemExit(f'bench.py --config {args.config} is a single-GPU line (cfg 2, 4 and 5 shard over ranks)')
     wl = WORKLOADS[args.config](args, device, ctx).setup()
     rec = measure(wl, args.steps, max(args.warmup, 3), ctx, lib, local_rank, with_cpu, cpu)
     rec['warmup'] = max(args.warmup, 3)

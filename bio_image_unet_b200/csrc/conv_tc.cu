@@ -329,7 +329,7 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   if (a.W < 128) return pl;                                  // one MMA tile = 128 consecutive pixels of a row
   if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
   // fused max-pool: every plane is pooled in (y, x); 3D callers reduce the z pairs afterwards (conv_tc_can_fuse_pool_xy)
-  if (a.pool_out != nullptr && ((a.H & 1) || (a.W & 1) || a.n_total > 32)) return pl;
+  if (a.pool_out != nullptr && ((a.H & 1) || (a.W & 1) || (a.kd == 3 && a.n_total > 32))) return pl;
   const int ck = pick_ck(a.cin, a.esz);
   if (ck == 0) return pl;
   const int rb = ck * a.esz, chunks = a.cin / ck, nfold = 3 * a.n_total;

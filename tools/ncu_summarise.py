@@ -3,8 +3,11 @@
 
     python tools/ncu_summarise.py launches <launch_list.csv> <out.csv> "<header note>"
     python tools/ncu_summarise.py full <raw_page.csv> <out.csv> "<header note>"
+    python tools/ncu_summarise.py metrics <metrics.csv> <out.csv> "<header note>" [first_id last_id]
 
 `launches`: per-kernel launch count, total time and share from `ncu --metrics gpu__time_duration.sum --csv`.
+`metrics`: one row per launch of a `tools/ncu_step.sh` capture (ncu --metrics ... --csv, long format): time, DRAM bytes
+and achieved GB/s against the measured HBM peak, DRAM %, tensor-pipe %, L2 hit rate; optional launch-id window.
 `full`: one row per launch (layer order of one Unet forward) with time, DRAM bytes, tensor-pipe utilisation, from
 `ncu -i <rep> --page raw --csv` of a `--set full` capture of the network kernels.
 """
@@ -41,6 +44,51 @@ def launches(src, dst, note):
         f.write('kernel,launches,total_us,share\n')
         for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f'{k},{n},{us:.1f},{us / total:.3f}\n')
+
+
+def metrics(src, dst, note, first=None, last=None, hbm_peak=6549.1):
+    rows = rows_of(src)
+    hdr = rows[0]
+    ci = {h: i for i, h in enumerate(hdr)}
+    per = OrderedDict()
+    for r in rows[1:]:
+        if len(r) < len(hdr):
+            continue
+        k = (int(r[ci['ID']]), r[ci['Kernel Name']].split('(')[0].replace('void ', '').replace('biu::', '')[:64])
+        per.setdefault(k, {})[r[ci['Metric Name']]] = (float(r[ci['Metric Value']].replace(',', '') or 0)
+                                                       if r[ci['Metric Value']] not in ('n/a', '') else float('nan'),
+                                                       r[ci['Metric Unit']])
+    to_gb = {'byte': 1e-9, 'Kbyte': 1e-6, 'Mbyte': 1e-3, 'Gbyte': 1.0}
+    to_ms = {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}
+    T = 'sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed'
+    tot_ms = tot_gb = tc_gb = tc_ms = 0.0
+    lines = []
+    for (i, name), m in per.items():
+        if (first is not None and i < first) or (last is not None and i > last):
+            continue
+        t = m['gpu__time_duration.sum'][0] * to_ms[m['gpu__time_duration.sum'][1]]
+        rd = m['dram__bytes_read.sum'][0] * to_gb[m['dram__bytes_read.sum'][1]]
+        wr = m['dram__bytes_write.sum'][0] * to_gb[m['dram__bytes_write.sum'][1]]
+        gbs = (rd + wr) / t * 1e3 if t > 0 else 0.0
+        tp = m.get(T, (float('nan'), ''))[0]
+        tot_ms += t
+        tot_gb += rd + wr
+        if 'conv_rows' in name or 'conv_halo' in name or 'conv_tc' in name:
+            tc_gb += rd + wr
+            tc_ms += t
+        qname = '"' + name + '"'
+        lines.append(f"{i},{qname},{t:.4f},{rd:.4f},{wr:.4f},{gbs:.0f},{gbs / hbm_peak:.3f},"
+                     f"{m['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'][0]:.1f},{tp:.1f},"
+                     f"{m['lts__t_sector_hit_rate.pct'][0]:.1f},{int(m['launch__registers_per_thread'][0])},"
+                     f"{int(m['launch__grid_size'][0])}")
+    with open(dst, 'w') as f:
+        f.write(f'# {note}\n')
+        f.write('# ncu --metrics (tools/ncu_step.sh), --clock-control none: cold-cache, serialised launches - compare SHARES and\n')
+        f.write(f'# per-kernel rates, not absolute step time. hbm_frac = achieved GB/s / {hbm_peak} (MEASURED_PEAKS.json hbm_gbs).\n')
+        f.write(f'# all launches: {tot_ms:.3f} ms, {tot_gb:.2f} GB DRAM; tcgen05 conv launches: {tc_ms:.3f} ms, {tc_gb:.2f} GB DRAM\n')
+        f.write('id,kernel,time_ms,dram_rd_gb,dram_wr_gb,dram_gbs,hbm_frac,dram_pct,tensor_math_pct,l2_hit_pct,regs,grid\n')
+        f.write('\n'.join(lines) + '\n')
+    return tc_gb, tc_ms, tot_gb, tot_ms
 
 
 def full(src, dst, note):
@@ -87,4 +135,9 @@ def full(src, dst, note):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](*sys.argv[2:5])
+    if sys.argv[1] == 'metrics':
+        extra = sys.argv[5:]
+        print(metrics(sys.argv[2], sys.argv[3], sys.argv[4], int(extra[0]) if extra else None,
+                      int(extra[1]) if len(extra) > 1 else None))
+    else:
+        {'launches': launches, 'full': full}[sys.argv[1]](*sys.argv[2:5])
