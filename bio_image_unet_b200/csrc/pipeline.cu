@@ -60,7 +60,8 @@ int launch_histogram(const void* img, int dtype_bytes, long long n_per_frame, in
                      cudaStream_t stream) {
   BIU_REQUIRE(dtype_bytes == 1 || dtype_bytes == 2, "histogram: only uint8/uint16 input (got %d-byte)", dtype_bytes);
   BIU_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)frames * kHistBins * sizeof(unsigned int), stream));
-  long long work = ceil_div_ll(n_per_frame, 512LL * 16);
+  // a block zeroes and flushes its 8192-bin sub-histogram: give it at least 64 K pixels so that this does not dominate
+  long long work = ceil_div_ll(n_per_frame, 512LL * 128);
   int bpf = (int)(work < 1 ? 1 : (work > 592 ? 592 : work));
   if (frames * bpf < 148) bpf = ceil_div(148, frames) < work ? ceil_div(148, frames) : (int)(work < 1 ? 1 : work);
   if (dtype_bytes == 2)

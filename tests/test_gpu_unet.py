@@ -211,11 +211,45 @@ def test_normalisation_kernels_bit_exact():
                 assert params[2, 0].item() == lo_ref and params[2, 1].item() == hi_ref
 
 
+@pytest.mark.parametrize('dtype', ['uint16', 'uint8'])
+def test_fused_normalise_gather_equals_two_pass(dtype):
+    """biu_gather_tiles_lut (normalisation fused into the split: what Session.predict_device and the 3D sessions run)
+    against biu_apply_lut + biu_gather_tiles and against the oracle's preprocess + split: bit-exact, per-frame and
+    stack-wide tables, reflect / zero padding of undersized frames, 16-pixel vector and 4-pixel scalar runs."""
+    from bio_image_unet_b200 import engine as E
+    from bio_image_unet_b200 import tiling
+    rng = np.random.default_rng(12)
+    hi = 4096 if dtype == 'uint16' else 256
+    for (f, h, w, th, tw, add, pad_mode) in [(3, 80, 112, 32, 48, 1, 0), (2, 40, 40, 64, 64, 0, 0), (2, 40, 40, 64, 64, 0, 1),
+                                              (4, 64, 96, 32, 24, 2, 0), (1, 96, 160, 32, 160, 0, 0)]:
+        stack = rng.integers(0, hi, (f, h, w)).astype(dtype)
+        dev = torch.from_numpy(stack).cuda()
+        hist = E.histogram(dev)
+        n_x, n_y, xs, ys = tiling.grid_2d(h, w, (th, tw), add)
+        for per_frame in (True, False):
+            if per_frame:
+                lut, _ = E.norm_lut(hist, hist, f, 0.5, 99.5, False)
+            else:
+                tot = E.hist_sum(hist)
+                lut, _ = E.norm_lut(tot, tot, 1, 0.5, 99.5, False)
+            two = E.gather_tiles(E.apply_lut(dev, lut).view(f, 1, h, w), [0], xs, ys, (1, th, tw), pad_mode)
+            one = E.gather_tiles_lut(dev.view(f, 1, h, w), lut, [0], xs, ys, (1, th, tw), pad_mode)
+            assert torch.equal(one, two), (dtype, f, h, w, th, tw, add, pad_mode, per_frame)
+        if pad_mode == 0 and dtype == 'uint16':          # and against the reference's numpy path ('single' mode)
+            lut, _ = E.norm_lut(hist, hist, f, 0.0, 99.8, False)
+            one = E.gather_tiles_lut(dev.view(f, 1, h, w), lut, [0], xs, ys, (1, th, tw), 0)
+            want = opipe.split_2d(opipe.preprocess_stack(stack.copy(), 'single', (0., 99.8), False), (th, tw), add)[0]
+            assert np.array_equal(one.cpu().numpy().reshape(want.shape), want)
+
+
 def test_stitch_mean_bit_exact():
     from bio_image_unet_b200 import engine as E
     from bio_image_unet_b200 import tiling
     rng = np.random.default_rng(4)
-    for (h, w, th, tw, add, c) in [(70, 90, 32, 48, 1, 1), (64, 64, 32, 32, 2, 2), (20, 100, 32, 48, 0, 1), (33, 47, 16, 16, 3, 1)]:
+    # (96, 200, ..., add 14): more than eight tiles cover a 16-pixel run (the kernel's list of covering columns overflows
+    # and it walks all columns); (64, 256, 32, 64): aligned 16-byte vector loads and stores
+    for (h, w, th, tw, add, c) in [(70, 90, 32, 48, 1, 1), (64, 64, 32, 32, 2, 2), (20, 100, 32, 48, 0, 1), (33, 47, 16, 16, 3, 1),
+                                   (96, 200, 32, 160, 14, 1), (64, 256, 32, 64, 1, 2)]:
         n_x, n_y, xs, ys = tiling.grid_2d(h, w, (th, tw), add)
         f = 2
         tiles = rng.integers(0, 256, (f * n_x * n_y, c, th, tw)).astype('uint8')
