@@ -67,6 +67,14 @@ struct ConvRowsParams {
   int plane;
   int tiles_x, tiles_y;          // plane mode: 16 x 8 tiles per plane
   int slot_px;                   // pixels (shared-memory rows) per channel chunk of a slot: 130, or 18 * 10 = 180
+  // K split over several launches (blocks whose resident weights would leave no room for the A ring, e.g. 96 input
+  // channels x 27 taps): a launch covers the channel chunks [cin_chunk0, cin_chunk0 + cin_chunks) and
+  //   acc_mode 1: stores its raw fp32 accumulators to acc_scratch [pixel][cp] instead of an output,
+  //   acc_mode 3: adds the stored partial sums to its own and stores them again,
+  //   acc_mode 2: adds them and finishes the block (BatchNorm, activation, store) as usual.   (0: single launch)
+  int cin_chunk0;
+  int acc_mode;
+  float* acc_scratch;
   int mode;                      // EPI_CONV or EPI_HEAD
   float slope;
   const float* scale;
@@ -296,6 +304,31 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     const long long out_row_bytes = (plane ? (long long)p.H * p.W : (long long)p.W) * p.out_ctot * ESZ;   // next output row / plane
     const int out_px_bytes = p.out_ctot * ESZ;
     const long long out_q8_bytes = (plane ? (long long)p.W : 8LL) * out_px_bytes;      // 8 quarter-pixels further
+    // K split: this lane's pixel in the fp32 partial-sum scratch [pixel][CP] (pixel index of output row / plane o = + o * pix_per_o)
+    const long long lane_pix0 = plane ? (plane_row0 + (lane >> 3)) * p.W + px0 + (lane & 7) : plane_row0 * p.W + px;
+    const long long pix_per_o = plane ? (long long)p.H * p.W : (long long)p.W;
+    auto partial = [&](uint32_t (&e)[HC], int o, int hh, int mode) {        // mode bit 1: add the stored sums, bit 0: store
+      if (!col_ok) return;
+      float4* sp = reinterpret_cast<float4*>(p.acc_scratch + (lane_pix0 + o * pix_per_o) * CP + hh * HC);
+      if (mode & 2) {
+#pragma unroll
+        for (int i4 = 0; i4 < HC / 4; ++i4) {
+          const float4 s4 = sp[i4];
+          e[4 * i4 + 0] = __float_as_uint(__uint_as_float(e[4 * i4 + 0]) + s4.x);
+          e[4 * i4 + 1] = __float_as_uint(__uint_as_float(e[4 * i4 + 1]) + s4.y);
+          e[4 * i4 + 2] = __float_as_uint(__uint_as_float(e[4 * i4 + 2]) + s4.z);
+          e[4 * i4 + 3] = __float_as_uint(__uint_as_float(e[4 * i4 + 3]) + s4.w);
+        }
+      }
+      if (mode & 1) {
+#pragma unroll
+        for (int i4 = 0; i4 < HC / 4; ++i4)
+          sp[i4] = make_float4(__uint_as_float(e[4 * i4 + 0]), __uint_as_float(e[4 * i4 + 1]),
+                               __uint_as_float(e[4 * i4 + 2]), __uint_as_float(e[4 * i4 + 3]));
+      }
+    };
+    const int amode = (MODE == EPI_CONV && !POOL) ? p.acc_mode : 0;
+    const bool finish = !(amode & 1);              // this launch produces the block's output
     char* pool_px = nullptr;
     long long pool_row_bytes = 0;
     if (POOL) {
@@ -421,7 +454,10 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
           if (drain) tmem_ld_cp<HC>(tmem_base + lane_addr + (uint32_t)(sl * CP + hh * HC), acc);
           tmem_ld_wait_cp<HC>(acc);
           if (MODE == EPI_HEAD) heads(acc, v - 2);
-          else activate(acc, w0, hh);
+          else {
+            if (amode) partial(acc, v - 2, hh, amode);
+            if (finish) activate(acc, w0, hh);
+          }
         }
       }
       if (real1) {
@@ -429,7 +465,10 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
         for (int hh = 0; hh < NH; ++hh) {
           if (drain) tmem_ld_cp<HC>(tmem_base + lane_addr + (uint32_t)(s1 * CP + hh * HC), acc);
           tmem_ld_wait_cp<HC>(acc);
-          if (NH > 1) activate(acc, w1, hh);       // 64-channel rows: activated half by half before the release
+          if (NH > 1) {                             // 64-channel rows: activated half by half before the release
+            if (amode) partial(acc, v - 1, hh, amode);
+            if (finish) activate(acc, w1, hh);
+          }
         }
       }
       tmem_zero_cp<CP>(tmem_base + lane_addr + (uint32_t)(sl * CP));
@@ -444,8 +483,14 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
       if (MODE == EPI_HEAD) {
         if (real1) heads(acc, v - 1);
       } else {
-        if (real0) emit(w0, v - 2);                // before row 1 is activated: keeps the live registers at two rows
-        if (real1) { if (NH == 1) activate(acc, w1, 0); emit(w1, v - 1); }
+        if (real0 && finish) emit(w0, v - 2);      // before row 1 is activated: keeps the live registers at two rows
+        if (real1) {
+          if (NH == 1) {
+            if (amode) partial(acc, v - 1, 0, amode);
+            if (finish) activate(acc, w1, 0);
+          }
+          if (finish) emit(w1, v - 1);
+        }
         if (POOL && real0 && real1) {              // MaxPool2d(2): x pairs are adjacent lanes, y pairs = this row pair
           if (ESZ == 2) {
 #pragma unroll
@@ -537,7 +582,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
               "%5}], [%2];" ::"r"(smem_base + (uint32_t)(tdx * p.cin_chunks + ch) * p.w_tile_bytes),
-              "l"(reinterpret_cast<uint64_t>(&tmW)), "r"(smem_u32(&w_full)), "r"(ch * p.ck), "r"(0), "r"(tdx)
+              "l"(reinterpret_cast<uint64_t>(&tmW)), "r"(smem_u32(&w_full)), "r"((p.cin_chunk0 + ch) * p.ck), "r"(0), "r"(tdx)
               : "memory");
     }
   }
@@ -565,7 +610,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
                 asm volatile(
                     "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
                     "%5, %6, %7}], [%2];" ::"r"(a_base + (a0 + as) * p.a_slot_bytes + c * p.a_chunk_bytes),
-                    "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[a0 + as])), "r"((g * cps + c) * p.ck),
+                    "l"(reinterpret_cast<uint64_t>(&tmA)), "r"(smem_u32(&a_full[a0 + as])),
+                    "r"((p.cin_chunk0 + g * cps + c) * p.ck),
                     "r"(it.x0 - 1), "r"(p.plane ? it.y0 - 1 : it.y0 - 1 + i),
                     "r"(p.plane ? i - 1 : it.z - (p.kd >> 1) + dz), "r"(it.b)
                     : "memory");

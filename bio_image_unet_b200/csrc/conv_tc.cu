@@ -370,7 +370,8 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   return pl;
 }
 
-static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_t stream) {
+static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_t stream, int chunk0 = 0, int nchunks = 0,
+                            int acc_mode = 0) {
   ConvRowsParams p;
   memset(&p, 0, sizeof(p));
   p.W = a.W; p.H = a.H; p.D = a.D; p.B = a.B;
@@ -383,7 +384,8 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
     p.total_items = p.tiles_x * p.tiles_y * a.B;
   }
   p.kd = a.kd;
-  p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
+  p.ck = pl.ck; p.cin_chunks = nchunks > 0 ? nchunks : a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
+  p.cin_chunk0 = chunk0; p.acc_mode = acc_mode; p.acc_scratch = reinterpret_cast<float*>(a.acc_scratch);
   p.cp = a.n_total;
   p.a_slots = pl.a_slots; p.a_slot_bytes = pl.a_slot_bytes; p.a_chunk_bytes = pl.a_chunk_bytes; p.cps = pl.cps; p.stage_px = pl.stage_px;
   // two pipelines per CTA when the A ring is deep enough to be halved and there is work for both
@@ -434,7 +436,8 @@ static bool rows_plane_enabled() {
   if (v < 0) { const char* e = getenv("BIU_ROWS_NO_PLANE"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
-static RowsPlan plan_rows_plane(const ConvTcArgs& a) {
+// chunks_limit > 0: plan for a launch that covers only that many channel chunks of the block (K split)
+static RowsPlan plan_rows_plane(const ConvTcArgs& a, int chunks_limit = 0) {
   RowsPlan pl{};
   pl.ok = false;
   if (rows_disabled() || halo_disabled() || !rows_plane_enabled() || a.wgt_fold_z == nullptr) return pl;
@@ -444,7 +447,7 @@ static RowsPlan plan_rows_plane(const ConvTcArgs& a) {
   if (a.W < 8 || a.H < 16) return pl;                        // tiny planes: the halo / per-tap kernels (wide ones try the row mode first)
   const int ck = pick_ck(a.cin, a.esz);
   if (ck == 0) return pl;
-  const int rb = ck * a.esz, chunks = a.cin / ck, nfold = 3 * a.n_total;
+  const int rb = ck * a.esz, chunks = chunks_limit > 0 ? chunks_limit : a.cin / ck, nfold = 3 * a.n_total;
   pl.plane = 1;
   pl.ck = ck;
   pl.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
@@ -505,6 +508,29 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
     if (rp.ok) return launch_conv_rows(a, rp, stream);
     const RowsPlan pp = plan_rows_plane(a);
     if (pp.ok) return launch_conv_rows(a, pp, stream);
+    // K split: the nine-tap weights of all channel chunks do not fit beside a usable A ring (96 input channels: 162 KB).
+    // Run the block as several launches over groups of chunks; the partial sums travel through an fp32 scratch.
+    if (a.acc_scratch != nullptr && a.cin > 0) {
+      const int ck = pick_ck(a.cin, a.esz);
+      const int chunks = ck ? a.cin / ck : 0;
+      const long long need = (long long)a.B * a.D * a.H * a.W * a.n_total * 4;
+      int group = 0;
+      RowsPlan gp{};
+      for (int g = chunks - 1; g >= 1; --g) {
+        gp = plan_rows_plane(a, g);
+        if (gp.ok) { group = g; break; }
+      }
+      if (group > 0 && chunks > group && need <= a.acc_scratch_bytes) {
+        for (int c0 = 0; c0 < chunks; c0 += group) {
+          const int n = chunks - c0 < group ? chunks - c0 : group;
+          const bool first = c0 == 0, last = c0 + n >= chunks;
+          const RowsPlan lp = n == group ? gp : plan_rows_plane(a, n);
+          BIU_REQUIRE(lp.ok, "conv_rows K split: no plan for %d channel chunks", n);
+          if (int rc = launch_conv_rows(a, lp, stream, c0, n, first ? 1 : (last ? 2 : 3))) return rc;
+        }
+        return 0;
+      }
+    }
   }
   const int n_blk = choose_n_blk(a);
   {

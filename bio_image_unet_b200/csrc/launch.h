@@ -35,6 +35,8 @@ struct ConvTcArgs {
   int smem_budget;              // 0 = default
   const void* wgt_fold;         // optional: weights packed [kd*3 (dz,dx)][3*cout ((2-dy),co)][cin] for the row-streaming kernel
   const void* wgt_fold_z;       // optional (3D): [9 (dy,dx)][3*cout ((2-dz),co)][cin] for the row kernel's plane mode
+  void* acc_scratch;            // optional: fp32 scratch of B*D*H*W*n_total floats for blocks whose K is split over several
+  long long acc_scratch_bytes;  // launches (conv_rows.cuh acc_mode): an activation buffer that is dead while the block runs
   void* pool_out;               // optional fused MaxPool2d(2) output (EPI_CONV, 2D, halo-tile / row kernels only)
   int pool_ctot, pool_coff;
 };

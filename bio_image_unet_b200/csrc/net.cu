@@ -241,6 +241,7 @@ int net_build(Net* n) {
       upt[l] = (interp && !tri) ? b.buf("upn" + std::to_string(3 - l), l, pad16(up_c[l])) : -1;
     }
     if (pad16(dec_mid[0]) >= pad16(c_b[0])) n->pool_scratch = d_a[0];
+    n->acc_scratch = e_a[0];
     for (int l = 0; l < 3; ++l) {
       const std::string n1 = "encode" + std::to_string(2 * l + 1), n2 = "encode" + std::to_string(2 * l + 2);
       if (l == 0) {
@@ -962,6 +963,13 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         a.scale = L.scale; a.shift = L.shift;
         a.out = head ? nullptr : dst_ptr(d, h, w);
         a.out_ctot = head ? 0 : db->ctot; a.out_coff = o.dst_coff;
+        if (n->acc_scratch >= 0 && o.level > 0 && o.src != n->acc_scratch && o.dst != n->acc_scratch) {
+          const Buf& sc = n->bufs[n->acc_scratch];     // level-0 buffer: dead once the encoder has left level 0
+          int d0, h0, w0;
+          level_dims(n, sc.level, &d0, &h0, &w0);
+          a.acc_scratch = ws + sc.offset;
+          a.acc_scratch_bytes = (long long)n->B * sc.batch_mul * d0 * h0 * w0 * sc.ctot * n->esz;
+        }
         if (head) {
           a.head_n = n->head_total; a.head_w = n->head_w; a.head_b = n->head_b;
           int row = 0;

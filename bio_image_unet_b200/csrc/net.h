@@ -81,6 +81,7 @@ struct Net {
   float* head_w = nullptr;
   float* head_b = nullptr;
   int gate_scratch = -1;            // AttentionUnet: buffer for the CUDA-core fallback of the gate GEMM
+  int acc_scratch = -1;             // 3D nets: the first block's output buffer, dead after encode2, as fp32 scratch for K-split blocks
   int pool_scratch = -1;            // UNet3D: a level-0 decoder buffer, idle during the encoder, that takes the (y, x)-pooled
                                     // planes the row kernel's epilogue writes before the z pairs are reduced
   std::vector<void*> dev_allocs;

@@ -449,19 +449,10 @@ __global__ void __launch_bounds__(256) stitch_mean_kernel(StitchMeanArgs a) {
     unsigned int sum[16], cnt[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) { sum[q] = 0; cnt[q] = 0; }
-    // covering tiles per axis first (ny + nx tests instead of ny * nx), then only their products are visited
-    int kl[8], nk = 0;
-    for (int k = 0; k < a.nx; ++k) {
-      const int tx0 = x16 - a.xs[k];
-      if (tx0 > -16 && tx0 < a.pw) { if (nk < 8) kl[nk] = k; ++nk; }
-    }
-    const bool listed = nk <= 8;                        // heavier overlap: walk all columns
-    const int kcount = listed ? nk : a.nx;
     for (int j = 0; j < a.ny; ++j) {
       const int ty = y - a.ys[j];
       if (ty < 0 || ty >= a.ph) continue;
-      for (int kk = 0; kk < kcount; ++kk) {
-        const int k = listed ? kl[kk] : kk;
+      for (int k = 0; k < a.nx; ++k) {
         const int tx0 = x16 - a.xs[k];
         if (tx0 <= -16 || tx0 >= a.pw) continue;
         const uint8_t* t = a.tiles + ((((long long)f * a.ny + j) * a.nx + k) * a.C + c) * a.ph * a.pw + (long long)ty * a.pw;
