@@ -214,3 +214,31 @@ def test_zslab_plan_sharded_stitch_equals_full_stitch(z, d, add, world):
         st = opipe.stitch_mod3(local, (ext, x, y), (d, h, w), (len(rows), n_x, n_y, zs_local, xs, ys)).reshape(ext, x, y)
         assert np.array_equal(st[shift:shift + (o1 - o0)], full[o0:o1]), (r, p)
     assert np.all(covered[:z] == 1)
+
+
+def test_even_batch_splits_a_job_into_equal_forwards():
+    """pipeline2d.even_batch: as few forwards as the workspace budget allows, all of (almost) the same size."""
+    from bio_image_unet_b200.pipeline2d import even_batch
+    assert even_batch(288, 160) == 144          # cfg 3: 2 x 144 tile pairs instead of 160 + 128 padded to 160
+    assert even_batch(6400, 266) == 256         # cfg 2, 256 frames: 25 forwards of 256
+    assert even_batch(25, 266) == 25            # cfg 1: one forward, no padding
+    assert even_batch(200, 200) == 200 and even_batch(201, 200) == 101 and even_batch(1, 7) == 1
+    for total in (1, 7, 99, 1000):
+        for budget in (1, 3, 64, 5000):
+            b = even_batch(total, budget)
+            assert 1 <= b <= max(budget, 1) and -(-total // b) == -(-total // min(budget, total))
+
+
+def test_siam_chunk_frames_layout():
+    """siam_unet.Session.chunk_frames: upload order of the frames a chunk of pairs needs. Shared encoder ('single'
+    normalisation): [previous frame of the first pair | current frames], pair j = (position j, position j + 1), frame 0
+    paired with frame 1 (siam_unet/predict.py:108-112)."""
+    from bio_image_unet_b200.siam_unet.predict import Session
+    s = Session.__new__(Session)
+    s.shared_encoder = True
+    assert s.chunk_frames(10, 0, 3) == ([1, 0, 1, 2], [0, 1, 2], [1, 2, 3])
+    assert s.chunk_frames(10, 4, 7) == ([3, 4, 5, 6], [0, 1, 2], [1, 2, 3])
+    assert s.chunk_frames(1, 0, 1) == ([0, 0], [0], [1])
+    s.shared_encoder = False
+    assert s.chunk_frames(10, 0, 3) == ([0, 1, 2], [1, 0, 1], [0, 1, 2])
+    assert s.chunk_frames(10, 4, 6) == ([3, 4, 5], [0, 1], [1, 2])
