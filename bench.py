@@ -19,7 +19,6 @@ CPU arm (`--impl reference`, `cpu_baseline`): the UNMODIFIED reference package (
 __graft_entry__.build(); kind "reference") with torch on all host cores; the oracle port (kind "port") if absent.
 """
 import argparse
-import ctypes
 import json
 import os
 import subprocess

@@ -33,8 +33,6 @@ class DistContext:
         self.rank = torch.distributed.get_rank() if self.active else 0
         self.world = torch.distributed.get_world_size() if self.active else 1
         self.backend = torch.distributed.get_backend() if self.active else None
-        self.comm_ms = 0.0                      # filled by the timed helpers when `timing` is set
-        self.comm_bytes = 0
 
     @property
     def multi(self):
