@@ -33,6 +33,13 @@ class PinnedOut:
     def __init__(self):
         self.buf = None
 
+    def view(self, shape, dtype):
+        """Pinned host tensor of the given shape (the buffer is reused by the next call)."""
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        if self.buf is None or self.buf.numel() < n:
+            self.buf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        return self.buf[:n].view(dtype).view(*shape)
+
     def fetch(self, t):
         n = t.numel() * t.element_size()
         if self.buf is None or self.buf.numel() < n:

@@ -35,10 +35,54 @@ class Session:
         self._planner = P.BatchPlanner(self.engine, self.workspace_bytes)
         self.exchanged_bytes = 0
         self._out = P.PinnedOut()
+        self._s_out = None
 
     def _plan(self, tile, n_tiles):
         self.tile_batch = self._planner.ensure(tile, n_tiles)
         return self.tile_batch
+
+    def _predict_pipelined(self, vol_dev, lut, zs, patch, shape, n_xy, groups=4):
+        """Single process, host result wanted: the z-rows of the patch grid run in `groups` groups from the far end of
+        the volume towards z = 0 (tiling.zslab_plan with the groups as virtual ranks: a group borrows only from groups
+        that ran before it). Each group's output planes are stitched as soon as its patches are predicted and travel
+        to the pinned host result on a copy stream while the next group computes."""
+        d, h, w = patch
+        z, x, y = shape
+        dev = self.device
+        plans = tiling.zslab_plan(zs, d, z, min(groups, self.N_z))
+        out_host = self._out.view((z, x, y), torch.uint8)
+        if self._s_out is None:
+            self._s_out = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        self._s_out.wait_stream(cur)
+        res_rows = {}
+        src = vol_dev.contiguous().view(1, z, x, y)
+        for g in reversed(range(len(plans))):
+            lo, hi = plans[g]['rows']
+            own_lo, own_hi = plans[g]['own']
+            if hi <= lo:
+                continue
+            n = (hi - lo) * n_xy
+            patches = P.E.gather_tiles_lut(src, lut, zs[lo:hi], self.X_start, self.Y_start, (d, h, w), 0)
+            tile_batch = self._plan((d, h, w), n)
+            res, _ = P.run_tiles(self.engine, patches.reshape(n, 1, d, h, w), tile_batch)
+            res = res.reshape(hi - lo, n_xy, d, h, w)
+            for i, zi in enumerate(range(lo, hi)):
+                res_rows[zi] = res[i]
+            if own_hi > own_lo:
+                extra = [zi for s in sorted(plans[g]['borrow']) for zi in plans[g]['borrow'][s]]
+                st_rows = list(range(lo, hi)) + extra
+                tiles = res.reshape(n, d, h, w) if not extra else torch.cat([res_rows[zi] for zi in st_rows])
+                st = P.E.stitch_mod3_u8(tiles, (own_hi - own_lo, x, y), [zs[zi] - own_lo for zi in st_rows],
+                                        self.X_start, self.Y_start, (d, h, w))
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self._s_out):
+                    self._s_out.wait_event(ev)
+                    out_host[own_lo:own_hi].copy_(st, non_blocking=True)
+                    st.record_stream(self._s_out)
+        self._s_out.synchronize()
+        return out_host.numpy()
 
     def close(self):
         if self.engine is not None:
@@ -84,6 +128,8 @@ class Session:
                                 'not fit its 32-bit counters')
         total = total.to(torch.int32)
         lut, _ = P.E.norm_lut(total, total, 1, self.clip_threshold[0], self.clip_threshold[1], self.invert)
+        if not ctx.multi and to_host and not keep and self.N_z >= 2:
+            return self._predict_pipelined(slab_dev, lut, zs, (d, h, w), (z, x, y), n_xy)
         n_local = (r_hi - r_lo) * n_xy
         if n_local > 0:
             # normalisation fused into the patch gather: the normalised (b - a, X, Y) slab is never written

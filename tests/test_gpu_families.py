@@ -376,3 +376,24 @@ def test_siam_shared_encoder_is_bit_identical(mode, precision):
     ref = opipe.siam_predict(movie.copy(), sd, mode, (64, 64), False, 'single', (0.0, 99.98), 1)
     if precision == 'fp32':
         assert np.abs(outs[True].astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
+@pytest.mark.parametrize('add_patch', [0, 1, 2])
+def test_unet3d_pipelined_groups_equal_whole_volume(add_patch):
+    """unet3d.Session.predict without intermediates runs the z-rows in groups from the far end of the volume (stitching
+    and copying each group's planes back while the next group computes); with keep=True it runs the whole volume in one
+    go. Same result bit for bit - also with overlapping patches, where a group borrows rows of the groups before it -
+    and equal to the oracle's whole-volume pipeline."""
+    from bio_image_unet_b200.unet3d import Session, UNet3D
+    torch.manual_seed(9)
+    sd = UNet3D(n_filter=4).state_dict()
+    vol = np.random.default_rng(21).integers(0, 3000, (52, 40, 48)).astype('uint16')
+    ses = Session({'state_dict': sd, 'n_filter': 4, 'in_channels': 1, 'out_channels': 1}, (8, 16, 16), add_patch=add_patch,
+                  device='cuda:0', precision='fp32')
+    piped = np.array(ses.predict(vol.copy()))
+    assert ses.N_z >= 2
+    plain = np.array(ses.predict(vol.copy(), keep=True))
+    assert piped.std() > 0 and np.array_equal(piped, plain)
+    ref = opipe.unet3d_predict(vol.copy(), sd, (8, 16, 16), False, (0., 99.8), add_patch)
+    assert np.abs(piped.astype(np.int16) - ref.astype(np.int16)).max() <= 1
+    ses.close()
