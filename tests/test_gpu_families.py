@@ -384,16 +384,19 @@ def test_unet3d_pipelined_groups_equal_whole_volume(add_patch):
     and copying each group's planes back while the next group computes); with keep=True it runs the whole volume in one
     go. Same result bit for bit - also with overlapping patches, where a group borrows rows of the groups before it -
     and equal to the oracle's whole-volume pipeline."""
-    from bio_image_unet_b200.unet3d import Session, UNet3D
-    torch.manual_seed(9)
-    sd = UNet3D(n_filter=4).state_dict()
-    vol = np.random.default_rng(21).integers(0, 3000, (52, 40, 48)).astype('uint16')
-    ses = Session({'state_dict': sd, 'n_filter': 4, 'in_channels': 1, 'out_channels': 1}, (8, 16, 16), add_patch=add_patch,
-                  device='cuda:0', precision='fp32')
+    from bio_image_unet_b200.unet3d import Session
+    g = _golden.load('unet3d_overlap')
+    sd, rd = _golden.state_dict(g), tuple(int(v) for v in g['resize_dim'])
+    base = g['vol']
+    reps = (-(-(5 * rd[0] + 3) // base.shape[0]), 1, 1)
+    vol = np.tile(base, reps)[:5 * rd[0] + 3].copy()
+    vol[::2] = vol[::2, ::-1]                                   # no two z-rows alike
+    ses = Session({'state_dict': sd, 'n_filter': int(g['n_filter']), 'in_channels': 1, 'out_channels': 1}, rd,
+                  add_patch=add_patch, clip_threshold=tuple(g['clip']), device='cuda:0', precision='fp32')
     piped = np.array(ses.predict(vol.copy()))
     assert ses.N_z >= 2
     plain = np.array(ses.predict(vol.copy(), keep=True))
     assert piped.std() > 0 and np.array_equal(piped, plain)
-    ref = opipe.unet3d_predict(vol.copy(), sd, (8, 16, 16), False, (0., 99.8), add_patch)
+    ref = opipe.unet3d_predict(vol.copy(), sd, rd, False, tuple(g['clip']), add_patch)
     assert np.abs(piped.astype(np.int16) - ref.astype(np.int16)).max() <= 1
     ses.close()
