@@ -331,10 +331,17 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     const bool finish = !(amode & 1);              // this launch produces the block's output
     char* pool_px = nullptr;
     long long pool_row_bytes = 0;
-    if (POOL) {
+    if (POOL && !plane) {
       const long long prow0 = ((long long)it.b * p.D + it.z) * (p.H >> 1) + (it.y0 >> 1);
       pool_px = reinterpret_cast<char*>(p.pool_out) + ((prow0 * (p.W >> 1) + (px >> 1)) * p.pool_ctot + p.pool_coff) * ESZ;
       pool_row_bytes = (long long)(p.W >> 1) * p.pool_ctot * ESZ;
+    } else if (POOL) {
+      // plane mode = MaxPool3d(2): the row pairs below are PLANE pairs (z), the (y, x) pairs lie inside the warp's 4 x 8
+      // pixels (lanes ^ 8 and ^ 1); pool_px = this lane's pooled pixel in pooled plane 0, one pooled plane per pair
+      const long long prow0 = ((long long)it.b * (p.D >> 1)) * (p.H >> 1) + ((it.y0 + 4 * q + (lane >> 3)) >> 1);
+      pool_px = reinterpret_cast<char*>(p.pool_out) +
+                ((prow0 * (p.W >> 1) + ((it.x0 + (lane & 7)) >> 1)) * p.pool_ctot + p.pool_coff) * ESZ;
+      pool_row_bytes = (long long)(p.H >> 1) * (p.W >> 1) * p.pool_ctot * ESZ;
     }
     const int vrows = it.rows + 4;               // virtual output rows: 2 dummies, rows real ones, 2 dummies
 
@@ -414,7 +421,9 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
       }
       if (col_ok) {
         const long long plane = (long long)p.D * p.H * p.W;
-        const long long sp = ((long long)it.z * p.H + it.y0 + o) * p.W + px;
+        // row mode: output row o of plane it.z; plane mode: this lane's pixel of the 16 x 8 tile in output plane o
+        const long long sp = p.plane ? ((long long)o * p.H + it.y0 + 4 * q + (lane >> 3)) * p.W + it.x0 + (lane & 7)
+                                     : ((long long)it.z * p.H + it.y0 + o) * p.W + px;
 #pragma unroll
         for (int h = 0; h < kMaxHead; ++h) {
           if (h >= p.head_n) break;
@@ -492,23 +501,30 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
           if (finish) emit(w1, v - 1);
         }
         if (POOL && real0 && real1) {              // MaxPool2d(2): x pairs are adjacent lanes, y pairs = this row pair
-          if (ESZ == 2) {
+          if (ESZ == 2) {                          // (plane mode, MaxPool3d(2): the pair is a z pair, y pairs are lanes ^ 8)
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
               __nv_bfloat162 mx = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w0[i]), *reinterpret_cast<__nv_bfloat162*>(&w1[i]));
-              const uint32_t mine = *reinterpret_cast<uint32_t*>(&mx);
-              const uint32_t ot = __shfl_xor_sync(0xffffffffu, mine, 1);
+              uint32_t mine = *reinterpret_cast<uint32_t*>(&mx);
+              uint32_t ot = __shfl_xor_sync(0xffffffffu, mine, 1);
               mx = __hmax2(mx, *reinterpret_cast<const __nv_bfloat162*>(&ot));
+              if (plane) {
+                mine = *reinterpret_cast<uint32_t*>(&mx);
+                ot = __shfl_xor_sync(0xffffffffu, mine, 8);
+                mx = __hmax2(mx, *reinterpret_cast<const __nv_bfloat162*>(&ot));
+              }
               w0[i] = *reinterpret_cast<uint32_t*>(&mx);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
-              const float mx = fmaxf(__uint_as_float(w0[i]), __uint_as_float(w1[i]));
-              w0[i] = __float_as_uint(fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)));
+              float mx = fmaxf(__uint_as_float(w0[i]), __uint_as_float(w1[i]));
+              mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+              if (plane) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+              w0[i] = __float_as_uint(mx);
             }
           }
-          if (col_ok && !(lane & 1)) {
+          if (col_ok && !(lane & (plane ? 9 : 1))) {
             uint4* d4 = reinterpret_cast<uint4*>(pool_px + ((v - 2) >> 1) * pool_row_bytes);
 #pragma unroll
             for (int j = 0; j < NV; ++j) d4[j] = make_uint4(w0[4 * j], w0[4 * j + 1], w0[4 * j + 2], w0[4 * j + 3]);

@@ -330,6 +330,7 @@ static RowsPlan plan_rows(const ConvTcArgs& a) {
   if (a.mode == EPI_HEAD && a.out != nullptr) return pl;
   // fused max-pool: every plane is pooled in (y, x); 3D callers reduce the z pairs afterwards (conv_tc_can_fuse_pool_xy)
   if (a.pool_out != nullptr && ((a.H & 1) || (a.W & 1) || (a.kd == 3 && a.n_total > 32))) return pl;
+  if (a.pool_out != nullptr && a.pool_3d) return pl;        // z pairs: plane mode only
   const int ck = pick_ck(a.cin, a.esz);
   if (ck == 0) return pl;
   const int rb = ck * a.esz, chunks = a.cin / ck, nfold = 3 * a.n_total;
@@ -441,7 +442,10 @@ static RowsPlan plan_rows_plane(const ConvTcArgs& a, int chunks_limit = 0) {
   RowsPlan pl{};
   pl.ok = false;
   if (rows_disabled() || halo_disabled() || !rows_plane_enabled() || a.wgt_fold_z == nullptr) return pl;
-  if (a.mode != EPI_CONV || a.pool_out != nullptr || a.out == nullptr) return pl;
+  if (a.mode != EPI_CONV && a.mode != EPI_HEAD) return pl;
+  // fused MaxPool3d(2): the planes of a tile come in pairs (z), the 16 x 8 tile holds whole (y, x) pairs
+  if (a.pool_out != nullptr && (!a.pool_3d || a.mode != EPI_CONV || (a.D & 1) || (a.H & 1) || (a.W & 1))) return pl;
+  if (a.mode == EPI_CONV ? a.out == nullptr : a.out != nullptr) return pl;      // heads: no feature output
   if (a.kw != 3 || a.kh != 3 || a.kd != 3 || a.D < 2) return pl;
   if (a.n_total != 16 && a.n_total != 32) return pl;
   if (a.W < 8 || a.H < 16) return pl;                        // tiny planes: the halo / per-tap kernels (wide ones try the row mode first)
@@ -478,6 +482,24 @@ static RowsPlan plan_rows_plane(const ConvTcArgs& a, int chunks_limit = 0) {
   return pl;
 }
 
+// 3D blocks both modes can take (planes >= 128 px wide): the plane mode loads every input plane of a tile once instead
+// of every row three times (once per dz), needs no halo rows, and pools in (z, y, x). Measured on UNet3D(16) at
+// 64 x 128 x 128, ms per 256 patches, row -> plane mode: encode2 + pool 9.4 -> 7.8, decode5 (48 -> 16, 8-slot ring)
+// 14.5 -> 12.0, decode6 + head 7.6 -> 5.5; MO-3D full-resolution blocks 1.12 -> 0.76 and 1.98 -> 1.70 per forward.
+// Preferred when its ring holds at least BIU_ROWS_PLANE_MIN_SLOTS (default 8) tiles; BIU_ROWS_PLANE_FIRST=0 / 1 forces
+// the choice (A/B runs).
+static bool rows_plane_preferred(const RowsPlan& pp) {
+  static int plane_first = -1;
+  if (plane_first < 0) { const char* e = getenv("BIU_ROWS_PLANE_FIRST"); plane_first = e ? (e[0] == '1' ? 1 : 0) : 2; }
+  static int min_slots = -1;
+  if (min_slots < 0) { const char* e = getenv("BIU_ROWS_PLANE_MIN_SLOTS"); min_slots = e ? atoi(e) : 8; }
+  return pp.ok && (plane_first == 1 || (plane_first == 2 && pp.a_slots >= min_slots));
+}
+
+bool conv_tc_can_fuse_pool3d(const ConvTcArgs& a) {
+  if (!conv_tc_supported(a) || a.mode != EPI_CONV || a.kd != 3 || !a.pool_3d) return false;
+  return rows_plane_preferred(plan_rows_plane(a));
+}
 bool conv_tc_can_fuse_pool_xy(const ConvTcArgs& a) {
   // 3D blocks: only the row kernel pools (plane by plane, in y and x)
   if (!conv_tc_supported(a) || a.mode != EPI_CONV || a.kd != 3 || (a.H & 1) || (a.W & 1) || (a.D & 1)) return false;
@@ -504,13 +526,24 @@ int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream) {
   p.cin_chunks = a.cin / p.ck;
   p.row_bytes = p.ck * a.esz;
   {
+    const RowsPlan pp = plan_rows_plane(a);
+    {
+      static int dbg = -1;
+      if (dbg < 0) { const char* e = getenv("BIU_PLAN_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
+      if (dbg && a.kd == 3) {
+        const RowsPlan rp0 = plan_rows(a);
+        fprintf(stderr, "[plan] cin=%d n=%d %dx%dx%d B=%d mode=%d pool=%d/%d | rows ok=%d slots=%d cps=%d RB=%d | plane ok=%d slots=%d cps=%d ck=%d\n",
+                a.cin, a.n_total, a.D, a.H, a.W, a.B, a.mode, a.pool_out != nullptr, a.pool_3d, rp0.ok, rp0.a_slots, rp0.cps,
+                rp0.RB, pp.ok, pp.a_slots, pp.cps, pp.ck);
+      }
+    }
+    if (pp.ok && (a.pool_3d || rows_plane_preferred(pp))) return launch_conv_rows(a, pp, stream);
     const RowsPlan rp = plan_rows(a);
     if (rp.ok) return launch_conv_rows(a, rp, stream);
-    const RowsPlan pp = plan_rows_plane(a);
     if (pp.ok) return launch_conv_rows(a, pp, stream);
     // K split: the nine-tap weights of all channel chunks do not fit beside a usable A ring (96 input channels: 162 KB).
     // Run the block as several launches over groups of chunks; the partial sums travel through an fp32 scratch.
-    if (a.acc_scratch != nullptr && a.cin > 0) {
+    if (a.acc_scratch != nullptr && a.cin > 0 && a.mode == EPI_CONV) {
       const int ck = pick_ck(a.cin, a.esz);
       const int chunks = ck ? a.cin / ck : 0;
       const long long need = (long long)a.B * a.D * a.H * a.W * a.n_total * 4;

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) first_conv1_3d_kernel(FirstConvArgs a)
   const int zchunks = (a.D + kFc3ZC - 1) / kFc3ZC;
   const int ncols = a.B * zchunks * tiles_y * tiles_x;
   const long long plane = (long long)a.D * a.H * a.W;
-  const int real_c = (a.cout + 7) & ~7;              // channels [real_c, cout_pad) are padding
+  const int real_c = ((a.cout_real > 0 ? min(a.cout_real, a.cout) : a.cout) + 7) & ~7;   // channels [real_c, cout_pad) are padding
   const TIN* in = reinterpret_cast<const TIN*>(a.in);
   TOUT* out = reinterpret_cast<TOUT*>(a.out);
   const unsigned long long slope2 = pack_f32x2(a.slope, a.slope);

@@ -39,10 +39,13 @@ struct ConvTcArgs {
   long long acc_scratch_bytes;  // launches (conv_rows.cuh acc_mode): an activation buffer that is dead while the block runs
   void* pool_out;               // optional fused MaxPool2d(2) output (EPI_CONV, 2D, halo-tile / row kernels only)
   int pool_ctot, pool_coff;
+  int pool_3d;                  // 3D blocks: pool_out is the MaxPool3d(2) result [B][D/2][H/2][W/2] (plane mode of the row
+                                // kernel, conv_tc_can_fuse_pool3d); 0: every plane pooled in (y, x) only
 };
 bool conv_tc_supported(const ConvTcArgs& a);
 bool conv_tc_can_fuse_pool(const ConvTcArgs& a);
 bool conv_tc_can_fuse_pool_xy(const ConvTcArgs& a);   // 3D: the row kernel pools every plane in (y, x) only
+bool conv_tc_can_fuse_pool3d(const ConvTcArgs& a);    // 3D: the row kernel's plane mode pools in (z, y, x)
 void conv_halo_set_cta2(int on);      // test hook: CTA pairs (tcgen05.mma.cta_group::2) in the halo-tile kernel (default on)
 void conv_rows_set_enabled(int on);   // test hook: route narrow 3x3 blocks through the row-streaming kernel (default on)
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
@@ -89,7 +92,9 @@ struct FirstConvArgs {          // planar u8 / f32 input with few channels -> NH
   int W, H, D, B;
   int kd;                       // 1 (2D) or 3
   const float* wgt;             // fp32 [tap][cin][cout]
-  int cout;                     // real output channels
+  int cout;                     // channels of the weight / scale / shift arrays (their stride)
+  int cout_real;                // 0, or the block's real width when `cout` is a padded count: 8-channel groups at or above it
+                                // are pure padding and are written as zeros without arithmetic (3D kernel)
   float slope;
   const float* scale;
   const float* shift;

@@ -945,7 +945,7 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         }
         BIU_REQUIRE(a.in != nullptr, "network input pointer is null");
         a.cin = n->in_ch; a.W = w; a.H = h; a.D = d; a.B = shared > 0 ? n->B + shared : n->B; a.kd = L.kd;
-        a.wgt = L.w_direct; a.cout = L.cout_pad; a.slope = L.slope; a.scale = L.scale; a.shift = L.shift;
+        a.wgt = L.w_direct; a.cout = L.cout_pad; a.cout_real = L.cout; a.slope = L.slope; a.scale = L.scale; a.shift = L.shift;
         a.esz = n->esz; a.out = shared > 0 ? ws + db->offset : dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
         a.cout_pad = L.cout_pad; a.round_tf32 = round_tf32;
         if (int rc = launch_first_conv(a, stream)) return rc;
@@ -994,7 +994,20 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
           // plane in (y, x) into an idle decoder buffer, a second pass over a quarter of the data reduces the z pairs
           bool zpairs = false;
           PoolArgs zp;
-          if (!head && n->dims == 3 && !n->no_fuse && o.level == 0 && n->pool_scratch >= 0 &&
+          // first choice, any level: the row kernel's plane mode streams the planes of a tile in pairs and pools in
+          // (z, y, x) straight into the pool's destination
+          if (!head && n->dims == 3 && !n->no_fuse && op_index + 1 < (int)n->ops.size()) {
+            const Op& nx = n->ops[op_index + 1];
+            if (nx.kind == OP_POOL && nx.pool_mode == 0 && nx.src == o.dst && nx.src_coff == o.dst_coff &&
+                nx.c == L.cout_pad && nx.batch_mul == 1 && o.batch_mul == 1 && nx.level == o.level &&
+                nx.src_img0 == 0 && nx.dst_img0 == 0 && o.dst_img0 == 0) {
+              const Buf& pb = n->bufs[nx.dst];
+              a.pool_out = ws + pb.offset; a.pool_ctot = pb.ctot; a.pool_coff = nx.dst_coff; a.pool_3d = 1;
+              if (conv_tc_can_fuse_pool3d(a)) skip_pool = true;
+              else { a.pool_out = nullptr; a.pool_3d = 0; }
+            }
+          }
+          if (!skip_pool && !head && n->dims == 3 && !n->no_fuse && o.level == 0 && n->pool_scratch >= 0 &&
               op_index + 1 < (int)n->ops.size()) {
             const Op& nx = n->ops[op_index + 1];
             if (nx.kind == OP_POOL && nx.pool_mode == 0 && nx.src == o.dst && nx.src_coff == o.dst_coff &&
