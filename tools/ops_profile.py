@@ -1,3 +1,7 @@
+"""Per-op device times of one forward of a BASELINE config (bench.py workload objects, CUDA events around every op of the
+network handle): `python tools/ops_profile.py 4`. Op kinds: 0 first block, 1 conv block, 2 conv block + heads, 3 transposed
+conv, 4 pool, 5 nearest upsample (+16: CUDA-core fallback, +32: fused into the previous op). Set BIU_PLAN_DEBUG=1 to print
+the row / plane plans of the 3D blocks."""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 import bench, argparse
