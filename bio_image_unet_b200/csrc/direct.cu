@@ -199,30 +199,42 @@ __device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, un
 // four input planes (10 rows x 130 voxels with the halo, already float32(u8)/255 - exact division,
 // unet3d/predict.py:161) rotate through shared memory, the plane needed two steps ahead is fetched from global
 // memory while the current plane is computed (one __syncthreads per plane, no global latency and no bounds checks in
-// the arithmetic). A thread produces a run of XR = 4 consecutive voxels along x: the 3x3x3 windows of the run share
-// their inputs, a weight vector read from shared memory serves all four voxels, the arithmetic runs on packed float
-// pairs (FFMA2), channel groups that are pure padding (UNet3D's first block has n_filter / 2 = 8 real channels in a
-// 16-channel buffer) are written as zeros without any arithmetic, and a thread's stores cover XR * C_out contiguous
-// elements.
+// the arithmetic). A thread produces a run of 4 consecutive voxels along x as TWO VOXEL PAIRS: the arithmetic runs on
+// packed float pairs (FFMA2: {out[x], out[x+1]} += {in[x+dx], in[x+1+dx]} * {w, w}), so the input pairs of all three dx
+// taps come straight out of shared memory as aligned 64-bit register pairs - the planes are kept twice, the second
+// copy shifted by one voxel, which makes the odd-aligned pairs of the dx = 0 / 2 taps 16- / 8-byte aligned loads - and
+// the weights are kept pre-duplicated ({w, w}), one 16-byte broadcast load per two output channels: no register
+// shuffling between the loads and the FMAs (the previous form spent two moves per FFMA2 operand on {v, v} pairs).
+// The FMA order of every output is unchanged ((dz, dy, dx) ascending): results are bit-identical to the scalar form.
+// Channel groups that are pure padding (UNet3D's first block has n_filter / 2 = 8 real channels in a 16-channel
+// buffer) are written as zeros without any arithmetic; a thread's stores cover 4 * C_out contiguous elements.
 constexpr int kFc3Rows = 8, kFc3Cols = 128, kFc3Pitch = 136, kFc3Planes = 4, kFc3ZC = 16;
-template <typename TIN, typename TOUT, int XR>
+constexpr int kFc3PlaneF = (kFc3Rows + 2) * kFc3Pitch;                 // floats of one staged plane
+static size_t first_conv1_3d_smem(int cout_pad) {
+  return ((size_t)27 * cout_pad * 2 + 4 * cout_pad + 256 + 2 * kFc3Planes * kFc3PlaneF) * sizeof(float);
+}
+template <typename TIN, typename TOUT>
 __global__ void __launch_bounds__(256, 2) first_conv1_3d_kernel(FirstConvArgs a) {
-  extern __shared__ float sw[];  // [27][cout_pad], scale[cout_pad], shift[cout_pad]
-  __shared__ float lut[256];
-  __shared__ __align__(16) float tile[kFc3Planes * (kFc3Rows + 2) * kFc3Pitch];
-  float* s_scale = sw + 27 * a.cout_pad;
-  float* s_shift = s_scale + a.cout_pad;
+  extern __shared__ __align__(16) float fc3_smem[];
+  float* sw2 = fc3_smem;                                   // [27][cout_pad] x {w, w}
+  float* s_scale2 = sw2 + 27 * a.cout_pad * 2;             // [cout_pad] x {s, s}
+  float* s_shift2 = s_scale2 + 2 * a.cout_pad;
+  float* lut = s_shift2 + 2 * a.cout_pad;                  // u8 -> float32(u8)/255
+  float* tile_a = lut + 256;                               // voxel xt - 4 + j of a row at index j
+  float* tile_b = tile_a + kFc3Planes * kFc3PlaneF;        // the same rows one voxel further right: b[j] = a[j - 1]
   for (int i = threadIdx.x; i < 27 * a.cout_pad; i += blockDim.x) {
     const int co = i % a.cout_pad, k = i / a.cout_pad;
-    sw[i] = co < a.cout ? a.wgt[k * a.cout + co] : 0.f;
+    const float w = co < a.cout ? a.wgt[k * a.cout + co] : 0.f;
+    sw2[2 * i] = w; sw2[2 * i + 1] = w;
   }
   for (int i = threadIdx.x; i < a.cout_pad; i += blockDim.x) {
-    s_scale[i] = i < a.cout ? a.scale[i] : 0.f;
-    s_shift[i] = i < a.cout ? a.shift[i] : 0.f;
+    const float sc = i < a.cout ? a.scale[i] : 0.f, sh = i < a.cout ? a.shift[i] : 0.f;
+    s_scale2[2 * i] = sc; s_scale2[2 * i + 1] = sc;
+    s_shift2[2 * i] = sh; s_shift2[2 * i + 1] = sh;
   }
   if (sizeof(TIN) == 1) lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
   __syncthreads();
-  constexpr int PLANE = (kFc3Rows + 2) * kFc3Pitch, NVAL = (kFc3Rows + 2) * (kFc3Cols + 2), NLD = (NVAL + 255) / 256;
+  constexpr int PLANE = kFc3PlaneF, NVAL = (kFc3Rows + 2) * (kFc3Cols + 2), NLD = (NVAL + 255) / 256;
   const int tiles_x = (a.W + kFc3Cols - 1) / kFc3Cols, tiles_y = (a.H + kFc3Rows - 1) / kFc3Rows;
   const int zchunks = (a.D + kFc3ZC - 1) / kFc3ZC;
   const int ncols = a.B * zchunks * tiles_y * tiles_x;
@@ -265,108 +277,107 @@ __global__ void __launch_bounds__(256, 2) first_conv1_3d_kernel(FirstConvArgs a)
       }
     };
     auto stash = [&](int zz) {
-      float* pl = tile + ((zz + kFc3Planes) % kFc3Planes) * PLANE;
+      const int po = ((zz + kFc3Planes) % kFc3Planes) * PLANE;
 #pragma unroll
       for (int k = 0; k < NLD; ++k) {
         float t = 0.f;
         if (stg_ok[k]) t = sizeof(TIN) == 1 ? lut[(int)stg[k]] : (float)stg[k];
-        if (s_off[k] >= 0) pl[s_off[k]] = t;
+        if (s_off[k] >= 0) { tile_a[po + s_off[k]] = t; tile_b[po + s_off[k] + 1] = t; }
       }
     };
     __syncthreads();                                               // the previous column's planes are consumed
     for (int zz = z0 - 1; zz <= z0 + 1; ++zz) { fetch(zz); stash(zz); }
     __syncthreads();
-    const int y = yt + wid, x0 = xt + XR * lane;
+    const int y = yt + wid, x0 = xt + 4 * lane;
     const bool active = y < a.H && x0 < a.W;
+    const int t_off = wid * kFc3Pitch + 4 * lane;                  // a[t_off + 3 + i] = voxel x0 - 1 + i of row y - 1
     for (int z = z0; z < z1; ++z) {
       const bool more = z + 1 < z1;
       if (more) fetch(z + 2);                                      // in flight while this plane is computed
       if (active) {
-        float v[3][3][XR + 2];
-#pragma unroll
-        for (int dz = 0; dz < 3; ++dz) {
-          const float* pl = tile + ((z + dz - 1 + kFc3Planes) % kFc3Planes) * PLANE + (wid * kFc3Pitch + XR * lane);
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const float* rowp = pl + dy * kFc3Pitch;
-            const float4 mid = *reinterpret_cast<const float4*>(rowp + 4);
-            v[dz][dy][0] = rowp[3];
-            v[dz][dy][1] = mid.x; v[dz][dy][2] = mid.y; v[dz][dy][3] = mid.z; v[dz][dy][4] = mid.w;
-            v[dz][dy][5] = rowp[8];
-          }
-        }
         TOUT* o = out + ((r * plane + ((long long)z * a.H + y) * a.W + x0) * a.out_ctot + a.out_coff);
-    for (int g = 0; g < a.cout_pad; g += 8) {
-      if (g >= real_c) {
+        for (int g = 0; g < a.cout_pad; g += 8) {
+          if (g >= real_c) {
 #pragma unroll
-        for (int xi = 0; xi < XR; ++xi) {
-          if (x0 + xi >= a.W) break;
-          TOUT* ov = o + (long long)xi * a.out_ctot + g;
-          if (sizeof(TOUT) == 2) *reinterpret_cast<uint4*>(ov) = make_uint4(0, 0, 0, 0);
-          else { *reinterpret_cast<float4*>(ov) = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(reinterpret_cast<float*>(ov) + 4) = make_float4(0.f, 0.f, 0.f, 0.f); }
-        }
-        continue;
-      }
-      unsigned long long acc2[XR][4];
+            for (int xi = 0; xi < 4; ++xi) {
+              if (x0 + xi >= a.W) break;
+              TOUT* ov = o + (long long)xi * a.out_ctot + g;
+              if (sizeof(TOUT) == 2) *reinterpret_cast<uint4*>(ov) = make_uint4(0, 0, 0, 0);
+              else { *reinterpret_cast<float4*>(ov) = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(reinterpret_cast<float*>(ov) + 4) = make_float4(0.f, 0.f, 0.f, 0.f); }
+            }
+            continue;
+          }
+          unsigned long long acc2[2][8];                           // [voxel pair (x0, x0+1) / (x0+2, x0+3)][channel]
 #pragma unroll
-      for (int xi = 0; xi < XR; ++xi)
+          for (int xp = 0; xp < 2; ++xp)
 #pragma unroll
-        for (int m = 0; m < 4; ++m) acc2[xi][m] = 0ull;
+            for (int c = 0; c < 8; ++c) acc2[xp][c] = 0ull;
 #pragma unroll
-      for (int dz = 0; dz < 3; ++dz)
+          for (int dz = 0; dz < 3; ++dz) {
+            const int po = ((z + dz - 1 + kFc3Planes) % kFc3Planes) * PLANE + t_off;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 3; ++dy) {
+              const float* ra = tile_a + po + dy * kFc3Pitch;
+              const float* rbp = tile_b + po + dy * kFc3Pitch;
+              // voxels x0-1 .. x0+4 = a[3..8]: pairs (a3,a4) (a5,a6) = b[4..7]; (a4,a5) (a6,a7) = a[4..7]; (a7,a8) = b[8..9]
+              const ulonglong2 p0 = *reinterpret_cast<const ulonglong2*>(rbp + 4);
+              const ulonglong2 p1 = *reinterpret_cast<const ulonglong2*>(ra + 4);
+              const unsigned long long p2 = *reinterpret_cast<const unsigned long long*>(rbp + 8);
+              const unsigned long long pr[3][2] = {{p0.x, p0.y}, {p1.x, p1.y}, {p0.y, p2}};
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const int t = (dz * 3 + dy) * 3 + dx;
-            const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(sw + t * a.cout_pad + g);
-            const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(sw + t * a.cout_pad + g + 4);
+              for (int dx = 0; dx < 3; ++dx) {
+                const float* wt = sw2 + (((dz * 3 + dy) * 3 + dx) * a.cout_pad + g) * 2;
 #pragma unroll
-            for (int xi = 0; xi < XR; ++xi) {
-              const unsigned long long b = pack_f32x2(v[dz][dy][xi + dx], v[dz][dy][xi + dx]);
-              acc2[xi][0] = fma_f32x2(b, w01.x, acc2[xi][0]);
-              acc2[xi][1] = fma_f32x2(b, w01.y, acc2[xi][1]);
-              acc2[xi][2] = fma_f32x2(b, w23.x, acc2[xi][2]);
-              acc2[xi][3] = fma_f32x2(b, w23.y, acc2[xi][3]);
+                for (int c2 = 0; c2 < 4; ++c2) {
+                  const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wt + 4 * c2);    // {w, w} of channels 2 c2, 2 c2 + 1
+                  acc2[0][2 * c2] = fma_f32x2(pr[dx][0], w.x, acc2[0][2 * c2]);
+                  acc2[1][2 * c2] = fma_f32x2(pr[dx][1], w.x, acc2[1][2 * c2]);
+                  acc2[0][2 * c2 + 1] = fma_f32x2(pr[dx][0], w.y, acc2[0][2 * c2 + 1]);
+                  acc2[1][2 * c2 + 1] = fma_f32x2(pr[dx][1], w.y, acc2[1][2 * c2 + 1]);
+                }
+              }
             }
           }
-      const ulonglong2 sc01 = *reinterpret_cast<const ulonglong2*>(s_scale + g), sc23 = *reinterpret_cast<const ulonglong2*>(s_scale + g + 4);
-      const ulonglong2 sh01 = *reinterpret_cast<const ulonglong2*>(s_shift + g), sh23 = *reinterpret_cast<const ulonglong2*>(s_shift + g + 4);
-      const unsigned long long sc2[4] = {sc01.x, sc01.y, sc23.x, sc23.y}, sh2[4] = {sh01.x, sh01.y, sh23.x, sh23.y};
+          // BatchNorm + LeakyReLU (t > 0 ? t : t * slope == max(t, t * slope) for 0 <= slope <= 1), per voxel 8 channels
+          float res[4][8];
 #pragma unroll
-      for (int xi = 0; xi < XR; ++xi) {
-        if (x0 + xi >= a.W) break;
-        float acc[8];
+          for (int c2 = 0; c2 < 4; ++c2) {
+            const ulonglong2 sc = *reinterpret_cast<const ulonglong2*>(s_scale2 + (g + 2 * c2) * 2);
+            const ulonglong2 sh = *reinterpret_cast<const ulonglong2*>(s_shift2 + (g + 2 * c2) * 2);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const unsigned long long t2 = fma_f32x2(acc2[xi][m], sc2[m], sh2[m]);
-          const unsigned long long u2 = mul_f32x2(t2, slope2);
-          float ta, tb, ua, ub;
-          unpack_f32x2(t2, ta, tb);
-          unpack_f32x2(u2, ua, ub);
-          acc[2 * m] = ta > 0.f ? ta : ua;
-          acc[2 * m + 1] = tb > 0.f ? tb : ub;
-        }
-        TOUT* ov = o + (long long)xi * a.out_ctot + g;
-        if (sizeof(TOUT) == 2) {
-          uint32_t w[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&b2);
+            for (int xp = 0; xp < 2; ++xp) {
+              const unsigned long long t0 = fma_f32x2(acc2[xp][2 * c2], sc.x, sh.x);
+              const unsigned long long t1 = fma_f32x2(acc2[xp][2 * c2 + 1], sc.y, sh.y);
+              const unsigned long long u0 = mul_f32x2(t0, slope2), u1 = mul_f32x2(t1, slope2);
+              float ta, tb, ua, ub;
+              unpack_f32x2(t0, ta, tb); unpack_f32x2(u0, ua, ub);
+              res[2 * xp][2 * c2] = fmaxf(ta, ua); res[2 * xp + 1][2 * c2] = fmaxf(tb, ub);
+              unpack_f32x2(t1, ta, tb); unpack_f32x2(u1, ua, ub);
+              res[2 * xp][2 * c2 + 1] = fmaxf(ta, ua); res[2 * xp + 1][2 * c2 + 1] = fmaxf(tb, ub);
+            }
           }
-          *reinterpret_cast<uint4*>(ov) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else {
-          float* of = reinterpret_cast<float*>(ov);
-          if (a.round_tf32) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = to_tf32(acc[j]);
+          for (int xi = 0; xi < 4; ++xi) {
+            if (x0 + xi >= a.W) break;
+            TOUT* ov = o + (long long)xi * a.out_ctot + g;
+            if (sizeof(TOUT) == 2) {
+              uint32_t w[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(res[xi][2 * j], res[xi][2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              *reinterpret_cast<uint4*>(ov) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              float* of = reinterpret_cast<float*>(ov);
+              float v8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v8[j] = a.round_tf32 ? to_tf32(res[xi][j]) : res[xi][j];
+              *reinterpret_cast<float4*>(of) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+              *reinterpret_cast<float4*>(of + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+            }
           }
-          *reinterpret_cast<float4*>(of) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-          *reinterpret_cast<float4*>(of + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
-      }
-    }
       }                                                            // active
       if (more) stash(z + 2);
       __syncthreads();
@@ -545,7 +556,15 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
 #define BIU_FC1(TIN, TOUT)                                                                               \
   do {                                                                                                   \
     if (a.kd == 1) first_conv1_kernel<TIN, TOUT, 9><<<(int)fb, 256, smem, stream>>>(a);                  \
-    else first_conv1_3d_kernel<TIN, TOUT, 4><<<(int)rb3, 256, smem, stream>>>(a);                        \
+    else {                                                                                               \
+      static bool attr_set = false;                                                                     \
+      if (!attr_set) {                                                                                   \
+        BIU_CHECK_CUDA(cudaFuncSetAttribute(first_conv1_3d_kernel<TIN, TOUT>,                            \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));    \
+        attr_set = true;                                                                                 \
+      }                                                                                                  \
+      first_conv1_3d_kernel<TIN, TOUT><<<(int)rb3, 256, first_conv1_3d_smem(a.cout_pad), stream>>>(a);    \
+    }                                                                                                    \
   } while (0)
     if (a.in_kind == 0 && a.esz == 2) BIU_FC1(uint8_t, __nv_bfloat16);
     else if (a.in_kind == 0 && a.esz == 4) BIU_FC1(uint8_t, float);
