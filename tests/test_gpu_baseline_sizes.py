@@ -237,3 +237,20 @@ def test_cfg5_mo3d_patch_matches_oracle(precision):
     _parity.check(val[pick], ref, fwd, precision, sd, x, what='mo3d 64x256x256')
     assert eng.fallback_ops == 0
     eng.close()
+
+
+@pytest.mark.gpu
+def test_cfg4_unet3d_patch_row_mode_of_the_full_resolution_blocks():
+    """Where both fit, the 3D blocks run in the row kernel's plane mode (fused MaxPool3d). BIU_ROWS_PLANE_FIRST=0 puts
+    the full-resolution blocks back on the row mode (planes pooled in (y, x) by the epilogue + the z-pair pass): the
+    same parity test has to pass there. The knob is read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BIU_ROWS_PLANE_FIRST='0')
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_baseline_sizes.py'), '-q', '-m', 'gpu',
+                        '-k', 'test_cfg4_unet3d_patch_matches_oracle', '-p', 'no:cacheprovider'],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '2 passed' in r.stdout, r.stdout[-500:]
