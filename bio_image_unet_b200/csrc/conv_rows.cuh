@@ -75,6 +75,13 @@ struct ConvRowsParams {
   int cin_chunk0;
   int acc_mode;
   float* acc_scratch;
+  // FIRST mode (first block of the 2D nets, one uint8 input channel): the three dx taps are the K dimension. An A-ring row
+  // is one pixel's {in[x-1], in[x], in[x+1], 0...} (32 bytes: bf16 K = 16 / tf32 K = 8) and is WRITTEN BY THE PRODUCER
+  // WARP itself from the planar uint8 tile (integers 0..255 are exact in bf16 / tf32; the 1/255 of unet/predict.py:192 is
+  // folded into the fp32 scale), so one MMA of N = 3 * Cout per input row does the whole block: w_taps = 1.
+  int first;
+  const uint8_t* first_in;       // [B][H][W] uint8
+  int w_taps;                    // weight tiles per channel chunk: kd * 3, or 1 in first mode
   int mode;                      // EPI_CONV or EPI_HEAD
   float slope;
   const float* scale;
@@ -551,7 +558,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
   const int lane = threadIdx.x & 31;
   const uint32_t smem_off = ((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw);
   const uint32_t smem_base = smem_u32(smem_raw) + smem_off;
-  const int w_tiles = p.kd * 3 * p.cin_chunks;
+  const int w_tiles = p.w_taps * p.cin_chunks;
   const uint32_t a_base = smem_base + (uint32_t)w_tiles * p.w_tile_bytes;
   uint8_t* tail = smem_raw + smem_off + (size_t)w_tiles * p.w_tile_bytes + (size_t)p.a_slots * p.a_slot_bytes;
   float* s_scale = reinterpret_cast<float*>(tail);
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
     // ============================ folded weights: loaded once, resident ============================
     if (elect_one()) {
       mbar_arrive_expect_tx(&w_full, (uint32_t)w_tiles * (uint32_t)nfold * rb);
-      for (int tdx = 0; tdx < p.kd * 3; ++tdx)                     // tdx = dz * 3 + dx
+      for (int tdx = 0; tdx < p.w_taps; ++tdx)                     // tdx = dz * 3 + dx
         for (int ch = 0; ch < p.cin_chunks; ++ch)
           asm volatile(
               "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
@@ -602,7 +609,86 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
               : "memory");
     }
   }
-  if (warp == 0 || (warp == 2 && pipes == 2)) {
+  if (p.first && (warp == 0 || (warp == 2 && pipes == 2))) {
+    // ===================== first block: the producer warp builds the A rows itself =====================
+    const int pipe = warp >> 1;
+    const int a0 = pipe * asl;
+    uint8_t* ring = smem_raw + smem_off + (size_t)w_tiles * p.w_tile_bytes + (size_t)a0 * p.a_slot_bytes;
+    for (uint32_t i = lane; i < (uint32_t)asl * p.a_slot_bytes / 16; i += 32)       // K padding stays zero for good
+      reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x + pipe * gridDim.x; t < p.total_items; t += pipes * gridDim.x) {
+      const RowsItem it = rows_decode(p, t);
+      const uint8_t* img = p.first_in + (long long)it.b * p.H * p.W;
+      const int xb = it.x0 + 4 * lane;                           // this lane's four pixels xb .. xb + 3
+      // One aligned 32-bit load per lane and row (pixels xb .. xb + 3; lane 0 / 31 also fetch the strip's two halo pixels),
+      // issued TWO row pairs ahead of their use: the warp handles the rows one after the other, so an exposed global-memory
+      // round trip per row would bound the whole kernel. The neighbours' edge pixels come by shuffle.
+      const bool vec = (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+      auto fetch = [&](int i, uint32_t& w, uint32_t& edge) {      // edge: x = it.x0 - 1 (lane 0) / it.x0 + 128 (lane 31)
+        const int y = it.y0 - 1 + i;
+        w = 0; edge = 0;
+        if (y < 0 || y >= p.H || i >= it.rows + 2) return;
+        const uint8_t* row = img + (long long)y * p.W;
+        if (vec) {
+          if (xb < p.W) w = __ldg(reinterpret_cast<const uint32_t*>(row + xb));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (xb + j < p.W) w |= (uint32_t)__ldg(row + xb + j) << (8 * j);
+        }
+        const int xe = lane == 0 ? it.x0 - 1 : it.x0 + 128;
+        if ((lane == 0 || lane == 31) && xe >= 0 && xe < p.W) edge = __ldg(row + xe);
+      };
+      // one input row into its ring slot: row r = pixel it.x0 + r = {in[x-1], in[x], in[x+1], 0...}
+      auto put = [&](uint32_t w, uint32_t edge, uint8_t* slot) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, w, 1), dn = __shfl_down_sync(0xffffffffu, w, 1);
+        float v[6];
+        v[0] = (float)(lane == 0 ? edge : (up >> 24));
+        v[1] = (float)(w & 0xffu); v[2] = (float)((w >> 8) & 0xffu); v[3] = (float)((w >> 16) & 0xffu); v[4] = (float)(w >> 24);
+        v[5] = (float)(lane == 31 ? edge : (dn & 0xffu));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 4 * lane + j;                             // 32B swizzle: 16-byte chunk ^ ((r >> 2) & 1)
+          uint8_t* row = slot + r * 32 + (((r >> 2) & 1) << 4);
+          if (ESZ == 2) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v[j], v[j + 1]), hi = __floats2bfloat162_rn(v[j + 2], 0.f);
+            *reinterpret_cast<uint2*>(row) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          } else {
+            *reinterpret_cast<float4*>(row) = make_float4(v[j], v[j + 1], v[j + 2], 0.f);
+          }
+        }
+      };
+      // rows in PAIRS: one proxy fence and one warp barrier per two rows
+      uint32_t wa[2], ea[2], wb[2], eb[2], wc[2], ec[2];
+      fetch(0, wa[0], ea[0]); fetch(1, wa[1], ea[1]);
+      fetch(2, wb[0], eb[0]); fetch(3, wb[1], eb[1]);
+      const int nrow = it.rows + 2;
+      for (int i = 0; i < nrow; i += 2) {
+        fetch(i + 4, wc[0], ec[0]); fetch(i + 5, wc[1], ec[1]);
+        const bool two = i + 1 < nrow;
+        const int s0 = as;
+        const uint32_t p0 = aph;
+        if (++as == asl) { as = 0; aph ^= 1; }
+        const int s1 = as;
+        const uint32_t p1 = aph;
+        if (two && ++as == asl) { as = 0; aph ^= 1; }
+        mbar_wait(&a_empty[a0 + s0], p0 ^ 1, 0xB00 + s0);
+        put(wa[0], ea[0], ring + (size_t)s0 * p.a_slot_bytes);
+        if (two) {
+          mbar_wait(&a_empty[a0 + s1], p1 ^ 1, 0xB00 + s1);
+          put(wa[1], ea[1], ring + (size_t)s1 * p.a_slot_bytes);
+        }
+        fence_proxy_async();                                      // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&a_full[a0 + s0]); if (two) mbar_arrive(&a_full[a0 + s1]); }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { wa[k] = wb[k]; ea[k] = eb[k]; wb[k] = wc[k]; eb[k] = ec[k]; }
+      }
+    }
+  } else if (warp == 0 || (warp == 2 && pipes == 2)) {
     // ================================== input row (A) producer ===================================
     const int pipe = warp >> 1;
     if (elect_one()) {
@@ -737,6 +823,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv_rows_kernel(const __grid
                         tc_mma_imm<ESZ, 1>(tmem_pipe, ad, wd + w_hi, n_hi);
                       }
                     }
+              }
+            } else if (p.first) {
+              if (!dbg_nomma && elect_one()) {                     // dx is the K dimension: one MMA per input row
+                if (wrap <= 0) {
+                  tc_mma_imm<ESZ, 1>(tcol, ad0, wd0, idesc3);
+                } else {
+                  tc_mma_imm<ESZ, 1>(tcol, ad0, wd0, wrap == 1 ? idesc2 : idesc1);
+                  tc_mma_imm<ESZ, 1>(tmem_pipe, ad0, wd0 + (uint32_t)(3 - wrap) * wrow_step, wrap == 1 ? idesc1 : idesc2);
+                }
               }
             } else if (!dbg_nomma && elect_one()) {
               if (wrap <= 0) {

@@ -384,7 +384,7 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
     p.strips = 1; p.rblocks = 1;
     p.total_items = p.tiles_x * p.tiles_y * a.B;
   }
-  p.kd = a.kd;
+  p.kd = a.kd; p.w_taps = a.kd * 3;
   p.ck = pl.ck; p.cin_chunks = nchunks > 0 ? nchunks : a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
   p.cin_chunk0 = chunk0; p.acc_mode = acc_mode; p.acc_scratch = reinterpret_cast<float*>(a.acc_scratch);
   p.cp = a.n_total;
@@ -412,6 +412,59 @@ static int launch_conv_rows(const ConvTcArgs& a, const RowsPlan& pl, cudaStream_
   const int grid = p.total_items < sm_count_cached() ? p.total_items : sm_count_cached();
   if (int rc = a.esz == 2 ? rows_dispatch_bf16(tmA, tmW, p, grid, pl.smem, stream)
                           : rows_dispatch_tf32(tmA, tmW, p, grid, pl.smem, stream))
+    return rc;
+  BIU_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// First block of the 2D nets on the row kernel's first mode (conv_rows.cuh): the producer warps build the 32-byte A rows
+// {in[x-1], in[x], in[x+1], 0...} from the uint8 tile, one MMA of N = 3 * Cout per input row.
+// ---------------------------------------------------------------------------------------------------------------------
+static bool first_rows_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BIU_FIRST_NO_ROWS"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+bool conv_first_rows_supported(const FirstRowsArgs& a) {
+  if (!first_rows_enabled() || rows_disabled() || halo_disabled()) return false;
+  if (a.wgt == nullptr || (a.n_total != 16 && a.n_total != 32) || (a.esz != 2 && a.esz != 4)) return false;
+  return a.W >= 128 && a.H >= 1 && a.out_ctot % 8 == 0 && a.out_coff % 8 == 0;
+}
+int launch_conv_first_rows(const FirstRowsArgs& a, cudaStream_t stream) {
+  BIU_REQUIRE(conv_first_rows_supported(a), "first block on the row kernel: unsupported configuration (n=%d W=%d)", a.n_total, a.W);
+  ConvRowsParams p;
+  memset(&p, 0, sizeof(p));
+  const int rb = 32, nfold = 3 * a.n_total;
+  p.W = a.W; p.H = a.H; p.D = 1; p.B = a.B;
+  p.strips = (a.W + 127) / 128;
+  const long long per_rb1 = (long long)p.strips * a.B;
+  p.RB = 16;
+  for (int rbk : {64, 32}) {
+    if (per_rb1 * ((a.H + rbk - 1) / rbk) >= 4LL * sm_count_cached()) { p.RB = rbk; break; }
+  }
+  p.rblocks = (a.H + p.RB - 1) / p.RB;
+  p.total_items = p.strips * p.rblocks * a.B;
+  p.kd = 1; p.slot_px = 128; p.first = 1; p.first_in = a.in; p.w_taps = 1;
+  p.ck = rb / a.esz; p.cin_chunks = 1; p.row_bytes = rb; p.cps = 1;
+  p.cp = a.n_total;
+  p.a_chunk_bytes = 128 * rb; p.a_slot_bytes = p.a_chunk_bytes;
+  p.w_tile_bytes = ((uint32_t)(nfold * rb) + 1023u) & ~1023u;
+  const int px_bytes = a.n_total * a.esz;
+  p.stage_px = px_bytes < 64 ? px_bytes : 64;
+  const int tail = (2 * a.n_total + kMaxHead * a.n_total) * 4 + 16 * 32 * p.stage_px + 64;
+  p.a_slots = kRowsMaxASlots;
+  p.t_slots = 512 / a.n_total;
+  p.pipes = (p.total_items >= 2 * sm_count_cached() && !rows_single_pipe()) ? 2 : 1;
+  const int smem = (int)p.w_tile_bytes + p.a_slots * (int)p.a_slot_bytes + tail + 1024;
+  p.mode = EPI_CONV; p.slope = a.slope; p.scale = a.scale; p.shift = a.shift;
+  p.out = a.out; p.out_ctot = a.out_ctot; p.out_coff = a.out_coff;
+  CUtensorMap tmW;
+  if (int rc = encode_wgt_map(&tmW, a.wgt, a.esz, p.ck, nfold, 1, p.ck, nfold)) return rc;
+  const int grid = p.total_items < sm_count_cached() ? p.total_items : sm_count_cached();
+  if (int rc = a.esz == 2 ? rows_dispatch_bf16(tmW, tmW, p, grid, smem, stream)        // no activation map: the rows are
+                          : rows_dispatch_tf32(tmW, tmW, p, grid, smem, stream))       // built in the kernel
     return rc;
   BIU_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -105,6 +105,23 @@ struct FirstConvArgs {          // planar u8 / f32 input with few channels -> NH
 };
 int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream);
 
+// First block of the 2D nets on the row kernel (conv_rows.cuh, first mode): uint8 tile in, NHWC features out; the three dx
+// taps are the GEMM's K, the dy taps are folded into N. bf16 / tf32 modes only (weights rounded like every other block's).
+struct FirstRowsArgs {
+  int esz;                      // 2 = bf16, 4 = tf32 storage
+  const uint8_t* in;            // [B][H][W] uint8 (one channel)
+  int W, H, B;
+  const void* wgt;              // [3 * n_total ((2 - dy), co)][16 bf16 | 8 tf32: (dx = 0..2, zeros)]
+  int n_total;                  // padded output channels: 16 or 32
+  float slope;
+  const float* scale;           // BatchNorm scale / 255 (the input rows hold the raw integers)
+  const float* shift;
+  void* out;
+  int out_ctot, out_coff;
+};
+bool conv_first_rows_supported(const FirstRowsArgs& a);
+int launch_conv_first_rows(const FirstRowsArgs& a, cudaStream_t stream);
+
 struct PoolArgs {
   int esz;
   const void* in;

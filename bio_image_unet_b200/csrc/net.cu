@@ -454,6 +454,32 @@ int net_finalize(Net* n) {
       if (upload(n, wd, &L.w_direct)) return -1;
       if (upload(n, scale, &L.scale)) return -1;
       if (upload(n, shift, &L.shift)) return -1;
+      // first block of a 2D net (one input channel): packing for the row kernel's first mode - the dx taps are the K
+      // dimension (zero padded to 16 bf16 / 8 tf32 elements), the dy taps are folded into N in the order dy = 2, 1, 0
+      if (n->precision != PREC_FP32 && L.cin_log == 1 && L.kd == 1 && L.kw == 3 && L.kh == 3 &&
+          (L.cout_pad == 16 || L.cout_pad == 32)) {
+        const int kel = 32 / n->esz, nfold = 3 * L.cout_pad;
+        std::vector<float> wf((size_t)nfold * kel, 0.f);
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx)
+            for (int co = 0; co < L.cout; ++co)
+              wf[((size_t)(2 - dy) * L.cout_pad + co) * kel + dx] = w->data[(size_t)co * taps + dy * 3 + dx];
+        if (n->esz == 2) {
+          std::vector<uint16_t> wp(wf.size());
+          for (size_t i = 0; i < wf.size(); ++i) wp[i] = host_bf16(wf[i]);
+          uint16_t* d = nullptr;
+          if (upload(n, wp, &d)) return -1;
+          L.w_first = d;
+        } else {
+          for (auto& v : wf) v = host_round_tf32(v);
+          float* d = nullptr;
+          if (upload(n, wf, &d)) return -1;
+          L.w_first = d;
+        }
+        std::vector<float> s255(L.cout_pad, 0.f);
+        for (int co = 0; co < L.cout; ++co) s255[co] = scale[co] / 255.0f;
+        if (upload(n, s255, &L.scale_first)) return -1;
+      }
       if (n->precision != PREC_FP32 && L.cin_phys % 16 == 0) {
         const size_t cnt = (size_t)taps * L.cout_pad * L.cin_phys;
         if (n->esz == 2) {
@@ -948,6 +974,17 @@ int net_forward(Net* n, const void* in, int in_kind, const void* in2, float* out
         a.wgt = L.w_direct; a.cout = L.cout_pad; a.cout_real = L.cout; a.slope = L.slope; a.scale = L.scale; a.shift = L.shift;
         a.esz = n->esz; a.out = shared > 0 ? ws + db->offset : dst_ptr(d, h, w); a.out_ctot = db->ctot; a.out_coff = o.dst_coff;
         a.cout_pad = L.cout_pad; a.round_tf32 = round_tf32;
+        if (tc_allowed && in_kind == 0 && n->dims == 2 && a.D == 1 && L.w_first != nullptr) {
+          FirstRowsArgs fr;
+          memset(&fr, 0, sizeof(fr));
+          fr.esz = n->esz; fr.in = reinterpret_cast<const uint8_t*>(a.in); fr.W = a.W; fr.H = a.H; fr.B = a.B;
+          fr.wgt = L.w_first; fr.n_total = L.cout_pad; fr.slope = L.slope; fr.scale = L.scale_first; fr.shift = L.shift;
+          fr.out = a.out; fr.out_ctot = a.out_ctot; fr.out_coff = a.out_coff;
+          if (conv_first_rows_supported(fr)) {
+            if (int rc = launch_conv_first_rows(fr, stream)) return rc;
+            break;
+          }
+        }
         if (int rc = launch_first_conv(a, stream)) return rc;
         break;
       }

@@ -40,6 +40,8 @@ struct ConvLayer {     // one Conv+BN+LeakyReLU block, a transposed conv, or the
   void* w_fold = nullptr;    // narrow 3x3 blocks: [dz*3+dx][(2-dy)*cout_pad + co][cin_phys] for the row-streaming kernel
   void* w_fold_z = nullptr;  // narrow 3x3x3 blocks: [dy*3+dx][(2-dz)*cout_pad + co][cin_phys] for its plane mode (dz folded)
   float* w_direct = nullptr; // fp32 [tap or q][cin_phys][cout_pad]
+  void* w_first = nullptr;   // first block of the 2D nets (1 input channel): [(2-dy)*cout_pad + co][dx, zeros] bf16 x16 / tf32 x8
+  float* scale_first = nullptr;   // scale / 255 (conv_rows.cuh first mode works on the raw uint8 values)
   float* scale = nullptr;    // [n_total]
   float* shift = nullptr;
 };
