@@ -311,6 +311,8 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     const long long out_row_bytes = (plane ? (long long)p.H * p.W : (long long)p.W) * p.out_ctot * ESZ;   // next output row / plane
     const int out_px_bytes = p.out_ctot * ESZ;
     const long long out_q8_bytes = (plane ? (long long)p.W : 8LL) * out_px_bytes;      // 8 quarter-pixels further
+    const int st_lane_off = (int)((rd_px >> 3) * out_q8_bytes) + (rd_px & 7) * out_px_bytes + rd_piece * 16;
+    const int rd_lane_off = rd_px * SB + ((rd_piece ^ (SV == 4 ? ((rd_px >> 1) & 3) : ((rd_px >> 2) & 1))) << 4);
     // K split: this lane's pixel in the fp32 partial-sum scratch [pixel][CP] (pixel index of output row / plane o = + o * pix_per_o)
     const long long lane_pix0 = plane ? (plane_row0 + (lane >> 3)) * p.W + px0 + (lane & 7) : plane_row0 * p.W + px;
     const long long pix_per_o = plane ? (long long)p.H * p.W : (long long)p.W;
@@ -352,20 +354,24 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
     }
     const int vrows = it.rows + 4;               // virtual output rows: 2 dummies, rows real ones, 2 dummies
 
+    const unsigned long long slope2 = pack_f32x2(p.slope, p.slope);
     // BatchNorm + LeakyReLU of one drained row, packed in the storage format (bf16 pairs / tf32-rounded floats)
     auto activate = [&](const uint32_t (&e)[HC], uint32_t (&w)[NW], int hh) {     // channels hh * HC .. hh * HC + HC - 1
       constexpr int NWH = HC * ESZ / 4;
 #pragma unroll
       for (int i4 = 0; i4 < HC / 4; ++i4) {
-        const float4 sc = reinterpret_cast<const float4*>(s_scale + hh * HC)[i4];
-        const float4 sh = reinterpret_cast<const float4*>(s_shift + hh * HC)[i4];
-        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-        float a[4];
+        // packed pairs (FFMA2 / FMUL2): two IEEE operations per issue slot, bit-identical to fmaf / a * slope - the
+        // epilogue warps are issue-bound at full resolution
+        const ulonglong2 sc = reinterpret_cast<const ulonglong2*>(s_scale + hh * HC)[i4];
+        const ulonglong2 sh = reinterpret_cast<const ulonglong2*>(s_shift + hh * HC)[i4];
+        const unsigned long long t0 = fma_f32x2(pack_f32x2(__uint_as_float(e[4 * i4]), __uint_as_float(e[4 * i4 + 1])), sc.x, sh.x);
+        const unsigned long long t1 = fma_f32x2(pack_f32x2(__uint_as_float(e[4 * i4 + 2]), __uint_as_float(e[4 * i4 + 3])), sc.y, sh.y);
+        const unsigned long long u0 = mul_f32x2(t0, slope2), u1 = mul_f32x2(t1, slope2);
+        float a[4], u[4];
+        unpack_f32x2(t0, a[0], a[1]); unpack_f32x2(t1, a[2], a[3]);
+        unpack_f32x2(u0, u[0], u[1]); unpack_f32x2(u1, u[2], u[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          a[k] = fmaf(__uint_as_float(e[4 * i4 + k]), scv[k], shv[k]);
-          a[k] = fmaxf(a[k], a[k] * p.slope);      // LeakyReLU for 0 <= slope <= 1
-        }
+        for (int k = 0; k < 4; ++k) a[k] = fmaxf(a[k], u[k]);        // LeakyReLU for 0 <= slope <= 1
         if (ESZ == 2) {
           __nv_bfloat162 b0 = __floats2bfloat162_rn(a[0], a[1]), b1 = __floats2bfloat162_rn(a[2], a[3]);
           w[(hh * NWH + 2 * i4) % NW] = *reinterpret_cast<uint32_t*>(&b0);
@@ -386,13 +392,14 @@ __device__ __forceinline__ void rows_epilogue(const ConvRowsParams& p, uint32_t 
           *reinterpret_cast<uint4*>(tile + lane * SB + ((j ^ wr_swz) << 4)) =
               make_uint4(w[4 * (h * SV + j)], w[4 * (h * SV + j) + 1], w[4 * (h * SV + j) + 2], w[4 * (h * SV + j) + 3]);
         __syncwarp();
-        char* orow = out_q + o * out_row_bytes + (h * SV + rd_piece) * 16;
+        // pixel i * PPI + rd_px: PPI is 8 or 16, so consecutive i are whole quarter-rows apart and the swizzle term and
+        // the position inside the quarter-row depend on the lane only - one pointer per row, constant steps per store
+        char* optr = out_q + o * out_row_bytes + h * SV * 16 + st_lane_off;
+        const uint8_t* tptr = tile + rd_lane_off;
 #pragma unroll
         for (int i = 0; i < SV; ++i) {
-          const int pxi = i * PPI + rd_px;
-          const int swz = SV == 4 ? ((pxi >> 1) & 3) : ((pxi >> 2) & 1);
-          const uint4 v4 = *reinterpret_cast<const uint4*>(tile + pxi * SB + ((rd_piece ^ swz) << 4));
-          if (pix_ok(pxi)) *reinterpret_cast<uint4*>(orow + (pxi >> 3) * out_q8_bytes + (long long)(pxi & 7) * out_px_bytes) = v4;
+          const uint4 v4 = *reinterpret_cast<const uint4*>(tptr + i * (PPI * SB));
+          if (pix_ok(i * PPI + rd_px)) *reinterpret_cast<uint4*>(optr + i * (PPI / 8) * out_q8_bytes) = v4;
         }
       }
     };

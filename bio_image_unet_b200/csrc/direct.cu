@@ -175,26 +175,6 @@ __global__ void __launch_bounds__(256) first_conv1_kernel(FirstConvArgs a) {
   }
 }
 
-// packed fp32 pairs (sm_100: FFMA2 / FMUL2)
-__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // 3D, single input channel. A block owns a column of ZC planes of an (8 rows x 128 voxels) tile and slides along z:
 // four input planes (10 rows x 130 voxels with the halo, already float32(u8)/255 - exact division,
 // unet3d/predict.py:161) rotate through shared memory, the plane needed two steps ahead is fetched from global
