@@ -517,7 +517,8 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
     first_conv_kernel<TIN, TOUT><<<(int)blocks, 256, smem, stream>>>(a);                                       \
   } while (0)
-  const bool fast = a.cin == 1 && a.out_ctot % 8 == 0 && a.out_coff % 8 == 0 && smem <= 48 * 1024;
+  const bool fast = a.cin == 1 && a.out_ctot % 8 == 0 && a.out_coff % 8 == 0 && smem <= 48 * 1024 &&
+                    (a.kd == 1 || first_conv1_3d_smem(a.cout_pad) <= 100 * 1024);   // 3D: two blocks of it per SM
   const int groups = a.cout_pad / 8;
   if (fast && a.kd == 1 && a.D == 1 && (groups == 1 || groups == 2 || groups == 4 || groups == 8)) {
     if (a.in_kind == 0 && a.esz == 2) launch_first_conv1_2d<uint8_t, __nv_bfloat16>(a, stream);
@@ -537,13 +538,14 @@ int launch_first_conv(const FirstConvArgs& a, cudaStream_t stream) {
   do {                                                                                                   \
     if (a.kd == 1) first_conv1_kernel<TIN, TOUT, 9><<<(int)fb, 256, smem, stream>>>(a);                  \
     else {                                                                                               \
-      static bool attr_set = false;                                                                     \
-      if (!attr_set) {                                                                                   \
+      static int attr_set = 0;                                                                          \
+      const int sm3 = (int)first_conv1_3d_smem(a.cout_pad);                                              \
+      if (sm3 > attr_set) {                                                                              \
         BIU_CHECK_CUDA(cudaFuncSetAttribute(first_conv1_3d_kernel<TIN, TOUT>,                            \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));    \
-        attr_set = true;                                                                                 \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, sm3));          \
+        attr_set = sm3;                                                                                  \
       }                                                                                                  \
-      first_conv1_3d_kernel<TIN, TOUT><<<(int)rb3, 256, first_conv1_3d_smem(a.cout_pad), stream>>>(a);    \
+      first_conv1_3d_kernel<TIN, TOUT><<<(int)rb3, 256, sm3, stream>>>(a);                               \
     }                                                                                                    \
   } while (0)
     if (a.in_kind == 0 && a.esz == 2) BIU_FC1(uint8_t, __nv_bfloat16);
