@@ -34,6 +34,7 @@ struct ConvHaloParams {
   int mt;                          // MMA tiles (16x8 pixels) per work item along x
   int tiles_x, tiles_y;            // macro tiles per image plane
   int n_blocks;                    // output-channel blocks
+  int nblk_inner;                  // work-item order: the output-channel block is the FASTEST index (see halo_decode)
   int total_tiles;                 // tiles_x * tiles_y * D * B * n_blocks
   int kd;                          // z taps: 1 (2D) or 3
   int halo;                        // 1: 3x3(x3) convolution, 0: single tap (transposed convolution as GEMM)
@@ -82,11 +83,17 @@ struct HaloTile { int x0, y0, z0, b0, n0; };
 
 __device__ __forceinline__ HaloTile halo_decode(const ConvHaloParams& p, int t) {
   HaloTile r;
+  // Blocks whose weights stay resident walk all tiles of one output-channel block first. Where the weights are streamed
+  // anyway (transposed convolutions with N = 4 * Cout in several blocks) the block index is the fastest one instead:
+  // neighbouring CTAs work on the SAME pixels at the same time, so the input tile comes from DRAM once and from L2 for
+  // the other blocks (up1 of Unet(32): 0.84 -> 0.2 GB read per 200 tiles).
+  int nb = 0;
+  if (p.nblk_inner) { nb = t % p.n_blocks; t /= p.n_blocks; }
   const int tx = t % p.tiles_x; t /= p.tiles_x;
   const int ty = t % p.tiles_y; t /= p.tiles_y;
   r.z0 = t % p.D; t /= p.D;
   r.b0 = t % p.B; t /= p.B;
-  r.n0 = t * p.n_blk;
+  r.n0 = (p.nblk_inner ? nb : t) * p.n_blk;
   r.x0 = tx * 8 * p.mt;
   r.y0 = ty * 16;
   return r;

@@ -250,6 +250,7 @@ static int launch_conv_halo(const ConvTcArgs& a, int n_blk, const HaloPlan& pl, 
   p.tiles_y = ceil_div(a.H, 16);
   p.n_blocks = a.n_total / n_blk;
   p.total_tiles = p.tiles_x * p.tiles_y * a.D * a.B * p.n_blocks;
+  p.nblk_inner = (p.n_blocks > 1 && !pl.b_resident && !pl.cta2) ? 1 : 0;
   p.kd = a.kd;
   p.halo = a.kw == 3 ? 1 : 0;
   p.ck = pl.ck; p.cin_chunks = a.cin / pl.ck; p.row_bytes = pl.ck * a.esz;
