@@ -177,8 +177,18 @@ def test_state_dict_layouts_match_reference():
         model.load_state_dict(ref)      # strict
 
 
+def _random_zslab_cases(n=40, seed=7):
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        d = int(rng.choice([4, 8, 16]))
+        z = int(rng.integers(d, 9 * d))
+        cases.append((z, d, int(rng.integers(0, 4)), int(rng.integers(1, 9))))
+    return cases
+
+
 @pytest.mark.parametrize('z,d,add,world', [(40, 8, 1, 2), (40, 8, 1, 3), (64, 16, 0, 4), (8, 8, 1, 2), (50, 16, 2, 8),
-                                           (6, 8, 0, 2), (33, 8, 1, 5)])
+                                           (6, 8, 0, 2), (33, 8, 1, 5)] + _random_zslab_cases())
 def test_zslab_plan_sharded_stitch_equals_full_stitch(z, d, add, world):
     """3D multi-GPU plan (tiling.zslab_plan): the planes the ranks own partition the volume, rows only travel to lower
     ranks, and stitching every rank's own planes from its rows + the borrowed ones (local patch numbering) gives
